@@ -1,0 +1,305 @@
+/*
+ * xrt.h -- C ABI of the B200 photon-raytrace path (libxrt.so).
+ *
+ * The reference (XICSRT 0.8.13) is pure Python and has no FFI of its own, so
+ * these entry points are cut at the one place its driver hands the rays to the
+ * numerics: the body of `_raytrace_iter` (xicsrt/xicsrt_raytrace.py:178-226),
+ * i.e. `sources.generate_rays()` (:192) followed by `optics.trace()` (:194),
+ * plus the per-element bookkeeping `Dispatcher.trace` does around each optic
+ * (xicsrt/objects/_Dispatcher.py:166-196: num_out, history copy, make_image).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - plain C structs, pointers and sizes; no C++ or torch types;
+ *   - every function returns 0 on success, a negative XRT_E* code on failure;
+ *     xrt_last_error() returns the message for the calling thread's last error;
+ *   - "dev" pointers are CUDA device pointers owned by the caller (the Python
+ *     side allocates them as torch tensors); the library never frees them;
+ *   - "host" pointers inside the *Desc structs are only read during
+ *     xrt_scene_create, which uploads what it needs;
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (void*, 0 =
+ *     legacy default stream) and is asynchronous with respect to the host;
+ *   - all ray quantities are IEEE binary64, as in the reference
+ *     (xicsrt/objects/_RayArray.py:82-86).
+ */
+#ifndef XRT_H
+#define XRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRT_VERSION 1
+#define XRT_MAX_OPTICS 16
+#define XRT_MAX_SIGHTLINES 4
+
+/* error codes */
+#define XRT_OK 0
+#define XRT_EINVAL (-1)      /* bad argument / descriptor                      */
+#define XRT_EUNSUPPORTED (-2)/* class / option the kernels do not implement    */
+#define XRT_ECUDA (-3)       /* a CUDA runtime call failed (see last error)    */
+#define XRT_ENOMEM (-4)
+
+/* ---- enumerations ------------------------------------------------------ */
+
+/* surface shapes: xicsrt/optics/_Shape{Plane,Sphere,Cylinder,Torus,Mesh}.py */
+enum { XRT_SHAPE_PLANE = 0, XRT_SHAPE_SPHERE = 1, XRT_SHAPE_CYLINDER = 2,
+       XRT_SHAPE_TORUS = 3, XRT_SHAPE_MESH = 4 };
+
+/* interactions: xicsrt/optics/_Interact{None,Mirror,Crystal,MosaicCrystal}.py */
+enum { XRT_INTERACT_NONE = 0, XRT_INTERACT_MIRROR = 1, XRT_INTERACT_CRYSTAL = 2,
+       XRT_INTERACT_MOSAIC = 3 };
+
+/* rocking curves: xicsrt/optics/_InteractCrystal.py:139-184 */
+enum { XRT_ROCK_STEP = 0, XRT_ROCK_GAUSS = 1, XRT_ROCK_TABLE = 2 };
+
+/* optic flags */
+enum { XRT_F_TRACE_LOCAL = 1 << 0, XRT_F_CHECK_SIZE = 1 << 1,
+       XRT_F_CHECK_APERTURE = 1 << 2, XRT_F_CHECK_BRAGG = 1 << 3,
+       XRT_F_CONVEX = 1 << 4, XRT_F_HAS_XSIZE = 1 << 5, XRT_F_HAS_YSIZE = 1 << 6,
+       XRT_F_HAS_ZSIZE = 1 << 7, XRT_F_IMAGE = 1 << 8,
+       XRT_F_MOSAIC_CUTOFF = 1 << 9, XRT_F_MESH_REFINE = 1 << 10,
+       XRT_F_MESH_INTERP = 1 << 11 };
+
+/* aperture shapes and logic: xicsrt/tools/xicsrt_aperture.py:13-204 */
+enum { XRT_AP_NONE = 0, XRT_AP_CIRCLE = 1, XRT_AP_SQUARE = 2, XRT_AP_RECTANGLE = 3,
+       XRT_AP_ELLIPSE = 4, XRT_AP_TRIANGLE = 5 };
+enum { XRT_LOGIC_AND = 0, XRT_LOGIC_NOT = 1, XRT_LOGIC_OR = 2, XRT_LOGIC_NAND = 3,
+       XRT_LOGIC_NOR = 4, XRT_LOGIC_XOR = 5, XRT_LOGIC_XNOR = 6 };
+
+/* sources: xicsrt/sources/_XicsrtSource{Generic,Directed,Focused}.py, _XicsrtPlasma*.py */
+enum { XRT_SRC_FIXED_AXIS = 0,   /* Generic (zaxis) and Directed (direction)   */
+       XRT_SRC_FOCUSED = 1,      /* cone axis = normalize(target - origin)      */
+       XRT_SRC_BUNDLES = 2 };    /* plasma: table of focused voxel sources      */
+enum { XRT_SPATIAL_UNIFORM = 0, XRT_SPATIAL_GAUSSIAN = 1 };
+/* cone distributions: xicsrt/tools/xicsrt_spread.py */
+enum { XRT_CONE_ISOTROPIC = 0, XRT_CONE_ISOTROPIC_XY = 1, XRT_CONE_FLAT = 2,
+       XRT_CONE_FLAT_XY = 3 };
+/* wavelength models: xicsrt/sources/_XicsrtSourceGeneric.py:295-367 */
+enum { XRT_WAVE_CONST = 0, XRT_WAVE_UNIFORM = 1, XRT_WAVE_NORMAL = 2, XRT_WAVE_TABLE = 3 };
+
+/* ---- descriptors ------------------------------------------------------- */
+
+typedef struct XrtAperture {
+    int32_t shape;          /* XRT_AP_*    */
+    int32_t logic;          /* XRT_LOGIC_* */
+    double origin[2];
+    double size[2];         /* circle: [r, -]; square: [w, -]; rectangle/ellipse: [sx, sy] */
+    double vert[6];         /* triangle: x0 y0 x1 y1 x2 y2 (origin already added)          */
+} XrtAperture;
+
+/* triangle mesh tables of one ShapeMesh optic (xicsrt/optics/_ShapeMesh.py:198-287) */
+typedef struct XrtMesh {
+    int32_t n_points, n_faces;
+    const double *points;        /* [n_points][3]                                        */
+    const int32_t *faces;        /* [n_faces][3]                                         */
+    const double *face_normals;  /* [n_faces][3]                                         */
+    int32_t n_coarse_points, n_coarse_faces;   /* 0 when there is no coarse mesh         */
+    const double *coarse_points;
+    const int32_t *coarse_faces;
+    const int32_t *point_faces;  /* [8][n_points] faces around each fine point           */
+    const uint8_t *point_faces_mask; /* [8][n_points]                                    */
+    /* Clough-Tocher interpolation of z and the normal over the xy Delaunay triangulation */
+    int32_t n_tri;               /* 0 when mesh_interpolate is off                       */
+    const int32_t *tri;          /* [n_tri][3] vertex ids                                */
+    const int32_t *tri_neighbors;/* [n_tri][3], -1 on the hull                           */
+    const double *tri_xy;        /* [n_points][2] (= points[:, 0:2])                     */
+    const double *values;        /* [n_points][4]  z, nx, ny, nz                         */
+    const double *grads;         /* [n_points][4][2] scipy's estimated vertex gradients  */
+    /* uniform xy lookup grid over the triangulation (built by the host side)            */
+    int32_t grid_nx, grid_ny;
+    double grid_x0, grid_y0, grid_inv_dx, grid_inv_dy;
+    const int32_t *grid_start;   /* [grid_nx*grid_ny + 1]                                */
+    const int32_t *grid_items;   /* triangle ids                                         */
+    /* kd-tree replacement: nearest fine vertex is found through the same grid           */
+    const int32_t *vgrid_start;  /* [grid_nx*grid_ny + 1] vertices per cell              */
+    const int32_t *vgrid_items;
+} XrtMesh;
+
+typedef struct XrtOpticDesc {
+    int32_t shape;           /* XRT_SHAPE_*    */
+    int32_t interact;        /* XRT_INTERACT_* */
+    int32_t rocking_type;    /* XRT_ROCK_*     */
+    uint32_t flags;          /* XRT_F_*        */
+    double origin[3];
+    double orient[9];        /* rows: xaxis, yaxis = z cross x, zaxis (_GeometryObject.py:88-94) */
+    double half_size[3];     /* xsize/2, ysize/2, zsize/2 (used when the HAS_* flag is set)      */
+    double center[3];        /* sphere / cylinder / torus centre (global)                        */
+    double radius;           /* sphere / cylinder                                                */
+    double torus_major, torus_minor;   /* geometric radii (_ShapeTorus.py:70-87)                 */
+    int32_t root_idx;        /* quartic solver slot (_ShapeTorus.py:72-85)                       */
+    int32_t mosaic_depth;
+    double two_d;            /* 2 * crystal_spacing                                              */
+    double reflectivity;
+    double rocking_fwhm;
+    double rock_two_sigma2;  /* gaussian: 2 sigma^2 with sigma = fwhm / (2 sqrt(2 ln 2))         */
+    double rocking_mix;
+    double mosaic_spread;    /* fwhm of crystallite normals [rad]                                */
+    double mosaic_sin_sigma; /* sin(sigma) of the crystallite (x, y) offsets, sigma = hwhm/sqrt(2 ln 2) */
+    double mosaic_angle_cut; /* angle cutoff derived from mosaic_cutoff (when XRT_F_MOSAIC_CUTOFF) */
+    int32_t n_aperture;
+    int32_t n_rock;
+    const XrtAperture *apertures;     /* [n_aperture]                                            */
+    const double *rock_dtheta;        /* [n_rock] radians, ascending                             */
+    const double *rock_s;             /* [n_rock] sigma reflectivity                             */
+    const double *rock_p;             /* [n_rock] pi reflectivity                                */
+    const XrtMesh *mesh;              /* when shape == XRT_SHAPE_MESH                            */
+    int32_t npix[2];         /* pixel_xsize, pixel_ysize (when XRT_F_IMAGE)                      */
+    double pixel_size;
+    uint64_t image_offset;   /* element offset of this optic's image in XrtOutputs.images        */
+} XrtOpticDesc;
+
+typedef struct XrtSightline {    /* xicsrt/filters/_XicsrtBundleFilterSightline.py:31-56 */
+    double origin[3];
+    double axis[3];
+    double radius;
+} XrtSightline;
+
+/* one plasma bundle = one focused voxel source (_XicsrtPlasmaGeneric.py:286-345) */
+typedef struct XrtBundle {
+    double origin[3];
+    double cos_spread;       /* cos(spread) of the isotropic cone                                */
+    double wave_sigma;       /* Doppler sigma of this bundle [A] (XRT_WAVE_NORMAL)               */
+    double velocity_c[3];    /* velocity / c                                                     */
+} XrtBundle;
+
+typedef struct XrtSourceDesc {
+    int32_t kind;            /* XRT_SRC_*     */
+    int32_t spatial;         /* XRT_SPATIAL_* */
+    int32_t cone;            /* XRT_CONE_*    */
+    int32_t wave;            /* XRT_WAVE_*    */
+    double origin[3];
+    double orient[9];
+    double extent[3];        /* uniform: full box sizes; gaussian: sigmas (fwhm / 2.3548)        */
+    double axis_basis[9];    /* FIXED_AXIS: rows o_2, o_1, axis of the cone basis, precomputed
+                                on the host exactly as _XicsrtSourceGeneric.py:282-288 does      */
+    double target[3];        /* FOCUSED / BUNDLES                                                */
+    double cone_par[4];      /* isotropic: [cos(spread)]; flat: [tan(spread)];
+                                flat_xy: tan of [xmin,xmax,ymin,ymax];
+                                isotropic_xy: sin of [xmin,xmax,ymin,ymax]                       */
+    double cone_cos_max;     /* isotropic_xy: cos of the enclosing circular cone                 */
+    double wave_par[4];      /* const: [lam]; uniform: [lo, hi]; normal: [lam0, sigma];
+                                table: [lam0, cdf_min, cdf_max]                                  */
+    double velocity_c[3];    /* velocity / c (all zero = no Doppler shift)                       */
+    int32_t n_table;
+    int32_t n_sightlines;
+    const double *table_cdf; /* [n_table] ascending                                              */
+    const double *table_x;   /* [n_table]                                                        */
+    XrtSightline sightlines[XRT_MAX_SIGHTLINES];
+    /* plasma */
+    uint64_t n_bundles;
+    const XrtBundle *bundles;        /* [n_bundles]                                              */
+    const uint64_t *bundle_end;      /* [n_bundles] inclusive prefix sum of rays per bundle      */
+    double voxel_size;
+} XrtSourceDesc;
+
+typedef struct XrtSceneDesc {
+    int32_t version;         /* XRT_VERSION */
+    int32_t n_optics;
+    XrtSourceDesc source;
+    XrtOpticDesc optics[XRT_MAX_OPTICS];
+} XrtSceneDesc;
+
+typedef struct XrtScene XrtScene;   /* opaque; one per device context */
+
+/* ---- per-call buffers (device pointers, caller-owned) ------------------ */
+
+typedef struct XrtOutputs {
+    uint64_t *counts;        /* [1 + n_optics] += rays alive after the source / each optic
+                                (meta['num_out'], _Dispatcher.py:157-159,182-184)                */
+    uint64_t *images;        /* concatenated per-optic pixel counts, [npix_x][npix_y] row-major,
+                                += 1 per hit (_TraceObject.py:234-293); may be NULL              */
+    uint64_t *found_ids;     /* optional: global ids of rays alive after the last optic          */
+    uint64_t *found_count;   /* [1] number of found rays (may exceed found_capacity)             */
+    uint64_t found_capacity;
+    uint64_t *lost_ids;      /* optional: sample of lost rays (key < lost_threshold)             */
+    uint64_t *lost_keys;     /* their 64-bit sampling keys (sort ascending, keep the first m)    */
+    uint64_t *lost_count;    /* [1]                                                              */
+    uint64_t lost_capacity;
+    uint64_t lost_threshold; /* keep a lost ray when its key < threshold (2^64-1 = keep all)     */
+} XrtOutputs;
+
+/* per-element history, struct-of-arrays: 7 double planes + 1 byte plane per element
+   (_Dispatcher.py:161-162,186-187 deepcopy of the ray dict after each element) */
+typedef struct XrtHistory {
+    double *rays;            /* [1 + n_optics][7][capacity]: ox oy oz dx dy dz wavelength        */
+    uint8_t *mask;           /* [1 + n_optics][capacity]                                         */
+    uint64_t capacity;
+} XrtHistory;
+
+typedef struct XrtRaysIn {   /* array-of-rows input, as the reference holds rays                */
+    const double *origin;    /* [n][3] */
+    const double *direction; /* [n][3] */
+    const double *wavelength;/* [n]    */
+    const uint8_t *mask;     /* [n]    */
+} XrtRaysIn;
+
+/* injected random draws, one entry per optic (NULL where the optic draws nothing).
+   u[k]:  [depth_k][n]    U[0,1) for the rocking-curve test (_InteractCrystal.py:189)
+   xy[k]: [depth_k][2][n] mosaic (x, y) offsets (xicsrt_spread.py:332)                           */
+typedef struct XrtInject {
+    const double *u[XRT_MAX_OPTICS];
+    const double *xy[XRT_MAX_OPTICS];
+} XrtInject;
+
+/* injected raw draws for source generation (parity of _XicsrtSourceGeneric.py:198-393) */
+typedef struct XrtSourceInject {
+    const double *origin;    /* [3][n]: U[0,1) (uniform box) or final offsets (gaussian)        */
+    const double *cone;      /* [2][n]: U[0,1)                                                   */
+    const double *wave;      /* [n]: U[0,1) (uniform / table) or standard normal (normal)        */
+} XrtSourceInject;
+
+/* ---- entry points ------------------------------------------------------ */
+
+int xrt_version(void);
+const char *xrt_last_error(void);
+
+/* Upload a scene (source + optic train + tables) to the current CUDA device. */
+int xrt_scene_create(const XrtSceneDesc *desc, XrtScene **scene);
+int xrt_scene_destroy(XrtScene *scene);
+
+/* Fused generate -> trace -> bin for rays [ray_begin, ray_begin + ray_count) of random
+   stream (seed, stream_id).  Replaces one `_raytrace_iter` call with history off.
+   Random numbers are Philox4x32-10 keyed by (seed, stream_id) and counted by global ray
+   id, so any partition of the id range over calls / GPUs gives identical results. */
+int xrt_trace(XrtScene *scene, uint64_t seed, uint64_t stream_id, uint64_t ray_begin,
+              uint64_t ray_count, const XrtOutputs *out, void *stream);
+
+/* Re-trace the listed global ray ids (device array) and store every element's ray state
+   into `hist` slot i for ids[i].  With xrt_trace's found/lost lists this yields the
+   reference's found/lost histories (xicsrt_raytrace.py:229-278) without an N-sized copy.
+   ids == NULL means ids[i] = ray_begin + i. */
+int xrt_trace_history(XrtScene *scene, uint64_t seed, uint64_t stream_id,
+                      const uint64_t *ids, uint64_t ray_begin, uint64_t n,
+                      const XrtHistory *hist, void *stream);
+
+/* Parity entry: trace caller-supplied rays with caller-supplied random draws through the
+   optic train; fills counts / images (out, optional) and history (hist, optional).
+   Element 0 of the history is the input ray set. */
+int xrt_trace_injected(XrtScene *scene, const XrtRaysIn *rays, const XrtInject *draws,
+                       uint64_t n, const XrtOutputs *out, const XrtHistory *hist, void *stream);
+
+/* Parity entry for the source: generate n rays from caller-supplied raw draws into
+   history element 0 of `hist` (box sources; fixed draw count distributions). */
+int xrt_source_injected(XrtScene *scene, const XrtSourceInject *draws, uint64_t n,
+                        const XrtHistory *hist, void *stream);
+
+/* Generate rays [ray_begin, +n) of the Philox stream into history element 0 only. */
+int xrt_source_generate(XrtScene *scene, uint64_t seed, uint64_t stream_id,
+                        uint64_t ray_begin, uint64_t n, const XrtHistory *hist, void *stream);
+
+/* FP64 FMA-chain microbenchmark: runs `iters` dependent-chain DFMA steps per thread on a
+   full grid and reports the number of FP64 flops issued; the caller times it with CUDA
+   events to obtain the roofline denominator.  out_dev: [1] double (sink). */
+int xrt_fp64_burn(uint64_t iters, double *out_dev, double *flops, void *stream);
+
+/* Launch geometry used by xrt_trace (for reporting). */
+int xrt_launch_info(XrtScene *scene, int32_t *grid, int32_t *block, int32_t *regs,
+                    int32_t *blocks_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRT_H */

@@ -1,0 +1,89 @@
+# -*- coding: utf-8 -*-
+"""
+GPU parity tests (run with ``-m gpu`` on the B200 box).  Everything goes through
+the C ABI of libxrt.so.
+
+Bar (BASELINE.json north_star): with the oracle's own ray bundle and uniform /
+normal draws injected, found/lost masks are bit-equal, per-ray fp64 positions,
+directions and wavelengths agree within 1e-9 relative, per-element counts and
+pixel images are identical.  RNG-driven runs are compared statistically in
+test_gpu_statistics.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import scenes
+
+import harness
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch
+
+
+ANALYTIC = [n for n in scenes.ANALYTIC if n != 'two_iter_two_runs']
+
+
+@pytest.mark.parametrize('name', ANALYTIC)
+def test_injected_trace_matches_oracle(torch, name):
+    single, hist, counts, images, layout = harness.oracle_and_cuda(torch, scenes.get(name))
+    for elem in layout.element_names:
+        harness.assert_rays_close(hist[elem], single['history'][elem], f'{name}/{elem}', RTOL)
+        assert counts[elem] == int(single['meta'][elem]['num_out']), f'{name}/{elem}: num_out'
+    for elem in layout.optic_names:
+        ref = single['image'][elem]
+        if ref is None:
+            assert images[elem] is None
+        else:
+            assert np.array_equal(images[elem], ref), f'{name}/{elem}: image differs'
+
+
+@pytest.mark.parametrize('name', ANALYTIC)
+def test_injected_trace_matches_reference_golden(torch, golden_dir, name):
+    """Same comparison against the unmodified reference's stored per-element rays."""
+    path = os.path.join(golden_dir, name + '.npz')
+    if not os.path.exists(path):
+        pytest.skip('no fixture')
+    gold = np.load(path)
+    single, hist, counts, images, layout = harness.oracle_and_cuda(torch, scenes.get(name))
+    for elem in layout.element_names:
+        ref = {k: gold[f'iter/{elem}/{k}'] for k in ('origin', 'direction', 'wavelength', 'mask')}
+        harness.assert_rays_close(hist[elem], ref, f'{name}/{elem} (golden)', RTOL)
+        assert counts[elem] == int(gold[f'iter_meta/{elem}'])
+    for elem in layout.optic_names:
+        ref = gold[f'iter_image/{elem}']
+        if ref.ndim == 0:
+            assert images[elem] is None
+        else:
+            assert np.array_equal(images[elem], ref)
+
+
+def test_empty_and_all_dead_inputs(torch):
+    """n = 0 is a no-op; rays that enter dead stay dead with NaN origins downstream."""
+    cfg = scenes.get('sphere')
+    single, stream, oscene = oracle.trace_recorded(cfg)
+    scene, layout, _, optics = harness.device_scene(cfg)
+    rays0 = {k: v[:0] for k, v in single['history']['source'].items()}
+    hist, counts, images = harness.run_injected(torch, scene, layout, rays0, {0: np.zeros((1, 0))}, {})
+    assert all(v == 0 for v in counts.values())
+
+    rays0 = {k: np.array(v[:64], copy=True) for k, v in single['history']['source'].items()}
+    rays0['mask'][:] = False
+    hist, counts, images = harness.run_injected(torch, scene, layout, rays0, {0: np.full((1, 64), 0.5)}, {})
+    assert all(v == 0 for v in counts.values())
+    for elem in layout.optic_names:
+        assert np.all(np.isnan(hist[elem]['origin']))
+        assert not hist[elem]['mask'].any()
+        assert np.array_equal(hist[elem]['direction'], rays0['direction'])
+        assert images[elem].sum() == 0
+    scene.close()

@@ -1,0 +1,422 @@
+# -*- coding: utf-8 -*-
+"""
+The drop-in entry points: ``raytrace(config)``, ``raytrace_single(config)``,
+``raytrace_mp(config)``, ``combine_raytrace(list)`` with the reference's
+config dict in and its ``{'config','total','found','lost'}`` dict out
+(reference ``xicsrt/xicsrt_raytrace.py:28-393``).
+
+What differs from the reference is only *where* an iteration runs: the body of
+``_raytrace_iter`` + ``_sort_raytrace`` (``xicsrt_raytrace.py:178-278``) is one
+fused kernel launch (generate -> optic train -> bin) plus, when history is
+kept, a replay of the selected found / lost ray ids that writes their
+per-element states as struct-of-arrays.  Random numbers are Philox4x32-10
+keyed by ``(random_seed, iteration)`` and counted by global ray id, so results
+do not depend on how rays are partitioned over launches or GPUs (and are,
+by design, a different stream than the reference's MT19937).
+
+PyTorch only owns the device buffers; there is no CPU path.
+"""
+import copy
+import ctypes as C
+import logging
+import os
+
+import numpy as np
+
+from . import _lib as L
+from . import config as xconfig
+from . import scene as xscene
+
+log = logging.getLogger('xicsrt_b200')
+
+RAY_KEYS = ('origin', 'direction', 'mask', 'wavelength')
+U64_MAX = (1 << 64) - 1
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('xicsrt_b200 needs a CUDA device (B200); there is no CPU path.')
+    return torch
+
+
+def _skeleton(config):
+    return {'config': config,
+            'total': {'meta': {}, 'image': {}},
+            'found': {'meta': {}, 'history': {}},
+            'lost': {'meta': {}, 'history': {}}}
+
+
+def shard_range(n, rank, world):
+    """Contiguous global ray-id range of one rank: [begin, begin + count)."""
+    begin = (n * rank) // world
+    end = (n * (rank + 1)) // world
+    return begin, end - begin
+
+
+class HostRandom:
+    """Host-side draws (Poisson ray counts, plasma bundle centres): numpy Philox keyed by the run seed."""
+
+    def __init__(self, seed):
+        self.gen = np.random.Generator(np.random.Philox(key=int(seed) & U64_MAX))
+
+    def poisson(self, lam):
+        return int(self.gen.poisson(lam))
+
+    def uniform(self, lo, hi, n):
+        return self.gen.uniform(lo, hi, n)
+
+
+class Tracer:
+    """
+    One prepared run on one GPU: elements prepared on the host, scene uploaded,
+    device buffers allocated once and reused over iterations.
+    """
+
+    def __init__(self, config, seed, rank=0, world=1, device=None):
+        torch = _torch()
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.seed = int(seed) & U64_MAX
+        self.host_rng = HostRandom(self.seed)
+
+        (self.config, self.source_name, source_param, source_filters,
+         optics) = xscene.prepare(config, poisson=self.host_rng.poisson)
+        bundles = None
+        if source_param['_kind'].startswith('plasma'):
+            from . import plasma
+            bundles = plasma.build_bundles(source_param, source_filters, self.host_rng)
+        desc, self.layout, keep = xscene.flatten(self.source_name, source_param, source_filters, optics,
+                                                 bundles=bundles)
+        with torch.cuda.device(self.device):
+            self.scene = xscene.DeviceScene(desc, self.layout)
+        del keep
+        self.lib = self.scene.lib
+        self.n_elem = 1 + len(self.layout.optic_names)
+        self.n_rays = self.layout.n_rays
+
+        i64 = torch.int64
+        # one packed buffer [counts | images] so that a multi-GPU run reduces it with one call
+        self.packed = torch.zeros(self.n_elem + max(self.layout.n_pixels, 1), dtype=i64, device=self.device)
+        self.scalars = torch.zeros(2, dtype=i64, device=self.device)     # found_count, lost_count
+        self.found_ids = None
+        self.lost_ids = None
+        self.lost_keys = None
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _outputs(self, keep_images, found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False):
+        out = L.XrtOutputs()
+        out.counts = self.packed.data_ptr()
+        out.images = self.packed.data_ptr() + 8 * self.n_elem if (keep_images and self.layout.n_pixels) else None
+        if want_lists:
+            torch = self.torch
+            if self.found_ids is None or self.found_ids.numel() < found_cap:
+                self.found_ids = torch.empty(max(found_cap, 1), dtype=torch.int64, device=self.device)
+            if self.lost_ids is None or self.lost_ids.numel() < lost_cap:
+                self.lost_ids = torch.empty(max(lost_cap, 1), dtype=torch.int64, device=self.device)
+                self.lost_keys = torch.empty(max(lost_cap, 1), dtype=torch.int64, device=self.device)
+            out.found_ids = self.found_ids.data_ptr()
+            out.found_count = self.scalars.data_ptr()
+            out.found_capacity = found_cap
+            out.lost_ids = self.lost_ids.data_ptr()
+            out.lost_keys = self.lost_keys.data_ptr()
+            out.lost_count = self.scalars.data_ptr() + 8
+            out.lost_capacity = lost_cap
+            out.lost_threshold = lost_threshold
+        return out
+
+    def trace(self, stream_id, keep_images=True, ray_begin=None, ray_count=None, zero=True,
+              found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False):
+        """Enqueue one fused generate->trace->bin launch for this rank's ray range (asynchronous)."""
+        if ray_begin is None:
+            ray_begin, ray_count = shard_range(self.n_rays, self.rank, self.world)
+        if zero:
+            self.packed.zero_()
+            self.scalars.zero_()
+        out = self._outputs(keep_images, found_cap, lost_cap, lost_threshold, want_lists)
+        with self.torch.cuda.device(self.device):
+            L.check(self.lib.xrt_trace(self.scene.handle, self.seed, int(stream_id), int(ray_begin), int(ray_count),
+                                       C.byref(out), self._stream()))
+        return ray_begin, ray_count
+
+    def history(self, stream_id, ids):
+        """Replay the given global ray ids (int64 device tensor); returns (rays[E,7,n], mask[E,n]) on device."""
+        torch = self.torch
+        n = int(ids.numel())
+        rays = torch.empty((self.n_elem, 7, max(n, 1)), dtype=torch.float64, device=self.device)
+        mask = torch.empty((self.n_elem, max(n, 1)), dtype=torch.uint8, device=self.device)
+        if n:
+            h = L.XrtHistory()
+            h.rays, h.mask, h.capacity = rays.data_ptr(), mask.data_ptr(), max(n, 1)
+            with torch.cuda.device(self.device):
+                L.check(self.lib.xrt_trace_history(self.scene.handle, self.seed, int(stream_id), ids.data_ptr(),
+                                                   0, n, C.byref(h), self._stream()))
+        return rays[:, :, :n], mask[:, :n]
+
+    # ------------------------------------------------------------------
+    def counts_and_images(self, keep_images=True):
+        """Host copies of the packed counters: ({name: num_out}, {name: image or None})."""
+        host = self.packed.cpu().numpy()
+        names = self.layout.element_names
+        meta = {name: int(host[i]) for i, name in enumerate(names)}
+        image = {}
+        if keep_images:
+            for name in self.layout.optic_names:
+                spec = self.layout.images[name]
+                if spec is None:
+                    image[name] = None
+                else:
+                    off, nx, ny = spec
+                    image[name] = host[self.n_elem + off:self.n_elem + off + nx * ny].astype(np.float64).reshape(nx, ny)
+        return meta, image
+
+    def allreduce(self):
+        """Sum counters + images over ranks (one collective on the packed buffer)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.packed, op=dist.ReduceOp.SUM)
+
+    def select_ids(self, stream_id, max_lost, keep_images=True):
+        """
+        One launch that also compacts found ids and a random sample of lost ids.
+        Returns (found_ids sorted, lost_ids) as int64 device tensors; the lost sample is the
+        ``max_lost`` rays with the smallest Philox keys, i.e. a uniform random subset in random
+        order, as ``_sort_raytrace`` draws with a shuffle (xicsrt_raytrace.py:262-266).
+        """
+        torch = self.torch
+        begin, count = shard_range(self.n_rays, self.rank, self.world)
+        found_cap = min(count, max(1 << 20, count // 16))
+        want = 2 * max_lost + 10 * int(np.sqrt(max_lost)) + 64
+        prob = min(1.0, want / max(count, 1))
+        while True:
+            thr = U64_MAX if prob >= 1.0 else int(prob * float(1 << 64))
+            lost_cap = min(count, int(prob * count * 1.5) + 4096)
+            self.trace(stream_id, keep_images, begin, count, True, found_cap, lost_cap, thr, True)
+            n_found, n_kept = (int(v) for v in self.scalars.cpu().numpy())
+            n_lost = count - n_found
+            if n_found > found_cap:
+                found_cap = n_found
+                continue
+            if n_kept > lost_cap:
+                lost_cap = n_kept
+                continue
+            if n_kept < min(max_lost, n_lost) and prob < 1.0:
+                prob = min(1.0, 4.0 * prob * max(1.0, min(max_lost, n_lost) / max(n_kept, 1)))
+                continue
+            break
+        found = torch.sort(self.found_ids[:n_found]).values
+        keys = self.lost_keys[:n_kept]
+        # keys are unsigned 64-bit stored in int64: flip the sign bit to sort as unsigned
+        order = torch.argsort(keys ^ torch.tensor(-(1 << 63), dtype=torch.int64, device=self.device))
+        lost = self.lost_ids[:n_kept][order[:max_lost]]
+        return found, lost
+
+    def close(self):
+        self.scene.close()
+
+
+def _history_dicts(names, rays, mask):
+    """Device SoA [E,7,n] / [E,n] -> {element: {'origin','direction','wavelength','mask'}} on the host."""
+    rays = rays.cpu().numpy()
+    mask = mask.cpu().numpy()
+    out = {}
+    for e, name in enumerate(names):
+        out[name] = {
+            'origin': np.ascontiguousarray(rays[e, 0:3, :].T),
+            'direction': np.ascontiguousarray(rays[e, 3:6, :].T),
+            'mask': mask[e].astype(np.bool_),
+            'wavelength': np.ascontiguousarray(rays[e, 6, :]),
+        }
+    return out
+
+
+def run_iteration(tracer, stream_id, keep_history=True, keep_images=True, keep_meta=True, max_lost=1000):
+    """
+    ``_raytrace_iter`` + ``_sort_raytrace`` (xicsrt_raytrace.py:178-278) on the device;
+    returns the sorted single-iteration dict.  On ranks > 0 of a multi-GPU run the
+    reduced meta / images are still returned; histories hold the rank's own rays.
+    """
+    out = _skeleton(tracer.config)
+    names = tracer.layout.element_names
+    if keep_history:
+        lost_quota = max_lost if tracer.world == 1 else max(1, max_lost // tracer.world)
+        found, lost = tracer.select_ids(stream_id, lost_quota, keep_images)
+    else:
+        tracer.trace(stream_id, keep_images)
+    tracer.allreduce()
+    meta, image = tracer.counts_and_images(keep_images)
+    if keep_meta:
+        out['total']['meta'] = {name: {'num_out': meta[name]} for name in names}
+    if keep_images:
+        out['total']['image'] = image
+    if keep_history:
+        n_found = int(found.numel())
+        ids = tracer.torch.cat([found, lost])
+        rays, mask = tracer.history(stream_id, ids)
+        out['found']['history'] = _history_dicts(names, rays[:, :, :n_found], mask[:, :n_found])
+        out['lost']['history'] = _history_dicts(names, rays[:, :, n_found:], mask[:, n_found:])
+        if tracer.world > 1:
+            _gather_histories(out, names)
+    return out
+
+
+def merge_histories(parts, names):
+    """Concatenate per-rank {element: rays} dicts in rank order (= ascending global ray id for 'found')."""
+    return {name: {key: np.concatenate([p[name][key] for p in parts]) for key in RAY_KEYS} for name in names}
+
+
+def _gather_histories(out, names):
+    """Variable-length gather of the found / lost histories onto rank 0 (other ranks keep their own)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [None] * world if rank == 0 else None
+    dist.gather_object((out['found']['history'], out['lost']['history']), box, dst=0)
+    if rank == 0:
+        out['found']['history'] = merge_histories([b[0] for b in box], names)
+        out['lost']['history'] = merge_histories([b[1] for b in box], names)
+
+
+def combine_raytrace(input_list, keep_images=True, components=None):
+    """Sum meta and images, concatenate histories (xicsrt_raytrace.py:281-393)."""
+    out = _skeleton(input_list[0]['config'])
+    names = list(input_list[0]['total']['meta'].keys()) if components is None else list(components)
+
+    for name in names:
+        out['total']['meta'][name] = {}
+        for key in input_list[0]['total']['meta'][name]:
+            out['total']['meta'][name][key] = 0
+            for part in input_list:
+                out['total']['meta'][name][key] += part['total']['meta'][name][key]
+
+    if keep_images:
+        for name in names:
+            if name not in input_list[0]['total']['image']:
+                continue
+            first = input_list[0]['total']['image'][name]
+            if first is None:
+                out['total']['image'][name] = None
+            elif all(part['total']['image'][name].shape == first.shape for part in input_list):
+                acc = np.zeros(first.shape)
+                for part in input_list:
+                    acc += part['total']['image'][name]
+                out['total']['image'][name] = acc
+            else:
+                log.warning('Image dimensions do not match. Cannot combine images.')
+                out['total']['image'][name] = None
+
+    if len(input_list[0]['found']['history']) > 0:
+        for kind in ('found', 'lost'):
+            for name in names:
+                out[kind]['history'][name] = {
+                    key: np.concatenate([part[kind]['history'][name][key] for part in input_list])
+                    for key in RAY_KEYS}
+    return out
+
+
+def print_raytrace(results):
+    """xicsrt_raytrace.py:414-430."""
+    names = list(results['total']['meta'].keys())
+    num_source = results['total']['meta'][names[0]]['num_out']
+    num_detector = results['total']['meta'][names[-1]]['num_out']
+    print('')
+    print('Rays Generated: {:6.3e}'.format(num_source))
+    print('Rays Detected:  {:6.3e}'.format(num_detector))
+    print('Efficiency:     {:6.3e} ± {:3.1e} ({:7.5f}%)'.format(
+        num_detector / num_source, np.sqrt(num_detector) / num_source, num_detector / num_source * 100))
+    print('')
+
+
+def _dist_info():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def _resolve_seed(seed, world):
+    """``random_seed=None`` means fresh entropy (np.random.seed(None)); all ranks must agree on it."""
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), 'little') >> 1
+        if world > 1:
+            import torch.distributed as dist
+            box = [seed]
+            dist.broadcast_object_list(box, src=0)
+            seed = box[0]
+    return int(seed)
+
+
+def raytrace_single(config, _internal=False):
+    """One run = ``number_of_iter`` iterations, combined (xicsrt_raytrace.py:87-175)."""
+    config = xconfig.to_numpy(config)
+    config = xconfig.get_config(config)
+    g = config['general']
+    rank, world = _dist_info()
+
+    num_iter = g['number_of_iter']
+    max_lost_iter = int(g['history_max_lost'] / num_iter)
+    if _internal:
+        max_lost_iter = max_lost_iter // g['number_of_runs']
+    max_lost_iter = max(int(max_lost_iter), 1)
+
+    tracer = Tracer(config, _resolve_seed(g['random_seed'], world), rank=rank, world=world)
+    try:
+        parts = [run_iteration(tracer, it, keep_history=g['keep_history'], keep_images=g['keep_images'],
+                               keep_meta=g['keep_meta'], max_lost=max_lost_iter)
+                 for it in range(num_iter)]
+    finally:
+        tracer.close()
+    output = combine_raytrace(parts)
+    if _internal is False:
+        _finish(output, g, single=True)
+    return output
+
+
+def _finish(output, g, single=False):
+    from . import io as xio
+    if g['print_results'] and _dist_info()[0] == 0:
+        print_raytrace(output)
+    if _dist_info()[0] != 0:
+        return
+    if g['save_config']:
+        xio.save_config(output['config'])
+    if g['save_images'] and not single:
+        xio.save_images(output)
+    if g['save_results']:
+        xio.save_results(output)
+
+
+def raytrace(config):
+    """``number_of_runs`` runs with cumulative seeds, combined (xicsrt_raytrace.py:28-84)."""
+    config = xconfig.get_config(config)
+    g = config['general']
+    seed = g['random_seed']
+    outputs = []
+    for ii in range(g['number_of_runs']):
+        config_run = copy.deepcopy(config)
+        config_run['general']['output_run_suffix'] = '{:04d}'.format(ii)
+        if seed is not None:
+            seed += ii       # cumulative 0, 1, 3, 6, ... as in the reference (:61-63)
+        config_run['general']['random_seed'] = seed
+        outputs.append(raytrace_single(config_run, _internal=True))
+    output = combine_raytrace(outputs)
+    output['config']['general']['output_run_suffix'] = g['output_run_suffix']
+    output['config']['general']['random_seed'] = g['random_seed']
+    _finish(output, g)
+    return output
+
+
+def raytrace_mp(config, processes=None):
+    """
+    The reference's multiprocessing entry (xicsrt_multiprocessing.py:12-81) splits *runs*
+    over host processes.  Here the parallel resource is the GPU (and, under torchrun, the
+    GPUs of the box: rays of every iteration are sharded over ranks inside
+    :func:`raytrace_single`), so this is :func:`raytrace`; ``processes`` is accepted and ignored.
+    """
+    return raytrace(config)

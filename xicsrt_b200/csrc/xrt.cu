@@ -1,0 +1,578 @@
+// xrt.cu -- kernels and the C ABI of libxrt.so (see include/xrt.h).
+//
+// Kernels
+//   k_trace<FT>     fused generate -> optic train -> bin, one ray per thread, ray
+//                   state in registers from the source to the detector; the only
+//                   global traffic is the per-element survivor counters (one
+//                   atomic per block), the pixel counters of surviving rays
+//                   (warp-aggregated atomics) and the optional found / lost id
+//                   lists (ballot + prefix-sum compaction).
+//   k_record<FT,..> same ray code, but every element's ray state is stored as
+//                   struct-of-arrays history (coalesced 8-byte planes); rays come
+//                   either from Philox by id (history of selected rays) or from
+//                   caller memory with injected draws (parity entry).
+//   k_source<..>    source only (history element 0).
+//   k_burn          dependent DFMA chains: the FP64 roofline denominator.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "xrt_trace.cuh"
+
+namespace xrt {
+
+constexpr int kBlock = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------
+// fused kernel
+
+template <uint32_t FT>
+__global__ void __launch_bounds__(kBlock)
+k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
+        const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out) {
+    __shared__ unsigned long long s_cnt[XRT_MAX_OPTICS + 1];
+    if (threadIdx.x <= XRT_MAX_OPTICS) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const int nopt = sc.n_optics;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+
+    for (uint64_t base = (uint64_t)blockIdx.x * kBlock; base < ray_count; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        const bool valid = i < ray_count;
+        const uint64_t id = ray_begin + i;
+        PhiloxDraws dr;
+        dr.init(seed, stream_id, id);
+        Ray r;
+        r.alive = false;
+        if (valid) generate_ray<FT>(sc.source, dr, id, r);
+
+        unsigned m = __ballot_sync(kFull, r.alive);
+        if (lane == 0 && m) atomicAdd(&s_cnt[0], (unsigned long long)__popc(m));
+
+        for (int k = 0; k < nopt && m; ++k) {
+            const XrtOpticDesc &op = sc.optics[k];
+            if (r.alive) {
+                trace_optic<FT>(op, k, dr, r);
+                if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) {
+                    uint32_t pix;
+                    if (pixel_index(op, r.o, pix)) {
+                        // warp-aggregated: one atomic per distinct pixel in the warp
+                        unsigned act = __activemask();
+                        unsigned same = __match_any_sync(act, pix);
+                        if ((same & lt_mask) == 0)
+                            atomicAdd((unsigned long long *)(out.images + op.image_offset + pix),
+                                      (unsigned long long)__popc(same));
+                    }
+                }
+            }
+            m = __ballot_sync(kFull, r.alive);
+            if (lane == 0 && m) atomicAdd(&s_cnt[k + 1], (unsigned long long)__popc(m));
+        }
+
+        // ---- found list: ballot + prefix-sum compaction, one atomic per warp
+        if (out.found_count) {
+            if (m) {
+                unsigned long long off = 0;
+                if (lane == 0) off = atomicAdd((unsigned long long *)out.found_count, (unsigned long long)__popc(m));
+                off = __shfl_sync(kFull, off, 0);
+                if (r.alive && out.found_ids) {
+                    unsigned long long slot = off + __popc(m & lt_mask);
+                    if (slot < out.found_capacity) out.found_ids[slot] = id;
+                }
+            }
+        }
+        // ---- lost sample: keep a lost ray when its 64-bit key is below the threshold
+        if (out.lost_count) {
+            bool keep = false;
+            uint64_t key = 0;
+            if (valid && !r.alive) {
+                key = dr.lost_key();
+                keep = key < out.lost_threshold;
+            }
+            unsigned lm = __ballot_sync(kFull, keep);
+            if (lm) {
+                unsigned long long off = 0;
+                if (lane == 0) off = atomicAdd((unsigned long long *)out.lost_count, (unsigned long long)__popc(lm));
+                off = __shfl_sync(kFull, off, 0);
+                if (keep && out.lost_ids) {
+                    unsigned long long slot = off + __popc(lm & lt_mask);
+                    if (slot < out.lost_capacity) {
+                        out.lost_ids[slot] = id;
+                        if (out.lost_keys) out.lost_keys[slot] = key;
+                    }
+                }
+            }
+        }
+    }
+
+    __syncthreads();
+    if ((int)threadIdx.x <= nopt && out.counts) {
+        unsigned long long c = s_cnt[threadIdx.x];
+        if (c) atomicAdd((unsigned long long *)(out.counts + threadIdx.x), c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// recording kernel: history of every element, optional counters / images
+
+__device__ __forceinline__ void store_history(const XrtHistory &h, int elem, uint64_t slot, const Ray &r) {
+    if (h.rays) {
+        double *p = h.rays + ((uint64_t)elem * 7) * h.capacity + slot;
+        const uint64_t c = h.capacity;
+        p[0] = r.o.x; p[c] = r.o.y; p[2 * c] = r.o.z;
+        p[3 * c] = r.d.x; p[4 * c] = r.d.y; p[5 * c] = r.d.z;
+        p[6 * c] = r.w;
+    }
+    if (h.mask) h.mask[(uint64_t)elem * h.capacity + slot] = r.alive ? 1 : 0;
+}
+
+enum { REC_PHILOX = 0, REC_INJECT = 1 };
+
+template <uint32_t FT, int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
+         const uint64_t *__restrict__ ids, const uint64_t ray_begin, const uint64_t n,
+         const XrtRaysIn in, const XrtInject inj, const XrtOutputs out, const XrtHistory hist) {
+    const int nopt = sc.n_optics;
+    const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        Ray r;
+        PhiloxDraws pdr;
+        InjectedDraws idr;
+        if constexpr (MODE == REC_PHILOX) {
+            const uint64_t id = ids ? ids[i] : ray_begin + i;
+            pdr.init(seed, stream_id, id);
+            generate_ray<FT>(sc.source, pdr, id, r);
+        } else {
+            r.o = v3(in.origin + 3 * i);
+            r.d = v3(in.direction + 3 * i);
+            r.w = in.wavelength[i];
+            r.alive = in.mask[i] != 0;
+            idr.inj = &inj;
+            idr.i = i;
+            idr.n = n;
+        }
+        store_history(hist, 0, i, r);
+        if (out.counts && r.alive) atomicAdd((unsigned long long *)out.counts, 1ull);
+
+        for (int k = 0; k < nopt; ++k) {
+            const XrtOpticDesc &op = sc.optics[k];
+            if (r.alive) {
+                if constexpr (MODE == REC_PHILOX) trace_optic<FT>(op, k, pdr, r);
+                else trace_optic<FT>(op, k, idr, r);
+                if (r.alive) {
+                    if (out.counts) atomicAdd((unsigned long long *)(out.counts + k + 1), 1ull);
+                    uint32_t pix;
+                    if ((op.flags & XRT_F_IMAGE) && out.images && pixel_index(op, r.o, pix))
+                        atomicAdd((unsigned long long *)(out.images + op.image_offset + pix), 1ull);
+                }
+            } else {
+                pass_lost_ray<FT>(op, r);   // lost earlier: the reference carries NaN origins forward
+            }
+            store_history(hist, k + 1, i, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// source only
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_source(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
+         const uint64_t ray_begin, const uint64_t n, const XrtSourceInject sinj, const XrtHistory hist) {
+    const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        Ray r;
+        if constexpr (MODE == REC_PHILOX) {
+            PhiloxDraws dr;
+            dr.init(seed, stream_id, ray_begin + i);
+            generate_ray<FT_FULL>(sc.source, dr, ray_begin + i, r);
+        } else {
+            SourceInjectedDraws dr;
+            dr.inj = &sinj;
+            dr.i = i;
+            dr.n = n;
+            generate_ray<FT_FULL>(sc.source, dr, ray_begin + i, r);
+        }
+        store_history(hist, 0, i, r);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 pipe microbenchmark: 8 independent dependent-FMA chains per thread
+
+constexpr int kBurnChains = 8;
+
+__global__ void __launch_bounds__(kBlock) k_burn(uint64_t iters, double *sink) {
+    double a[kBurnChains];
+    const double m = 1.0 + 1e-9 * (double)(threadIdx.x & 7), c = 1e-12;
+#pragma unroll
+    for (int j = 0; j < kBurnChains; ++j) a[j] = 1.0 + (double)j * 1e-3 + (double)threadIdx.x * 1e-6;
+    for (uint64_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < kBurnChains; ++j) a[j] = fma(a[j], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kBurnChains; ++j) s += a[j];
+    if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
+}
+
+}  // namespace xrt
+
+// ===========================================================================
+// host side
+
+using namespace xrt;
+
+struct XrtScene {
+    XrtSceneDesc dev;               // descriptor whose pointers are device pointers
+    std::vector<void *> allocs;
+    uint32_t features;
+    int device;
+    int sm_count;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(XRT_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+static int upload(XrtScene *s, const T *host, size_t count, const T **dev) {
+    *dev = nullptr;
+    if (host == nullptr || count == 0) return XRT_OK;
+    void *p = nullptr;
+    CU(cudaMalloc(&p, count * sizeof(T)));
+    s->allocs.push_back(p);
+    CU(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (const T *)p;
+    return XRT_OK;
+}
+
+#define UP(field, count)                                                   \
+    do {                                                                   \
+        int rc_ = upload(s, field, (size_t)(count), &field);               \
+        if (rc_ != XRT_OK) return rc_;                                     \
+    } while (0)
+
+static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
+    XrtMesh m = *host;
+    UP(m.points, 3 * (size_t)m.n_points);
+    UP(m.faces, 3 * (size_t)m.n_faces);
+    UP(m.face_normals, 3 * (size_t)m.n_faces);
+    UP(m.coarse_points, 3 * (size_t)m.n_coarse_points);
+    UP(m.coarse_faces, 3 * (size_t)m.n_coarse_faces);
+    UP(m.point_faces, 8 * (size_t)m.n_points);
+    UP(m.point_faces_mask, 8 * (size_t)m.n_points);
+    UP(m.tri, 3 * (size_t)m.n_tri);
+    UP(m.tri_neighbors, 3 * (size_t)m.n_tri);
+    UP(m.tri_xy, m.n_tri ? 2 * (size_t)m.n_points : 0);
+    UP(m.values, m.n_tri ? 4 * (size_t)m.n_points : 0);
+    UP(m.grads, m.n_tri ? 8 * (size_t)m.n_points : 0);
+    size_t cells = (size_t)m.grid_nx * (size_t)m.grid_ny;
+    int32_t n_items = 0, n_vitems = 0;
+    if (cells && m.grid_start) n_items = m.grid_start[cells];
+    if (cells && m.vgrid_start) n_vitems = m.vgrid_start[cells];
+    UP(m.grid_start, cells ? cells + 1 : 0);
+    UP(m.grid_items, n_items);
+    UP(m.vgrid_start, (cells && m.vgrid_start) ? cells + 1 : 0);
+    UP(m.vgrid_items, n_vitems);
+    const XrtMesh *d = nullptr;
+    int rc = upload(s, &m, 1, &d);
+    if (rc != XRT_OK) return rc;
+    *dev = d;
+    return XRT_OK;
+}
+
+static uint32_t scene_features(const XrtSceneDesc &d) {
+    uint32_t ft = 0;
+    const XrtSourceDesc &src = d.source;
+    if (src.kind == XRT_SRC_BUNDLES || src.spatial != XRT_SPATIAL_UNIFORM || src.cone != XRT_CONE_ISOTROPIC ||
+        src.n_sightlines > 0)
+        ft |= FT_SRC_EXT;
+    for (int k = 0; k < d.n_optics; ++k) {
+        const XrtOpticDesc &op = d.optics[k];
+        if (op.flags & XRT_F_TRACE_LOCAL) ft |= FT_LOCAL;
+        if (op.shape == XRT_SHAPE_CYLINDER) ft |= FT_CYL;
+        if (op.shape == XRT_SHAPE_TORUS) ft |= FT_TORUS;
+        if (op.shape == XRT_SHAPE_MESH) ft |= FT_MESH;
+        if ((op.flags & XRT_F_CHECK_APERTURE) && op.n_aperture > 0) ft |= FT_APERTURE;
+        if (op.interact == XRT_INTERACT_MOSAIC) ft |= FT_MOSAIC;
+        if (op.rocking_type == XRT_ROCK_TABLE &&
+            (op.interact == XRT_INTERACT_CRYSTAL || op.interact == XRT_INTERACT_MOSAIC))
+            ft |= FT_ROCKTAB;
+    }
+    // three compiled variants: lean spectrometer, all analytic features, everything
+    if (ft == 0) return 0;
+    if ((ft & ~FT_MID) == 0) return FT_MID;
+    return FT_FULL;
+}
+
+extern "C" int xrt_version(void) { return XRT_VERSION; }
+
+extern "C" const char *xrt_last_error(void) { return g_err; }
+
+extern "C" int xrt_scene_destroy(XrtScene *s) {
+    if (!s) return XRT_OK;
+    for (void *p : s->allocs) cudaFree(p);
+    delete s;
+    return XRT_OK;
+}
+
+static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
+    s->dev = *desc;
+    XrtSceneDesc &d = s->dev;
+    XrtSourceDesc &src = d.source;
+
+    if (src.kind < XRT_SRC_FIXED_AXIS || src.kind > XRT_SRC_BUNDLES) return fail(XRT_EINVAL, "source.kind = %d", src.kind);
+    if (src.cone < XRT_CONE_ISOTROPIC || src.cone > XRT_CONE_FLAT_XY) return fail(XRT_EINVAL, "source.cone = %d", src.cone);
+    if (src.wave < XRT_WAVE_CONST || src.wave > XRT_WAVE_TABLE) return fail(XRT_EINVAL, "source.wave = %d", src.wave);
+    if (src.n_sightlines < 0 || src.n_sightlines > XRT_MAX_SIGHTLINES)
+        return fail(XRT_EINVAL, "source.n_sightlines = %d", src.n_sightlines);
+    if (src.wave == XRT_WAVE_TABLE && (src.n_table < 2 || !src.table_cdf || !src.table_x))
+        return fail(XRT_EINVAL, "source wavelength table missing");
+    if (src.kind == XRT_SRC_BUNDLES && (src.n_bundles == 0 || !src.bundles || !src.bundle_end))
+        return fail(XRT_EINVAL, "plasma source without bundles");
+    {
+        XrtSourceDesc &m = src;
+        UP(m.table_cdf, m.wave == XRT_WAVE_TABLE ? m.n_table : 0);
+        UP(m.table_x, m.wave == XRT_WAVE_TABLE ? m.n_table : 0);
+        UP(m.bundles, m.kind == XRT_SRC_BUNDLES ? m.n_bundles : 0);
+        UP(m.bundle_end, m.kind == XRT_SRC_BUNDLES ? m.n_bundles : 0);
+    }
+
+    for (int k = 0; k < d.n_optics; ++k) {
+        XrtOpticDesc &m = d.optics[k];
+        if (m.shape < XRT_SHAPE_PLANE || m.shape > XRT_SHAPE_MESH) return fail(XRT_EINVAL, "optic %d: shape = %d", k, m.shape);
+        if (m.interact < XRT_INTERACT_NONE || m.interact > XRT_INTERACT_MOSAIC)
+            return fail(XRT_EINVAL, "optic %d: interact = %d", k, m.interact);
+        const bool crystal = (m.interact == XRT_INTERACT_CRYSTAL || m.interact == XRT_INTERACT_MOSAIC);
+        if (crystal && (m.flags & XRT_F_CHECK_BRAGG)) {
+            if (m.rocking_type < XRT_ROCK_STEP || m.rocking_type > XRT_ROCK_TABLE)
+                return fail(XRT_EINVAL, "optic %d: rocking_type = %d", k, m.rocking_type);
+            if (m.rocking_type == XRT_ROCK_TABLE && (m.n_rock < 2 || !m.rock_dtheta || !m.rock_s || !m.rock_p))
+                return fail(XRT_EINVAL, "optic %d: rocking table missing", k);
+            if (!(m.two_d > 0.0)) return fail(XRT_EINVAL, "optic %d: crystal_spacing must be > 0", k);
+        }
+        if (m.shape == XRT_SHAPE_TORUS && (m.root_idx < 0 || m.root_idx > 3))
+            return fail(XRT_EINVAL, "optic %d: root_idx = %d", k, m.root_idx);
+        if ((m.flags & XRT_F_IMAGE) && (m.npix[0] <= 0 || m.npix[1] <= 0 || !(m.pixel_size > 0.0)))
+            return fail(XRT_EINVAL, "optic %d: bad pixel grid", k);
+        if (m.n_aperture < 0) return fail(XRT_EINVAL, "optic %d: n_aperture = %d", k, m.n_aperture);
+        UP(m.apertures, m.n_aperture);
+        const bool tab = crystal && m.rocking_type == XRT_ROCK_TABLE;
+        UP(m.rock_dtheta, tab ? m.n_rock : 0);
+        UP(m.rock_s, tab ? m.n_rock : 0);
+        UP(m.rock_p, tab ? m.n_rock : 0);
+        if (m.shape == XRT_SHAPE_MESH) {
+            if (!m.mesh) return fail(XRT_EINVAL, "optic %d: mesh tables missing", k);
+            int rc = upload_mesh(s, m.mesh, &m.mesh);
+            if (rc != XRT_OK) return rc;
+        } else {
+            m.mesh = nullptr;
+        }
+    }
+    s->features = scene_features(d);
+    return XRT_OK;
+}
+
+extern "C" int xrt_scene_create(const XrtSceneDesc *desc, XrtScene **scene) {
+    if (!desc || !scene) return fail(XRT_EINVAL, "null argument");
+    *scene = nullptr;
+    if (desc->version != XRT_VERSION) return fail(XRT_EINVAL, "descriptor version %d, library %d", desc->version, XRT_VERSION);
+    if (desc->n_optics < 0 || desc->n_optics > XRT_MAX_OPTICS)
+        return fail(XRT_EINVAL, "n_optics = %d (max %d)", desc->n_optics, XRT_MAX_OPTICS);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(XRT_ECUDA, "no CUDA device: libxrt has no CPU path");
+    }
+    XrtScene *s = new (std::nothrow) XrtScene();
+    if (!s) return fail(XRT_ENOMEM, "out of host memory");
+    cudaError_t e = cudaGetDevice(&s->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(XRT_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    }
+    int rc = scene_build(s, desc);
+    if (rc != XRT_OK) {
+        xrt_scene_destroy(s);
+        return rc;
+    }
+    *scene = s;
+    return XRT_OK;
+}
+
+// ---- launch helpers -------------------------------------------------------
+
+template <class K>
+static int occupancy(K kernel, int *blocks_per_sm, int *regs) {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kernel));
+    if (regs) *regs = fa.numRegs;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, kBlock, 0));
+    if (*blocks_per_sm < 1) *blocks_per_sm = 1;
+    return XRT_OK;
+}
+
+typedef void (*TraceKernel)(const XrtSceneDesc, const uint64_t, const uint64_t, const uint64_t, const uint64_t,
+                            const XrtOutputs);
+
+static TraceKernel trace_kernel(uint32_t ft) {
+    if (ft == 0) return k_trace<0>;
+    if (ft == FT_MID) return k_trace<FT_MID>;
+    return k_trace<FT_FULL>;
+}
+
+static int grid_for(const XrtScene *s, uint64_t n, int blocks_per_sm) {
+    uint64_t want = (n + kBlock - 1) / kBlock;
+    uint64_t cap = (uint64_t)s->sm_count * (uint64_t)blocks_per_sm;   // one resident wave, grid-stride beyond
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+extern "C" int xrt_launch_info(XrtScene *s, int32_t *grid, int32_t *block, int32_t *regs, int32_t *blocks_per_sm) {
+    if (!s) return fail(XRT_EINVAL, "null scene");
+    int bps = 0, r = 0;
+    int rc = occupancy(trace_kernel(s->features), &bps, &r);
+    if (rc != XRT_OK) return rc;
+    if (grid) *grid = s->sm_count * bps;
+    if (block) *block = kBlock;
+    if (regs) *regs = r;
+    if (blocks_per_sm) *blocks_per_sm = bps;
+    return XRT_OK;
+}
+
+extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_t ray_begin, uint64_t ray_count,
+                         const XrtOutputs *out, void *stream) {
+    if (!s || !out) return fail(XRT_EINVAL, "null argument");
+    if (ray_count == 0) return XRT_OK;
+    TraceKernel kern = trace_kernel(s->features);
+    int bps = 0;
+    int rc = occupancy(kern, &bps, nullptr);
+    if (rc != XRT_OK) return rc;
+    int grid = grid_for(s, ray_count, bps);
+    kern<<<grid, kBlock, 0, (cudaStream_t)stream>>>(s->dev, seed, stream_id, ray_begin, ray_count, *out);
+    CU(cudaGetLastError());
+    return XRT_OK;
+}
+
+template <int MODE>
+static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const uint64_t *ids, uint64_t ray_begin,
+                         uint64_t n, const XrtRaysIn &in, const XrtInject &inj, const XrtOutputs &out,
+                         const XrtHistory &hist, void *stream) {
+    if (hist.rays || hist.mask) {
+        if (hist.capacity < n) return fail(XRT_EINVAL, "history capacity %llu < %llu rays",
+                                           (unsigned long long)hist.capacity, (unsigned long long)n);
+    }
+    uint64_t want = (n + kBlock - 1) / kBlock;
+    uint64_t cap = (uint64_t)s->sm_count * 8;
+    int grid = (int)(want < cap ? want : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->features == 0)
+        k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist);
+    else if (s->features == FT_MID)
+        k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist);
+    else
+        k_record<FT_FULL, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist);
+    CU(cudaGetLastError());
+    return XRT_OK;
+}
+
+extern "C" int xrt_trace_history(XrtScene *s, uint64_t seed, uint64_t stream_id, const uint64_t *ids,
+                                 uint64_t ray_begin, uint64_t n, const XrtHistory *hist, void *stream) {
+    if (!s || !hist) return fail(XRT_EINVAL, "null argument");
+    if (n == 0) return XRT_OK;
+    XrtRaysIn in = {};
+    XrtInject inj = {};
+    XrtOutputs out = {};
+    return launch_record<REC_PHILOX>(s, seed, stream_id, ids, ray_begin, n, in, inj, out, *hist, stream);
+}
+
+extern "C" int xrt_trace_injected(XrtScene *s, const XrtRaysIn *rays, const XrtInject *draws, uint64_t n,
+                                  const XrtOutputs *out, const XrtHistory *hist, void *stream) {
+    if (!s || !rays) return fail(XRT_EINVAL, "null argument");
+    if (!rays->origin || !rays->direction || !rays->wavelength || !rays->mask)
+        return fail(XRT_EINVAL, "incomplete ray input");
+    if (n == 0) return XRT_OK;
+    XrtInject inj = {};
+    if (draws) inj = *draws;
+    for (int k = 0; k < s->dev.n_optics; ++k) {
+        const XrtOpticDesc &op = s->dev.optics[k];
+        const bool bragg = (op.flags & XRT_F_CHECK_BRAGG) != 0;
+        if (op.interact == XRT_INTERACT_CRYSTAL && bragg && !inj.u[k])
+            return fail(XRT_EINVAL, "optic %d needs injected uniforms", k);
+        if (op.interact == XRT_INTERACT_MOSAIC && (!inj.xy[k] || (bragg && !inj.u[k])))
+            return fail(XRT_EINVAL, "optic %d needs injected mosaic draws", k);
+    }
+    XrtOutputs o = {};
+    if (out) o = *out;
+    XrtHistory h = {};
+    if (hist) h = *hist;
+    return launch_record<REC_INJECT>(s, 0, 0, nullptr, 0, n, *rays, inj, o, h, stream);
+}
+
+template <int MODE>
+static int launch_source(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_t ray_begin, uint64_t n,
+                         const XrtSourceInject &sinj, const XrtHistory *hist, void *stream) {
+    if (!s || !hist) return fail(XRT_EINVAL, "null argument");
+    if (n == 0) return XRT_OK;
+    if (hist->capacity < n) return fail(XRT_EINVAL, "history capacity too small");
+    uint64_t want = (n + kBlock - 1) / kBlock;
+    uint64_t cap = (uint64_t)s->sm_count * 8;
+    int grid = (int)(want < cap ? want : cap);
+    k_source<MODE><<<grid, kBlock, 0, (cudaStream_t)stream>>>(s->dev, seed, stream_id, ray_begin, n, sinj, *hist);
+    CU(cudaGetLastError());
+    return XRT_OK;
+}
+
+extern "C" int xrt_source_injected(XrtScene *s, const XrtSourceInject *draws, uint64_t n, const XrtHistory *hist,
+                                   void *stream) {
+    if (!draws) return fail(XRT_EINVAL, "null argument");
+    if (s && s->dev.source.kind == XRT_SRC_BUNDLES) return fail(XRT_EUNSUPPORTED, "injected draws: box sources only");
+    if (s && s->dev.source.cone == XRT_CONE_ISOTROPIC_XY)
+        return fail(XRT_EUNSUPPORTED, "injected draws: isotropic_xy has a variable draw count");
+    return launch_source<REC_INJECT>(s, 0, 0, 0, n, *draws, hist, stream);
+}
+
+extern "C" int xrt_source_generate(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_t ray_begin, uint64_t n,
+                                   const XrtHistory *hist, void *stream) {
+    XrtSourceInject none = {};
+    return launch_source<REC_PHILOX>(s, seed, stream_id, ray_begin, n, none, hist, stream);
+}
+
+extern "C" int xrt_fp64_burn(uint64_t iters, double *out_dev, double *flops, void *stream) {
+    if (!out_dev) return fail(XRT_EINVAL, "null argument");
+    int dev = 0, sms = 0, bps = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_burn, kBlock, 0));
+    int grid = sms * bps;
+    k_burn<<<grid, kBlock, 0, (cudaStream_t)stream>>>(iters, out_dev);
+    CU(cudaGetLastError());
+    if (flops) *flops = 2.0 * (double)kBurnChains * (double)iters * (double)grid * (double)kBlock;
+    return XRT_OK;
+}

@@ -1,0 +1,86 @@
+// xrt_math.cuh -- small FP64 vector helpers, Philox4x32-10 and table lookup.
+#pragma once
+#include <stdint.h>
+#include <math_constants.h>
+
+namespace xrt {
+
+struct V3 { double x, y, z; };
+
+__device__ __forceinline__ V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 v3(const double *p) { return v3(p[0], p[1], p[2]); }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ V3 unit(V3 a) { return a * rsqrt(dot(a, a)); }
+__device__ __forceinline__ V3 nan3() { return v3(CUDART_NAN, CUDART_NAN, CUDART_NAN); }
+
+// rows of a 3x3 orientation (x, y, z axes of an element)
+// local = R . v   (reference _GeometryObject.py:156-168, einsum 'ji,ki->kj')
+__device__ __forceinline__ V3 to_local(const double *R, V3 v) {
+    return v3(R[0] * v.x + R[1] * v.y + R[2] * v.z,
+              R[3] * v.x + R[4] * v.y + R[5] * v.z,
+              R[6] * v.x + R[7] * v.y + R[8] * v.z);
+}
+// external = R^T . v  (reference _GeometryObject.py:143-154, einsum 'ij,ki->kj')
+__device__ __forceinline__ V3 to_external(const double *R, V3 v) {
+    return v3(R[0] * v.x + R[3] * v.y + R[6] * v.z,
+              R[1] * v.x + R[4] * v.y + R[7] * v.z,
+              R[2] * v.x + R[5] * v.y + R[8] * v.z);
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: no state, any ray can be
+// regenerated from (key, ray id, draw site).
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+// 53-bit uniform in [0, 1) from two 32-bit words (same construction as numpy's
+// random_sample: (a >> 5) * 2^26 + (b >> 6), scaled by 2^-53)
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// two independent standard normals from two uniforms (Box-Muller)
+__device__ __forceinline__ void box_muller(double u1, double u2, double &z1, double &z2) {
+    double r = sqrt(-2.0 * log(1.0 - u1));     // 1 - u1 in (0, 1]
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z1 = r * c;
+    z2 = r * s;
+}
+
+// np.interp(x, xp, fp) for x inside [xp[0], xp[n-1]] (caller handles the outside)
+__device__ __forceinline__ double interp_inside(double x, const double *__restrict__ xp,
+                                                const double *__restrict__ fp, int n) {
+    // largest j with xp[j] <= x
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(xp + mid) <= x) lo = mid; else hi = mid;
+    }
+    double x0 = __ldg(xp + lo), x1 = __ldg(xp + lo + 1);
+    double f0 = __ldg(fp + lo), f1 = __ldg(fp + lo + 1);
+    if (x == x1) return f1;
+    double slope = (f1 - f0) / (x1 - x0);
+    return slope * (x - x0) + f0;
+}
+
+}  // namespace xrt

@@ -1,0 +1,668 @@
+// xrt_trace.cuh -- per-ray device code: source generation and the optic train.
+//
+// One thread owns one ray; the ray state (origin, direction, wavelength, alive
+// flag) stays in registers from the source through every optic.  The scene is a
+// __grid_constant__ kernel parameter, so element parameters are read from the
+// constant bank with warp-uniform addresses.
+//
+// Feature mask FT: compile-time pruning of branches a scene does not use, so the
+// common spectrometer (plane / sphere optics, Gaussian or step rocking curve)
+// does not pay registers for the torus solver, mosaic loop or mesh lookup.
+#pragma once
+#include "../../include/xrt.h"
+#include "xrt_math.cuh"
+
+namespace xrt {
+
+enum : uint32_t {
+    FT_LOCAL = 1u << 0,     // some optic traces in local coordinates
+    FT_CYL = 1u << 1,
+    FT_TORUS = 1u << 2,
+    FT_MESH = 1u << 3,
+    FT_APERTURE = 1u << 4,
+    FT_MOSAIC = 1u << 5,
+    FT_ROCKTAB = 1u << 6,
+    FT_SRC_EXT = 1u << 7,   // anything beyond box + isotropic cone + const/uniform/normal line
+    FT_MID = FT_LOCAL | FT_CYL | FT_TORUS | FT_APERTURE | FT_MOSAIC | FT_ROCKTAB | FT_SRC_EXT,
+    FT_FULL = FT_MID | FT_MESH,
+};
+
+struct Ray {
+    V3 o, d;
+    double w;
+    bool alive;
+};
+
+// ---------------------------------------------------------------------------
+// draw providers
+
+// draw-site numbering for the Philox counter (word 2)
+__device__ __forceinline__ uint32_t site_optic(int k, int layer, int which) {
+    return ((uint32_t)(k + 1) << 16) | ((uint32_t)layer << 1) | (uint32_t)which;
+}
+enum : uint32_t { SITE_ORIGIN_XY = 0, SITE_ORIGIN_Z = 1, SITE_CONE = 2, SITE_WAVE = 3,
+                  SITE_LOSTKEY = 4, SITE_CONE_RETRY = 0x100 };
+
+struct PhiloxDraws {
+    uint2 key;
+    uint32_t ray_lo, ray_hi, stream;
+
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t stream_id, uint64_t ray) {
+        key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
+        stream = (uint32_t)stream_id;
+        ray_lo = (uint32_t)ray;
+        ray_hi = (uint32_t)(ray >> 32);
+    }
+    __device__ __forceinline__ uint4 raw(uint32_t site) const {
+        return philox4x32_10(make_uint4(ray_lo, ray_hi, site, stream), key);
+    }
+    __device__ __forceinline__ void pair(uint32_t site, double &a, double &b) const {
+        uint4 r = raw(site);
+        a = u01(r.x, r.y);
+        b = u01(r.z, r.w);
+    }
+    // ---- source sites
+    __device__ __forceinline__ void origin_uniform(double u[3]) const {
+        double d;
+        pair(SITE_ORIGIN_XY, u[0], u[1]);
+        pair(SITE_ORIGIN_Z, u[2], d);
+    }
+    __device__ __forceinline__ void origin_gauss(const double sig[3], double off[3]) const {
+        double a, b, c, d, z0, z1, z2, z3;
+        pair(SITE_ORIGIN_XY, a, b);
+        pair(SITE_ORIGIN_Z, c, d);
+        box_muller(a, b, z0, z1);
+        box_muller(c, d, z2, z3);
+        off[0] = sig[0] * z0; off[1] = sig[1] * z1; off[2] = sig[2] * z2;
+    }
+    __device__ __forceinline__ void cone(int attempt, double &a, double &b) const {
+        pair(attempt == 0 ? SITE_CONE : SITE_CONE_RETRY + (uint32_t)attempt, a, b);
+    }
+    __device__ __forceinline__ double wave_u() const { double a, b; pair(SITE_WAVE, a, b); return a; }
+    __device__ __forceinline__ double wave_z() const {
+        double a, b, z0, z1; pair(SITE_WAVE, a, b); box_muller(a, b, z0, z1); return z0;
+    }
+    __device__ __forceinline__ uint64_t lost_key() const {
+        uint4 r = raw(SITE_LOSTKEY);
+        return ((uint64_t)r.x << 32) | r.y;
+    }
+    // ---- optic sites
+    __device__ __forceinline__ double bragg_u(int k, int layer) const {
+        double a, b; pair(site_optic(k, layer, 0), a, b); return a;
+    }
+    __device__ __forceinline__ void mosaic_xy(int k, int layer, double s, double &x, double &y) const {
+        double a, b, z0, z1;
+        pair(site_optic(k, layer, 1), a, b);
+        box_muller(a, b, z0, z1);
+        x = s * z0; y = s * z1;
+    }
+};
+
+// draws recorded from the reference-order stream, scattered to full length
+struct InjectedDraws {
+    const XrtInject *inj;
+    uint64_t i, n;
+    __device__ __forceinline__ double bragg_u(int k, int layer) const {
+        return inj->u[k][(uint64_t)layer * n + i];
+    }
+    __device__ __forceinline__ void mosaic_xy(int k, int layer, double, double &x, double &y) const {
+        const double *p = inj->xy[k] + (uint64_t)layer * 2 * n;
+        x = p[i]; y = p[n + i];
+    }
+};
+
+struct SourceInjectedDraws {
+    const XrtSourceInject *inj;
+    uint64_t i, n;
+    __device__ __forceinline__ void origin_uniform(double u[3]) const {
+        u[0] = inj->origin[i]; u[1] = inj->origin[n + i]; u[2] = inj->origin[2 * n + i];
+    }
+    __device__ __forceinline__ void origin_gauss(const double *, double off[3]) const {
+        off[0] = inj->origin[i]; off[1] = inj->origin[n + i]; off[2] = inj->origin[2 * n + i];
+    }
+    __device__ __forceinline__ void cone(int, double &a, double &b) const { a = inj->cone[i]; b = inj->cone[n + i]; }
+    __device__ __forceinline__ double wave_u() const { return inj->wave[i]; }
+    __device__ __forceinline__ double wave_z() const { return inj->wave[i]; }
+};
+
+// ---------------------------------------------------------------------------
+// source: one ray from the draws  (reference _XicsrtSourceGeneric.py:198-393,
+// _XicsrtSourceFocused.py:35-44, _XicsrtPlasmaGeneric.py:286-345)
+
+template <uint32_t FT, class DR>
+__device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &dr, uint64_t index, Ray &r) {
+    V3 org = v3(s.origin);
+    double cos_spread = s.cone_par[0];
+    double wave_sigma = s.wave_par[1];
+    V3 vel = v3(s.velocity_c);
+    double ext0 = s.extent[0], ext1 = s.extent[1], ext2 = s.extent[2];
+
+    if constexpr ((FT & FT_SRC_EXT) != 0) {
+        if (s.kind == XRT_SRC_BUNDLES) {
+            // bundle of this ray: first b with bundle_end[b] > index
+            uint64_t lo = 0, hi = s.n_bundles - 1;
+            while (lo < hi) {
+                uint64_t mid = (lo + hi) >> 1;
+                if (__ldg(s.bundle_end + mid) > index) hi = mid; else lo = mid + 1;
+            }
+            const XrtBundle *b = s.bundles + lo;
+            org = v3(__ldg(&b->origin[0]), __ldg(&b->origin[1]), __ldg(&b->origin[2]));
+            cos_spread = __ldg(&b->cos_spread);
+            wave_sigma = __ldg(&b->wave_sigma);
+            vel = v3(__ldg(&b->velocity_c[0]), __ldg(&b->velocity_c[1]), __ldg(&b->velocity_c[2]));
+            ext0 = ext1 = ext2 = s.voxel_size;
+        }
+    }
+
+    // ---- origin (:229-255): three draws of U(-size/2, size/2), or N(0, sigma)
+    double off[3] = {0.0, 0.0, 0.0};
+    bool gauss = false;
+    if constexpr ((FT & FT_SRC_EXT) != 0) gauss = (s.spatial == XRT_SPATIAL_GAUSSIAN);
+    if (gauss) {
+        double sig[3] = {ext0, ext1, ext2};
+        dr.origin_gauss(sig, off);
+    } else if (ext0 != 0.0 || ext1 != 0.0 || ext2 != 0.0) {
+        double u[3];
+        dr.origin_uniform(u);
+        off[0] = -0.5 * ext0 + ext0 * u[0];
+        off[1] = -0.5 * ext1 + ext1 * u[1];
+        off[2] = -0.5 * ext2 + ext2 * u[2];
+    }
+    const double *R = s.orient;
+    r.o = v3(((org.x + off[0] * R[0]) + off[1] * R[3]) + off[2] * R[6],
+             ((org.y + off[0] * R[1]) + off[1] * R[4]) + off[2] * R[7],
+             ((org.z + off[0] * R[2]) + off[1] * R[5]) + off[2] * R[8]);
+
+    // ---- local cone vector (xicsrt_spread.py:80-294)
+    V3 l;
+    int cone = XRT_CONE_ISOTROPIC;
+    if constexpr ((FT & FT_SRC_EXT) != 0) cone = s.cone;
+    if (cone == XRT_CONE_ISOTROPIC) {
+        double a, b;
+        dr.cone(0, a, b);
+        double z = cos_spread + (1.0 - cos_spread) * a;
+        double phi = 0.0 + (2.0 * CUDART_PI - 0.0) * b;
+        double rho = sqrt(1.0 - z * z);
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        l = v3(rho * cs, rho * sn, z);
+    } else if (cone == XRT_CONE_ISOTROPIC_XY) {
+        // rejection from the enclosing circular cone (:130-196)
+        const double cm = s.cone_cos_max;
+        l = v3(0.0, 0.0, 1.0);
+        for (int attempt = 0; attempt < 100000; ++attempt) {
+            double a, b;
+            dr.cone(attempt, a, b);
+            double z = cm + (1.0 - cm) * a;
+            double phi = (2.0 * CUDART_PI) * b;
+            double rho = sqrt(1.0 - z * z);
+            double sn, cs;
+            sincos(phi, &sn, &cs);
+            double x = rho * cs, y = rho * sn;
+            double sx = x / sqrt(x * x + z * z);
+            double sy = y / sqrt(y * y + z * z);
+            l = v3(x, y, z);
+            if (sx > s.cone_par[0] && sx <= s.cone_par[1] && sy > s.cone_par[2] && sy <= s.cone_par[3]) break;
+        }
+    } else {
+        double a, b, a0, a1;
+        dr.cone(0, a, b);
+        if (cone == XRT_CONE_FLAT) {
+            double rr = sqrt(0.0 + (s.cone_par[0] - 0.0) * a);
+            a1 = (2.0 * CUDART_PI) * b;
+            a0 = atan(rr);
+        } else {
+            double x = s.cone_par[0] + (s.cone_par[1] - s.cone_par[0]) * a;
+            double y = s.cone_par[2] + (s.cone_par[3] - s.cone_par[2]) * b;
+            a0 = atan(sqrt(x * x + y * y));
+            a1 = atan2(y, x);
+        }
+        double s0, c0, s1, c1;
+        sincos(a0, &s0, &c0);
+        sincos(a1, &s1, &c1);
+        l = v3(c1 * s0, s1 * s0, c0);
+    }
+
+    // ---- cone axis and basis (:262-293): rows (o_2, o_1, axis)
+    V3 ax, o1, o2;
+    if (s.kind == XRT_SRC_FIXED_AXIS) {
+        // constant for every ray: precomputed on the host with the reference's formula
+        o2 = v3(s.axis_basis[0], s.axis_basis[1], s.axis_basis[2]);
+        o1 = v3(s.axis_basis[3], s.axis_basis[4], s.axis_basis[5]);
+        ax = v3(s.axis_basis[6], s.axis_basis[7], s.axis_basis[8]);
+    } else {
+        V3 t = v3(s.target) - r.o;
+        ax = t * (1.0 / sqrt(dot(t, t)));
+        V3 xa = v3(R[0], R[1], R[2]), za = v3(R[6], R[7], R[8]);
+        o1 = unit(cross(ax, xa) + cross(ax, za));
+        o2 = unit(cross(ax, o1));
+    }
+    r.d = v3(l.x * o2.x + l.y * o1.x + l.z * ax.x,
+             l.x * o2.y + l.y * o1.y + l.z * ax.y,
+             l.x * o2.z + l.y * o1.z + l.z * ax.z);
+
+    // ---- wavelength (:295-367)
+    double w;
+    if (s.wave == XRT_WAVE_NORMAL) {
+        w = s.wave_par[0] + wave_sigma * dr.wave_z();
+    } else if (s.wave == XRT_WAVE_CONST) {
+        w = s.wave_par[0];
+    } else if (s.wave == XRT_WAVE_UNIFORM) {
+        w = s.wave_par[0] + (s.wave_par[1] - s.wave_par[0]) * dr.wave_u();
+    } else {
+        double y = s.wave_par[1] + (s.wave_par[2] - s.wave_par[1]) * dr.wave_u();
+        w = interp_inside(y, s.table_cdf, s.table_x, s.n_table) + s.wave_par[0];
+    }
+    if (vel.x != 0.0 || vel.y != 0.0 || vel.z != 0.0) w *= 1.0 - dot(vel, r.d);
+    r.w = w;
+
+    // ---- source-level sightline filters (_XicsrtBundleFilterSightline.py:31-56)
+    r.alive = true;
+    if constexpr ((FT & FT_SRC_EXT) != 0) {
+        for (int f = 0; f < s.n_sightlines; ++f) {
+            const XrtSightline &sl = s.sightlines[f];
+            V3 l0 = v3(sl.origin) - r.o;
+            V3 axs = v3(sl.axis);
+            V3 perp = l0 - axs * dot(axs, l0);
+            r.alive = r.alive && (sl.radius >= sqrt(dot(perp, perp)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// analytic shapes: distance along the ray (NaN / false = no intersection)
+
+// _ShapePlane.py:32-53
+__device__ __forceinline__ bool hit_plane(const XrtOpticDesc &op, bool local, V3 o, V3 d, double &t) {
+    if (local) {
+        t = (0.0 - o.z) / d.z;
+    } else {
+        V3 z = v3(op.orient + 6);
+        t = dot(v3(op.origin) - o, z) / dot(d, z);
+    }
+    return t >= 0.0;
+}
+
+// _ShapeSphere.py:53-100 -- geometric solution; concave takes the larger root, no sign test
+__device__ __forceinline__ bool hit_sphere(const XrtOpticDesc &op, V3 o, V3 d, double &t) {
+    V3 L = v3(op.center) - o;
+    double tca = dot(L, d);
+    double dd = sqrt(dot(L, L) - tca * tca);
+    if (!(dd <= op.radius)) return false;
+    double thc = sqrt(op.radius * op.radius - dd * dd);
+    double t0 = tca - thc, t1 = tca + thc;
+    if (op.flags & XRT_F_CONVEX) t = (t0 < t1) ? t0 : t1;
+    else t = (t0 > t1) ? t0 : t1;
+    return true;
+}
+
+// _ShapeCylinder.py:52-109 -- axis = element x axis through `center`
+__device__ __forceinline__ bool hit_cylinder(const XrtOpticDesc &op, V3 o, V3 d, double &t) {
+    V3 va = v3(op.orient);
+    V3 dp = o - v3(op.center);
+    V3 A1 = d - va * dot(d, va);
+    V3 B1 = dp - va * dot(dp, va);
+    double A = dot(A1, A1);
+    double B = 2.0 * dot(A1, B1);
+    double C = dot(B1, B1) - op.radius * op.radius;
+    double dis = B * B - 4.0 * A * C;
+    if (!(dis >= 0.0)) return false;
+    double sq = sqrt(dis);
+    double t0 = (-B - sq) / (2.0 * A), t1 = (-B + sq) / (2.0 * A);
+    if (op.flags & XRT_F_CONVEX) t = (t0 < t1) ? t0 : t1;
+    else t = (t0 > t1) ? t0 : t1;
+    return true;
+}
+
+__device__ __forceinline__ double signed_cbrt(double x) { return cbrt(x); }
+
+// One real root of z^3 + p z^2 + r z + c (xicsrt_quartic.py:54-162, all_roots=False)
+__device__ __forceinline__ double resolvent_root(double p, double r, double c) {
+    const double third = 1.0 / 3.0;
+    double a13 = p * third;
+    double a2 = a13 * a13;
+    double f = third * r - a2;
+    double g = a13 * (2.0 * a2 - r) + c;
+    double h = 0.25 * g * g + f * f * f;
+    if (f == 0.0 && g == 0.0 && h == 0.0) return -signed_cbrt(c);
+    if (h <= 0.0) {
+        double j = sqrt(-f);
+        double k = acos(-0.5 * g / (j * j * j));
+        return 2.0 * j * cos(third * k) - a13;
+    }
+    double sh = sqrt(h);
+    return (signed_cbrt(-0.5 * g + sh) + signed_cbrt(-0.5 * g - sh)) - a13;
+}
+
+// _ShapeTorus.py:116-183 with xicsrt_quartic.py:165-207 in real arithmetic.
+// The reference keeps complex values and declares a slot "no hit" when its
+// imaginary part is non-zero; in real terms: s^2 = 2p + 2 z0 must be >= 0 (else
+// every slot is complex) and the slot's quadratic discriminant must be >= 0.
+// Slots 0,1 come from x^2 + s x + (z0 + t), slots 2,3 from x^2 - s x + (z0 - t),
+// each ordered (-sqrt, +sqrt); the optic takes slot `root_idx`.
+__device__ __forceinline__ bool hit_torus(const XrtOpticDesc &op, V3 o, V3 d, double &t) {
+    const double rmaj = op.torus_major, rmin = op.torus_minor;
+    V3 O = to_local(op.orient, o - v3(op.center));
+    V3 D = to_local(op.orient, d);
+    double OO = dot(O, O), OD = dot(O, D);
+    double rsq = rmaj * rmaj + rmin * rmin;
+    double rm2 = rmaj * rmaj;
+    // monic quartic t^4 + a t^3 + b t^2 + c t + e  (axis of the torus = local y)
+    double a = 4.0 * OD;
+    double b = 4.0 * OD * OD + 2.0 * OO - 2.0 * rsq + 4.0 * rm2 * D.y * D.y;
+    double c = 4.0 * OD * (OO - rsq) + 8.0 * rm2 * D.y * O.y;
+    double dm = rm2 - rmin * rmin;
+    double e = OO * OO - 2.0 * rsq * OO + 4.0 * rm2 * O.y * O.y + dm * dm;
+
+    double q4 = 0.25 * a;
+    double q42 = q4 * q4;
+    double p = 3.0 * q42 - 0.5 * b;
+    double q = a * q42 - b * q4 + 0.5 * c;
+    double r = 3.0 * q42 * q42 - b * q42 + c * q4 - e;
+    double z0 = resolvent_root(p, r, p * r - 0.5 * q * q);
+
+    double s2 = 2.0 * p + 2.0 * z0;
+    if (!(s2 >= 0.0)) return false;      // s imaginary (or NaN): all four slots complex
+    double s = sqrt(s2);
+    double tt = (s == 0.0) ? (z0 * z0 + r) : (-q / s);
+
+    const int idx = op.root_idx;
+    double half, cst;
+    if (idx < 2) { half = -0.5 * s; cst = z0 + tt; }
+    else { half = 0.5 * s; cst = z0 - tt; }
+    double disc = half * half - cst;
+    if (!(disc >= 0.0)) return false;
+    double sq = sqrt(disc);
+    double root = ((idx & 1) ? (half + sq) : (half - sq)) - q4;
+    t = root;
+    return isfinite(root) && root > 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// apertures (xicsrt_aperture.py:13-204): sequential fold over the list
+
+__device__ __forceinline__ bool aperture_inside(const XrtAperture &ap, double x, double y) {
+    double dx = x - ap.origin[0], dy = y - ap.origin[1];
+    switch (ap.shape) {
+    case XRT_AP_CIRCLE: return (dx * dx + dy * dy) < ap.size[0] * ap.size[0];
+    case XRT_AP_SQUARE: return (fabs(dx) < ap.size[0] / 2) && (fabs(dy) < ap.size[0] / 2);
+    case XRT_AP_RECTANGLE: return (fabs(dx) < ap.size[0] / 2) && (fabs(dy) < ap.size[1] / 2);
+    case XRT_AP_ELLIPSE: {
+        double ex = dx / ap.size[0], ey = dy / ap.size[1];   // full sizes as semi-axes (sic, :182)
+        return (ex * ex + ey * ey) < 1.0;
+    }
+    case XRT_AP_TRIANGLE: {
+        const double *v = ap.vert;   // p0 = (v0,v1) p1 = (v2,v3) p2 = (v4,v5)
+        double area = 0.5 * (-v[3] * v[4] + v[1] * (-v[2] + v[4]) + v[0] * (v[3] - v[5]) + v[2] * v[5]);
+        double k = 1.0 / (2.0 * area);
+        double a = k * (v[1] * v[4] - v[0] * v[5] + (v[5] - v[1]) * x + (v[0] - v[4]) * y);
+        double b = k * (v[0] * v[3] - v[1] * v[2] + (v[1] - v[3]) * x + (v[2] - v[0]) * y);
+        double c = 1.0 - a - b;
+        return (a >= 0.0) && (b >= 0.0) && (c >= 0.0);
+    }
+    default: return true;
+    }
+}
+
+__device__ __forceinline__ bool aperture_fold(const XrtOpticDesc &op, double x, double y) {
+    bool acc = true;
+    for (int i = 0; i < op.n_aperture; ++i) {
+        const XrtAperture ap = op.apertures[i];
+        bool test = aperture_inside(ap, x, y);
+        switch (ap.logic) {
+        case XRT_LOGIC_AND: acc = acc && test; break;
+        case XRT_LOGIC_NOT: acc = acc && !test; break;
+        case XRT_LOGIC_OR: acc = acc || test; break;
+        case XRT_LOGIC_NAND: acc = !(acc && test); break;
+        case XRT_LOGIC_NOR: acc = !(acc || test); break;
+        case XRT_LOGIC_XOR: acc = acc != test; break;
+        default: acc = !(acc != test); break;   // XNOR
+        }
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------
+// Bragg reflection test (_InteractCrystal.py:96-196)
+
+__device__ __forceinline__ void bragg_angles(const XrtOpticDesc &op, const Ray &r, V3 n, double &tb, double &ti) {
+    tb = asin(r.w / op.two_d);
+    double dt = fabs(dot(r.d, v3(-n.x, -n.y, -n.z)));
+    ti = (CUDART_PI / 2.0) - acos(dt / sqrt(dot(r.d, r.d)));
+}
+
+template <uint32_t FT>
+__device__ __forceinline__ double rocking_probability(const XrtOpticDesc &op, double ti, double tb) {
+    double dth = ti - tb;
+    double p;
+    if (op.rocking_type == XRT_ROCK_GAUSS) {
+        // sigma = fwhm / (2 sqrt(2 ln 2)); p = exp(-dth^2 / (2 sigma^2))
+        p = exp(-(dth * dth) / op.rock_two_sigma2);
+    } else if (op.rocking_type == XRT_ROCK_STEP) {
+        p = (fabs(dth) <= op.rocking_fwhm / 2.0) ? 1.0 : 0.0;
+    } else {
+        p = 0.0;
+        if constexpr ((FT & FT_ROCKTAB) != 0) {
+            int n = op.n_rock;
+            if (dth >= __ldg(op.rock_dtheta) && dth <= __ldg(op.rock_dtheta + n - 1)) {
+                double sg = interp_inside(dth, op.rock_dtheta, op.rock_s, n);
+                double pi = interp_inside(dth, op.rock_dtheta, op.rock_p, n);
+                p = op.rocking_mix * sg + (1.0 - op.rocking_mix) * pi;
+            }
+        }
+    }
+    return p * op.reflectivity;
+}
+
+// _InteractMirror.py:29-42
+__device__ __forceinline__ void reflect(Ray &r, V3 n) {
+    double k = 2.0 * dot(r.d, n);
+    r.d = v3(r.d.x - k * n.x, r.d.y - k * n.y, r.d.z - k * n.z);
+}
+
+// ---------------------------------------------------------------------------
+// surface normals at the intersection point X
+
+// _ShapeSphere.py:102-106
+__device__ __forceinline__ V3 normal_sphere(const XrtOpticDesc &op, V3 X) {
+    V3 v = v3(op.center) - X;
+    return v * (1.0 / sqrt(dot(v, v)));
+}
+
+// _ShapeCylinder.py:111-133 -- toward the point of the axis at the same x
+__device__ __forceinline__ V3 normal_cylinder(const XrtOpticDesc &op, V3 X) {
+    V3 pa = v3(op.center), va = v3(op.orient);
+    double s = dot(pa - X, va);
+    V3 v = (pa - va * s) - X;
+    return v * (1.0 / sqrt(dot(v, v)));
+}
+
+// _ShapeTorus.py:186-216 -- away from the nearest point of the axis circle
+__device__ __forceinline__ V3 normal_torus(const XrtOpticDesc &op, V3 X) {
+    V3 C = v3(op.center), ya = v3(op.orient + 3);
+    V3 p = X - C;
+    p = p - ya * dot(p, ya);
+    V3 Q = C + p * (op.torus_major / sqrt(dot(p, p)));
+    V3 v = X - Q;
+    return v * (1.0 / sqrt(dot(v, v)));
+}
+
+// ---------------------------------------------------------------------------
+// mosaic crystallite normal about the nominal normal n
+// (_InteractMosaicCrystal.py:109-139, xicsrt_spread.py:297-339)
+
+__device__ __forceinline__ V3 mosaic_normal(V3 n, double x, double y) {
+    double inv = 1.0 / sqrt(x * x + y * y + 1.0);
+    double lx = x * inv, ly = y * inv, lz = inv;
+    // R0 = n x [1,0,0] + n x [0,0,1];  R1 = n x R0
+    V3 r0 = v3(0.0 + n.y, n.z - n.x, -n.y + 0.0);
+    r0 = r0 * (1.0 / sqrt(dot(r0, r0)));
+    V3 r1 = cross(n, r0);
+    r1 = r1 * (1.0 / sqrt(dot(r1, r1)));
+    return v3(lx * r0.x + ly * r1.x + lz * n.x,
+              lx * r0.y + ly * r1.y + lz * n.y,
+              lx * r0.z + ly * r1.z + lz * n.z);
+}
+
+// ---------------------------------------------------------------------------
+// pixel binning (_TraceObject.py:234-293): channel = rint(local / pixel + (npix-1)/2)
+
+__device__ __forceinline__ bool pixel_index(const XrtOpticDesc &op, V3 o, uint32_t &idx) {
+    V3 pl = to_local(op.orient, o - v3(op.origin));
+    double cx = rint(pl.x / op.pixel_size + 0.5 * (double)(op.npix[0] - 1));
+    double cy = rint(pl.y / op.pixel_size + 0.5 * (double)(op.npix[1] - 1));
+    if (!(cx >= 0.0 && cx < (double)op.npix[0] && cy >= 0.0 && cy < (double)op.npix[1])) return false;
+    idx = (uint32_t)cx * (uint32_t)op.npix[1] + (uint32_t)cy;
+    return true;
+}
+
+}  // namespace xrt
+
+#include "xrt_mesh.cuh"
+
+namespace xrt {
+
+// A ray that is already lost still passes through trace_global of the following optics:
+// its origin is overwritten by the (NaN) intersection point and, for optics traced in
+// local coordinates, its direction is transformed there and back.
+template <uint32_t FT>
+__device__ __forceinline__ void pass_lost_ray(const XrtOpticDesc &op, Ray &r) {
+    r.o = nan3();
+    if constexpr ((FT & FT_LOCAL) != 0) {
+        if (op.flags & XRT_F_TRACE_LOCAL) r.d = to_external(op.orient, to_local(op.orient, r.d));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// one optic, start to end (_TraceObject.py:135-178).  `r` must be alive on entry.
+// On exit: r.alive = survived; r.o = intersection point (NaN when the surface was
+// missed), r.d reflected only for surviving rays -- exactly the state the
+// reference's history holds for this element.
+
+template <uint32_t FT, class DR>
+__device__ __forceinline__ void trace_optic(const XrtOpticDesc &op, int k, const DR &dr, Ray &r) {
+    V3 o = r.o, d = r.d;
+    bool local = false;
+    if constexpr ((FT & FT_LOCAL) != 0) {
+        local = (op.flags & XRT_F_TRACE_LOCAL) != 0;
+        if (local) {   // _GeometryObject.py:127-141
+            o = to_local(op.orient, o - v3(op.origin));
+            d = to_local(op.orient, d);
+        }
+    }
+
+    // ---- intersect: distance, location, normal
+    V3 X, n;
+    bool ok;
+    bool analytic = true;
+    if constexpr ((FT & FT_MESH) != 0) {
+        if (op.shape == XRT_SHAPE_MESH) {
+            analytic = false;
+            ok = mesh_intersect(op, o, d, X, n);
+        }
+    }
+    if (analytic) {
+        double t = 0.0;
+        const int shape = op.shape;
+        if (shape == XRT_SHAPE_PLANE) ok = hit_plane(op, local, o, d, t);
+        else if (shape == XRT_SHAPE_SPHERE) ok = hit_sphere(op, o, d, t);
+        else {
+            ok = false;
+            if constexpr ((FT & FT_CYL) != 0) { if (shape == XRT_SHAPE_CYLINDER) ok = hit_cylinder(op, o, d, t); }
+            if constexpr ((FT & FT_TORUS) != 0) { if (shape == XRT_SHAPE_TORUS) ok = hit_torus(op, o, d, t); }
+        }
+        if (ok) {
+            X = v3(o.x + d.x * t, o.y + d.y * t, o.z + d.z * t);   // _ShapeObject.py:69-81
+            // the plane normal is the element's (global) zaxis even when tracing in local
+            // coordinates -- _ShapePlane.py:55-62 does not transform it; replicated.
+            if (shape == XRT_SHAPE_PLANE) n = v3(op.orient + 6);
+            else if (shape == XRT_SHAPE_SPHERE) n = normal_sphere(op, X);
+            else {
+                n = v3(0.0, 0.0, 1.0);
+                if constexpr ((FT & FT_CYL) != 0) { if (shape == XRT_SHAPE_CYLINDER) n = normal_cylinder(op, X); }
+                if constexpr ((FT & FT_TORUS) != 0) { if (shape == XRT_SHAPE_TORUS) n = normal_torus(op, X); }
+            }
+        }
+    }
+    if (!ok) {
+        r.alive = false;
+        r.o = nan3();
+        // ray_to_external acts on every ray, hit or not (_TraceObject.py:135-155): the
+        // direction makes the local round trip (visible when the axes are not exactly unit)
+        if constexpr ((FT & FT_LOCAL) != 0) { if (local) r.d = to_external(op.orient, d); }
+        return;
+    }
+
+    // ---- bounds (_TraceObject.py:180-232): strict |x| < size/2, then apertures
+    V3 Xl = local ? X : to_local(op.orient, X - v3(op.origin));
+    bool in = true;
+    if (op.flags & XRT_F_CHECK_SIZE) {
+        if (op.flags & XRT_F_HAS_XSIZE) in = in && (fabs(Xl.x) < op.half_size[0]);
+        if (op.flags & XRT_F_HAS_YSIZE) in = in && (fabs(Xl.y) < op.half_size[1]);
+        if (op.flags & XRT_F_HAS_ZSIZE) in = in && (fabs(Xl.z) < op.half_size[2]);
+    }
+    if constexpr ((FT & FT_APERTURE) != 0) {
+        if (in && (op.flags & XRT_F_CHECK_APERTURE) && op.n_aperture > 0) in = aperture_fold(op, Xl.x, Xl.y);
+    }
+
+    // ---- interaction
+    bool alive = in;
+    if (in) {
+        const int ia = op.interact;
+        if (ia == XRT_INTERACT_MIRROR) {
+            Ray q; q.d = d; reflect(q, n); d = q.d;
+        } else if (ia == XRT_INTERACT_CRYSTAL) {
+            bool pass = true;
+            if (op.flags & XRT_F_CHECK_BRAGG) {
+                Ray q; q.d = d; q.w = r.w;
+                double tb, ti;
+                bragg_angles(op, q, n, tb, ti);
+                double p = rocking_probability<FT>(op, ti, tb);
+                pass = (p >= dr.bragg_u(k, 0));
+            }
+            if (pass) { Ray q; q.d = d; reflect(q, n); d = q.d; }
+            alive = pass;
+        } else if (ia == XRT_INTERACT_MOSAIC) {
+            if constexpr ((FT & FT_MOSAIC) != 0) {
+                Ray q; q.d = d; q.w = r.w;
+                if (op.flags & XRT_F_MOSAIC_CUTOFF) {
+                    double tb, ti;
+                    bragg_angles(op, q, n, tb, ti);
+                    alive = fabs(tb - ti) < op.mosaic_angle_cut;
+                }
+                if (alive) {
+                    bool done = false;
+                    for (int layer = 0; layer < op.mosaic_depth && !done; ++layer) {
+                        double x, y;
+                        dr.mosaic_xy(k, layer, op.mosaic_sin_sigma, x, y);
+                        V3 nm = mosaic_normal(n, x, y);
+                        bool pass = true;
+                        if (op.flags & XRT_F_CHECK_BRAGG) {
+                            double tb, ti;
+                            bragg_angles(op, q, nm, tb, ti);
+                            double p = rocking_probability<FT>(op, ti, tb);
+                            pass = (p >= dr.bragg_u(k, layer));
+                        }
+                        if (pass) { reflect(q, nm); d = q.d; done = true; }
+                    }
+                    alive = done;
+                }
+            } else {
+                alive = false;
+            }
+        }
+    }
+
+    // ---- back to external coordinates (_GeometryObject.py:113-125)
+    if constexpr ((FT & FT_LOCAL) != 0) {
+        if (local) {
+            X = to_external(op.orient, X) + v3(op.origin);
+            d = to_external(op.orient, d);
+        }
+    }
+    r.o = X;
+    r.d = d;
+    r.alive = alive;
+}
+
+}  // namespace xrt
