@@ -1,0 +1,176 @@
+# -*- coding: utf-8 -*-
+"""
+Host-side logic that needs no GPU: config semantics, the class_name registry,
+scene flattening, ray-id sharding, result combination and result files.
+"""
+import copy
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import scenes
+from xicsrt_b200 import _driver, _lib as L, config as xconfig, elements, io as xio, registry, scene as xscene
+
+
+def test_registry_covers_the_reference_class_names():
+    optics = ['XicsrtOpticAperture', 'XicsrtOpticDetector', 'XicsrtOpticPlanarMirror', 'XicsrtOpticSphericalMirror',
+              'XicsrtOpticCylindricalMirror', 'XicsrtOpticMeshMirror', 'XicsrtOpticPlanarCrystal',
+              'XicsrtOpticSphericalCrystal', 'XicsrtOpticCylindricalCrystal', 'XicsrtOpticToroidalCrystal',
+              'XicsrtOpticMeshCrystal', 'XicsrtOpticMeshSphericalCrystal', 'XicsrtOpticMeshCylindricalCrystal',
+              'XicsrtOpticMeshToroidalCrystal', 'XicsrtOpticPlanarMosaicCrystal',
+              'XicsrtOpticSphericalMosaicCrystal', 'XicsrtOpticMeshMosaicCrystal']
+    sources = ['XicsrtSourceGeneric', 'XicsrtSourceDirected', 'XicsrtSourceFocused', 'XicsrtPlasmaGeneric',
+               'XicsrtPlasmaCubic', 'XicsrtPlasmaToroidal', 'XicsrtPlasmaToroidalDatafile']
+    for name in optics:
+        assert registry.find(name)[0] == 'optics'
+        assert registry.defaults(name)['class_name'] == name
+    for name in sources:
+        assert registry.find(name)[0] == 'sources'
+    for name in ('XicsrtBundleFilter', 'XicsrtBundleFilterSightline'):
+        assert registry.find(name)[0] == 'filters'
+    with pytest.raises(NotImplementedError):
+        registry.find('XicsrtPlasmaCylindrical')
+    with pytest.raises(Exception, match='Could not find'):
+        registry.find('XicsrtOpticCrystalSpherical')     # the stale name of examples/example_01.py:39
+
+
+def test_strict_config_rejects_unknown_keys():
+    cfg = scenes.get('sphere')
+    cfg['optics']['crystal']['radius_of_curvature'] = 2.0
+    with pytest.raises(Exception, match='User option not recognized'):
+        oracle.raytrace(cfg)
+    cfg['general']['strict_config_check'] = False
+    full = xconfig.get_config(xconfig.to_numpy(cfg))
+    xscene.prepare(full)
+
+
+def test_default_axes_and_orthogonality_check():
+    _, p = elements.prepare_optic({'class_name': 'XicsrtOpticDetector', 'zaxis': [0.0, 0.0, 1.0]})
+    assert np.array_equal(p['xaxis'], [1.0, 0.0, 0.0])
+    _, p = elements.prepare_optic({'class_name': 'XicsrtOpticDetector', 'zaxis': [0.0, 1.0, 0.0]})
+    assert np.allclose(p['xaxis'], [-1.0, 0.0, 0.0])
+    assert np.allclose(p['orientation'][1], np.cross(p['zaxis'], p['xaxis']))
+    with pytest.raises(ValueError, match='not orthogonal'):
+        elements.prepare_optic({'class_name': 'XicsrtOpticDetector', 'zaxis': [0, 0, 1], 'xaxis': [0, 0.1, 1]})
+
+
+def flat(name):
+    cfg = xconfig.get_config(xconfig.to_numpy(scenes.get(name)))
+    _, sname, sparam, sfilters, optics = xscene.prepare(cfg)
+    return xscene.flatten(sname, sparam, sfilters, optics) + (optics,)
+
+
+def test_flatten_spectrometer_constants():
+    desc, layout, keep, optics = flat('sphere')
+    assert desc.n_optics == 2 and layout.n_rays == 10000
+    c, d = desc.optics[0], desc.optics[1]
+    assert c.shape == L.SHAPE['sphere'] and c.interact == L.INTERACT['crystal']
+    assert c.flags & L.F_CHECK_BRAGG and c.flags & L.F_IMAGE and not (c.flags & L.F_CONVEX)
+    assert c.two_d == 2 * 2.45676
+    sigma = 48.070e-6 / (2 * np.sqrt(2 * np.log(2)))
+    assert c.rock_two_sigma2 == 2 * sigma**2
+    assert np.allclose(list(c.center), np.array([0.0, 0.0, 0.80374151]) + np.array([0.0, 0.59497864, -0.80374151]))
+    assert (c.npix[0], c.npix[1], d.npix[0], d.npix[1]) == (100, 100, 100, 50)
+    assert c.image_offset == 0 and d.image_offset == 10000 and layout.n_pixels == 15000
+    assert list(c.half_size)[:2] == [0.1, 0.1]
+    src = desc.source
+    assert src.kind == L.SRC_FIXED_AXIS and src.wave == L.WAVE['normal'] and src.cone == L.CONE['isotropic']
+    assert src.cone_par[0] == np.cos(np.radians(10.0))
+    assert abs(src.wave_par[1] - 6.474e-4) < 1e-6          # Doppler sigma of SURVEY.md section 8d
+    basis = np.array(list(src.axis_basis)).reshape(3, 3)
+    assert np.allclose(basis @ basis.T, np.eye(3), atol=1e-14)
+
+
+def test_flatten_variants():
+    desc, _, keep, _ = flat('sphere_voigt')
+    assert desc.source.wave == L.WAVE['table'] and desc.source.n_table == 1000
+    desc, _, keep, _ = flat('sphere_step_box')
+    assert desc.source.kind == L.SRC_FOCUSED and desc.source.wave == L.WAVE['uniform']
+    assert desc.optics[0].rocking_type == L.ROCK['step'] and desc.optics[0].reflectivity == 0.8
+    assert any(v != 0.0 for v in desc.source.velocity_c)
+    desc, _, keep, _ = flat('torus_ft')
+    assert desc.optics[0].root_idx == 2 and desc.optics[0].torus_major == pytest.approx(1.2)
+    desc, _, keep, _ = flat('mosaic_sphere_cutoff')
+    assert desc.optics[0].flags & L.F_MOSAIC_CUTOFF and desc.optics[0].mosaic_depth == 5
+    desc, _, keep, _ = flat('apertures')
+    assert desc.optics[0].n_aperture == 8 and desc.optics[1].n_aperture == 1
+    ap = desc.optics[0].apertures
+    assert ap[1].shape == L.AP_SHAPE['ellipse'] and ap[1].logic == L.AP_LOGIC['not']
+    assert ap[4].shape == L.AP_SHAPE['triangle'] and list(ap[4].vert)[:2] == [-0.01, 0.03]
+    desc, _, keep, _ = flat('local_frames')
+    assert desc.optics[0].flags & L.F_TRACE_LOCAL and desc.optics[0].flags & L.F_HAS_ZSIZE
+
+
+def test_check_bragg_uses_identity_like_the_reference():
+    cfg = scenes.get('sphere')
+    cfg['optics']['crystal']['check_bragg'] = False
+    desc, *_ = xscene.flatten(*xscene.prepare(xconfig.get_config(xconfig.to_numpy(cfg)))[1:])
+    assert not (desc.optics[0].flags & L.F_CHECK_BRAGG)
+
+
+@pytest.mark.parametrize('n,world', [(10, 1), (10, 3), (1000000007, 8), (5, 8), (0, 4)])
+def test_shard_ranges_partition_the_ray_ids(n, world):
+    pieces = [_driver.shard_range(n, r, world) for r in range(world)]
+    assert pieces[0][0] == 0
+    for (b0, c0), (b1, _) in zip(pieces, pieces[1:]):
+        assert b0 + c0 == b1
+    assert pieces[-1][0] + pieces[-1][1] == n
+    counts = [c for _, c in pieces]
+    assert max(counts) - min(counts) <= 1
+
+
+def test_combine_matches_oracle_combine():
+    cfg = scenes.get('two_iter_two_runs')
+    res = oracle.raytrace(cfg)
+    # split it back into per-run results and recombine with the product's combine
+    runs = [oracle.raytrace_single(c, _internal=True) for c in oracle.driver._run_configs(scenes.get('two_iter_two_runs'))[1]]
+    got = _driver.combine_raytrace(runs)
+    for name in res['total']['meta']:
+        assert got['total']['meta'][name]['num_out'] == res['total']['meta'][name]['num_out']
+        if res['total']['image'].get(name) is not None:
+            assert np.array_equal(got['total']['image'][name], res['total']['image'][name])
+        for kind in ('found', 'lost'):
+            for key in _driver.RAY_KEYS:
+                assert np.array_equal(got[kind]['history'][name][key], res[kind]['history'][name][key], equal_nan=True)
+
+
+def test_run_seeds_are_cumulative():
+    cfg = xconfig.get_config(scenes.get('sphere'))
+    cfg['general']['number_of_runs'] = 4
+    cfg['general']['random_seed'] = 5
+    _, runs = oracle.driver._run_configs(cfg)
+    assert [r['general']['random_seed'] for r in runs] == [5, 6, 8, 11]
+    assert [r['general']['output_run_suffix'] for r in runs] == ['0000', '0001', '0002', '0003']
+
+
+@pytest.mark.parametrize('ext', ['.json', '.pkl'])
+def test_results_files_round_trip(tmp_path, ext):
+    cfg = scenes.get('sphere')
+    cfg['sources']['source']['intensity'] = 500
+    res = oracle.raytrace(cfg)
+    res['config']['general'].update({'output_path': str(tmp_path), 'results_ext': ext, 'output_suffix': 'x'})
+    xio.save_results(res)
+    path = xio.generate_filename(res['config'], 'results')
+    assert os.path.basename(path) == 'xicsrt_results_x' + ext
+    back = xio.load_results(config=res['config'])
+    assert back['total']['meta']['detector']['num_out'] == res['total']['meta']['detector']['num_out']
+    assert np.array_equal(np.asarray(back['total']['image']['detector']), res['total']['image']['detector'])
+    assert np.array_equal(np.asarray(back['found']['history']['crystal']['origin']),
+                          res['found']['history']['crystal']['origin'])
+    with pytest.raises(FileExistsError):
+        xio.save_results(res)
+
+
+def test_images_are_saved_rotated(tmp_path):
+    from PIL import Image
+    cfg = scenes.get('sphere')
+    cfg['sources']['source']['intensity'] = 2000
+    res = oracle.raytrace(cfg)
+    res['config']['general'].update({'output_path': str(tmp_path)})
+    xio.save_images(res)
+    img = np.array(Image.open(tmp_path / 'xicsrt_detector.tif'))
+    assert img.shape == (50, 100)
+    assert np.array_equal(img, np.rot90(res['total']['image']['detector']))

@@ -54,6 +54,17 @@ def shard_range(n, rank, world):
     return begin, end - begin
 
 
+def allreduce_packed(packed):
+    """
+    The one data-path collective of a multi-GPU iteration: sum of the packed int64 buffer
+    ``[counts | image_0 | image_1 | ...]`` over ranks (NCCL over NVLink on the GPUs; gloo in
+    the CPU tests).  Integer sums, so the result is independent of the reduction order.
+    """
+    import torch.distributed as dist
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    return packed
+
+
 class HostRandom:
     """Host-side draws (Poisson ray counts, plasma bundle centres): numpy Philox keyed by the run seed."""
 
@@ -177,8 +188,7 @@ class Tracer:
     def allreduce(self):
         """Sum counters + images over ranks (one collective on the packed buffer)."""
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.packed, op=dist.ReduceOp.SUM)
+            allreduce_packed(self.packed)
 
     def select_ids(self, stream_id, max_lost, keep_images=True):
         """

@@ -515,9 +515,9 @@ extern "C" int xrt_trace_history(XrtScene *s, uint64_t seed, uint64_t stream_id,
 extern "C" int xrt_trace_injected(XrtScene *s, const XrtRaysIn *rays, const XrtInject *draws, uint64_t n,
                                   const XrtOutputs *out, const XrtHistory *hist, void *stream) {
     if (!s || !rays) return fail(XRT_EINVAL, "null argument");
+    if (n == 0) return XRT_OK;
     if (!rays->origin || !rays->direction || !rays->wavelength || !rays->mask)
         return fail(XRT_EINVAL, "incomplete ray input");
-    if (n == 0) return XRT_OK;
     XrtInject inj = {};
     if (draws) inj = *draws;
     for (int k = 0; k < s->dev.n_optics; ++k) {
