@@ -132,6 +132,7 @@ typedef struct XrtOpticDesc {
     int32_t root_idx;        /* quartic solver slot (_ShapeTorus.py:72-85)                       */
     int32_t mosaic_depth;
     double two_d;            /* 2 * crystal_spacing                                              */
+    double inv_two_d;        /* 1 / two_d (sin(theta_B) = wavelength * inv_two_d)                */
     double reflectivity;
     double rocking_fwhm;
     double rock_two_sigma2;  /* gaussian: 2 sigma^2 with sigma = fwhm / (2 sqrt(2 ln 2))         */

@@ -30,93 +30,274 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // ---------------------------------------------------------------------------
 // fused kernel
+//
+// Each warp works through its share of the ray ids in three stages and re-packs the
+// survivors between them in per-warp shared-memory queues (ballot + popc prefix sums), so
+// that every stage runs with (nearly) all 32 lanes busy although ~48 % of the rays of a
+// typical spectrometer miss the crystal and ~98 % of the rest fail the Bragg test:
+//
+//   stage A  all rays     source origin + direction, optics before the split optic, geometry
+//                         (intersect + bounds) of the split optic           -> queue 1
+//   stage B  queue 1      wavelength (drawn here when it does not depend on the source
+//                         direction: Philox is counter based), interaction of the split
+//                         optic (Bragg / mosaic / mirror), its image          -> queue 2
+//   stage C  queue 2      the remaining optics, images, found list
+//
+// The split optic is the first crystal of the train (0 if there is none).  SPLIT >= 0 makes
+// its index a compile-time constant, so its parameters are fetched from the constant bank at
+// fixed offsets (uniform loads) instead of register-indexed ones.  Warps never wait for one
+// another: only __syncwarp and warp-uniform queue counters.
 
+constexpr int kQ1Cap = 64;     // stage A pushes <= 32 per pass, stage B pops 32 when >= 32 are queued
+constexpr int kQ2Cap = 64;     // stage B pushes <= 32 per pass, stage C pops 32 when >= 32 are queued
+constexpr int kQ2Planes = 8;   // id, origin, direction, wavelength
+
+template <uint32_t FT> __host__ __device__ constexpr int q1_planes() {
+    // id, intersection point, direction [, wavelength when it can be eager] [, normal for mesh shapes]
+    return 7 + (FT != 0 ? 1 : 0) + ((FT & FT_MESH) != 0 ? 3 : 0);
+}
+template <uint32_t FT> __host__ __device__ constexpr int warp_queue_doubles() {
+    return q1_planes<FT>() * kQ1Cap + kQ2Planes * kQ2Cap;
+}
+
+struct WarpCtx {
+    unsigned lane, lt_mask;
+    unsigned long long *s_cnt;
+};
+
+__device__ __forceinline__ void count_alive(const WarpCtx &c, int elem, bool alive) {
+    unsigned m = __ballot_sync(kFull, alive);
+    if (c.lane == 0 && m) atomicAdd(&c.s_cnt[elem], (unsigned long long)__popc(m));
+}
+
+// pixel hit: one atomic per distinct pixel among the calling lanes
+__device__ __forceinline__ void add_pixel(const XrtOutputs &out, const XrtOpticDesc &op, const Ray &r, unsigned lt_mask) {
+    uint32_t pix;
+    if (pixel_index(op, r.o, pix)) {
+        unsigned act = __activemask();
+        unsigned same = __match_any_sync(act, pix);
+        if ((same & lt_mask) == 0)
+            atomicAdd((unsigned long long *)(out.images + op.image_offset + pix), (unsigned long long)__popc(same));
+    }
+}
+
+// found list: ballot + prefix-sum compaction, one atomic per warp (all 32 lanes call this)
+__device__ __forceinline__ void emit_found(const XrtOutputs &out, const WarpCtx &c, bool found, uint64_t id) {
+    if (!out.found_count) return;
+    unsigned m = __ballot_sync(kFull, found);
+    if (!m) return;
+    unsigned long long off = 0;
+    if (c.lane == 0) off = atomicAdd((unsigned long long *)out.found_count, (unsigned long long)__popc(m));
+    off = __shfl_sync(kFull, off, 0);
+    if (found && out.found_ids) {
+        unsigned long long slot = off + __popc(m & c.lt_mask);
+        if (slot < out.found_capacity) out.found_ids[slot] = id;
+    }
+}
+
+// lost sample: a lost ray is kept when its 64-bit Philox key is below the threshold
+__device__ __forceinline__ void emit_lost(const XrtOutputs &out, const WarpCtx &c, const PhiloxDraws &dr, bool lost,
+                                          uint64_t id) {
+    if (!out.lost_count) return;
+    bool keep = false;
+    uint64_t key = 0;
+    if (lost) {
+        key = dr.lost_key();
+        keep = key < out.lost_threshold;
+    }
+    unsigned m = __ballot_sync(kFull, keep);
+    if (!m) return;
+    unsigned long long off = 0;
+    if (c.lane == 0) off = atomicAdd((unsigned long long *)out.lost_count, (unsigned long long)__popc(m));
+    off = __shfl_sync(kFull, off, 0);
+    if (keep && out.lost_ids) {
+        unsigned long long slot = off + __popc(m & c.lt_mask);
+        if (slot < out.lost_capacity) {
+            out.lost_ids[slot] = id;
+            if (out.lost_keys) out.lost_keys[slot] = key;
+        }
+    }
+}
+
+// ---- stage C: the optics after the split optic, for the `cnt` rays in queue 2
 template <uint32_t FT>
+__device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs &out, const WarpCtx &c, int split,
+                                        uint64_t seed, uint64_t stream_id, const double *q2, int first, int cnt) {
+    const bool active = (int)c.lane < cnt;
+    Ray r;
+    r.alive = false;
+    uint64_t id = 0;
+    PhiloxDraws dr;
+    if (active) {
+        const double *p = q2 + first + c.lane;
+        id = (uint64_t)__double_as_longlong(p[0]);
+        r.o = v3(p[1 * kQ2Cap], p[2 * kQ2Cap], p[3 * kQ2Cap]);
+        r.d = v3(p[4 * kQ2Cap], p[5 * kQ2Cap], p[6 * kQ2Cap]);
+        r.w = p[7 * kQ2Cap];
+        r.alive = true;
+    }
+    __syncwarp();
+    dr.init(seed, stream_id, id);
+    const int nopt = sc.n_optics;
+    for (int k = split + 1; k < nopt; ++k) {
+        const XrtOpticDesc &op = sc.optics[k];
+        if (r.alive) {
+            trace_optic<FT>(op, k, dr, r);
+            if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
+        }
+        count_alive(c, k + 1, r.alive);
+    }
+    emit_found(out, c, r.alive, id);
+    emit_lost(out, c, dr, active && !r.alive, id);
+}
+
+// ---- stage B: interaction of the split optic for `cnt` rays popped from queue 1
+template <uint32_t FT>
+__device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
+                                        const WarpCtx &c, int split, bool lazy, uint64_t seed, uint64_t stream_id,
+                                        const double *q1, int first, int cnt, double *q2, int &n2) {
+    constexpr int P = kQ1Cap;
+    const bool active = (int)c.lane < cnt;
+    Ray r;
+    r.alive = false;
+    r.w = 0.0;
+    V3 n = v3(0.0, 0.0, 1.0);
+    uint64_t id = 0;
+    if (active) {
+        const double *p = q1 + first + c.lane;
+        id = (uint64_t)__double_as_longlong(p[0]);
+        r.o = v3(p[1 * P], p[2 * P], p[3 * P]);
+        r.d = v3(p[4 * P], p[5 * P], p[6 * P]);
+        if constexpr (FT != 0) r.w = p[7 * P];
+        if constexpr ((FT & FT_MESH) != 0) n = v3(p[8 * P], p[9 * P], p[10 * P]);
+    }
+    __syncwarp();
+    PhiloxDraws dr;
+    dr.init(seed, stream_id, id);
+    if (active) {
+        if (lazy) {
+            SrcLocal L;
+            source_local<0>(sc.source, id, L);
+            r.w = generate_wavelength(sc.source, L, dr, r.d);
+        }
+        bool analytic = true;
+        if constexpr ((FT & FT_MESH) != 0) analytic = ops.shape != XRT_SHAPE_MESH;
+        if (analytic) n = analytic_normal<FT>(ops, r.o);
+        optic_interact<FT>(ops, split, dr, r, n);
+        if (r.alive && (ops.flags & XRT_F_IMAGE) && out.images) add_pixel(out, ops, r, c.lt_mask);
+    }
+    count_alive(c, split + 1, r.alive);
+    emit_lost(out, c, dr, active && !r.alive, id);
+
+    if (split + 1 >= sc.n_optics) {        // the split optic is the last one: survivors are found
+        emit_found(out, c, r.alive, id);
+        return;
+    }
+    const unsigned m = __ballot_sync(kFull, r.alive);     // the caller keeps n2 <= kQ2Cap - 32
+    if (r.alive) {
+        double *p = q2 + n2 + __popc(m & c.lt_mask);
+        p[0] = __longlong_as_double((long long)id);
+        p[1 * kQ2Cap] = r.o.x; p[2 * kQ2Cap] = r.o.y; p[3 * kQ2Cap] = r.o.z;
+        p[4 * kQ2Cap] = r.d.x; p[5 * kQ2Cap] = r.d.y; p[6 * kQ2Cap] = r.d.z;
+        p[7 * kQ2Cap] = r.w;
+    }
+    n2 += __popc(m);
+    __syncwarp();
+}
+
+template <uint32_t FT, int SPLIT>
 __global__ void __launch_bounds__(kBlock)
 k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
-        const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out) {
+        const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const int split_rt,
+        const int lazy_rt) {
+    extern __shared__ double s_queue[];
     __shared__ unsigned long long s_cnt[XRT_MAX_OPTICS + 1];
     if (threadIdx.x <= XRT_MAX_OPTICS) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
 
-    const int nopt = sc.n_optics;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+    constexpr int P = kQ1Cap;
+    WarpCtx c;
+    c.lane = threadIdx.x & 31u;
+    c.lt_mask = (1u << c.lane) - 1u;
+    c.s_cnt = s_cnt;
+    const int warp = threadIdx.x >> 5;
+    double *q1 = s_queue + (size_t)warp * warp_queue_doubles<FT>();
+    double *q2 = q1 + q1_planes<FT>() * kQ1Cap;
 
-    for (uint64_t base = (uint64_t)blockIdx.x * kBlock; base < ray_count; base += stride) {
-        const uint64_t i = base + threadIdx.x;
+    const int split = (SPLIT >= 0) ? SPLIT : split_rt;
+    const XrtOpticDesc &ops = sc.optics[split];
+    const bool lazy = (FT == 0) ? true : (lazy_rt != 0);
+    int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
+
+    const uint64_t n_warps = (uint64_t)gridDim.x * (kBlock / 32);
+    const uint64_t warp_global = (uint64_t)blockIdx.x * (kBlock / 32) + warp;
+
+    // One loop, one copy of each stage: the deepest stage that has a full warp of work runs
+    // first; when the ids are exhausted the queues are drained with partial warps.
+    uint64_t base = warp_global * 32;
+    for (;;) {
+        const bool more = base < ray_count;
+        if (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
+            const int cnt = n2 < 32 ? n2 : 32;
+            n2 -= cnt;
+            stage_c<FT>(sc, out, c, split, seed, stream_id, q2, n2, cnt);
+            continue;
+        }
+        if (n1 >= 32 || (!more && n1 > 0)) {
+            const int cnt = n1 < 32 ? n1 : 32;
+            n1 -= cnt;
+            stage_b<FT>(sc, ops, out, c, split, lazy, seed, stream_id, q1, n1, cnt, q2, n2);
+            continue;
+        }
+        if (!more) break;
+
+        // ---- stage A
+        const uint64_t i = base + c.lane;
+        base += n_warps * 32;
         const bool valid = i < ray_count;
         const uint64_t id = ray_begin + i;
         PhiloxDraws dr;
         dr.init(seed, stream_id, id);
         Ray r;
         r.alive = false;
-        if (valid) generate_ray<FT>(sc.source, dr, id, r);
-
-        unsigned m = __ballot_sync(kFull, r.alive);
-        if (lane == 0 && m) atomicAdd(&s_cnt[0], (unsigned long long)__popc(m));
-
-        for (int k = 0; k < nopt && m; ++k) {
+        r.w = 0.0;
+        if (valid) {
+            SrcLocal L;
+            source_local<FT>(sc.source, id, L);
+            generate_geometry<FT>(sc.source, L, dr, r);
+            if (!lazy) r.w = generate_wavelength(sc.source, L, dr, r.d);
+        }
+        count_alive(c, 0, r.alive);
+        for (int k = 0; k < split; ++k) {
             const XrtOpticDesc &op = sc.optics[k];
             if (r.alive) {
                 trace_optic<FT>(op, k, dr, r);
-                if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) {
-                    uint32_t pix;
-                    if (pixel_index(op, r.o, pix)) {
-                        // warp-aggregated: one atomic per distinct pixel in the warp
-                        unsigned act = __activemask();
-                        unsigned same = __match_any_sync(act, pix);
-                        if ((same & lt_mask) == 0)
-                            atomicAdd((unsigned long long *)(out.images + op.image_offset + pix),
-                                      (unsigned long long)__popc(same));
-                    }
-                }
+                if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
             }
-            m = __ballot_sync(kFull, r.alive);
-            if (lane == 0 && m) atomicAdd(&s_cnt[k + 1], (unsigned long long)__popc(m));
+            count_alive(c, k + 1, r.alive);
         }
+        V3 n = v3(0.0, 0.0, 1.0);
+        bool cand = false;
+        if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0>(ops, r, n) == HIT_INSIDE;
+        emit_lost(out, c, dr, valid && !cand, id);
 
-        // ---- found list: ballot + prefix-sum compaction, one atomic per warp
-        if (out.found_count) {
-            if (m) {
-                unsigned long long off = 0;
-                if (lane == 0) off = atomicAdd((unsigned long long *)out.found_count, (unsigned long long)__popc(m));
-                off = __shfl_sync(kFull, off, 0);
-                if (r.alive && out.found_ids) {
-                    unsigned long long slot = off + __popc(m & lt_mask);
-                    if (slot < out.found_capacity) out.found_ids[slot] = id;
-                }
-            }
+        const unsigned m = __ballot_sync(kFull, cand);
+        if (cand) {
+            double *p = q1 + n1 + __popc(m & c.lt_mask);
+            p[0] = __longlong_as_double((long long)id);
+            p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
+            p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
+            if constexpr (FT != 0) p[7 * P] = r.w;
+            if constexpr ((FT & FT_MESH) != 0) { p[8 * P] = n.x; p[9 * P] = n.y; p[10 * P] = n.z; }
         }
-        // ---- lost sample: keep a lost ray when its 64-bit key is below the threshold
-        if (out.lost_count) {
-            bool keep = false;
-            uint64_t key = 0;
-            if (valid && !r.alive) {
-                key = dr.lost_key();
-                keep = key < out.lost_threshold;
-            }
-            unsigned lm = __ballot_sync(kFull, keep);
-            if (lm) {
-                unsigned long long off = 0;
-                if (lane == 0) off = atomicAdd((unsigned long long *)out.lost_count, (unsigned long long)__popc(lm));
-                off = __shfl_sync(kFull, off, 0);
-                if (keep && out.lost_ids) {
-                    unsigned long long slot = off + __popc(lm & lt_mask);
-                    if (slot < out.lost_capacity) {
-                        out.lost_ids[slot] = id;
-                        if (out.lost_keys) out.lost_keys[slot] = key;
-                    }
-                }
-            }
-        }
+        n1 += __popc(m);
+        __syncwarp();
     }
 
     __syncthreads();
-    if ((int)threadIdx.x <= nopt && out.counts) {
-        unsigned long long c = s_cnt[threadIdx.x];
-        if (c) atomicAdd((unsigned long long *)(out.counts + threadIdx.x), c);
+    if ((int)threadIdx.x <= sc.n_optics && out.counts) {
+        unsigned long long cc = s_cnt[threadIdx.x];
+        if (cc) atomicAdd((unsigned long long *)(out.counts + threadIdx.x), cc);
     }
 }
 
@@ -238,6 +419,8 @@ struct XrtScene {
     XrtSceneDesc dev;               // descriptor whose pointers are device pointers
     std::vector<void *> allocs;
     uint32_t features;
+    int split;                      // first crystal of the train (0 if none): the kernel's re-pack point
+    int lazy_wavelength;            // wavelength independent of the source direction: drawn at the crystal
     int device;
     int sm_count;
 };
@@ -395,6 +578,17 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         }
     }
     s->features = scene_features(d);
+    s->split = 0;
+    for (int k = 0; k < d.n_optics; ++k) {
+        if (d.optics[k].interact == XRT_INTERACT_CRYSTAL || d.optics[k].interact == XRT_INTERACT_MOSAIC) {
+            s->split = k;
+            break;
+        }
+    }
+    s->lazy_wavelength = (src.kind != XRT_SRC_BUNDLES && src.velocity_c[0] == 0.0 && src.velocity_c[1] == 0.0 &&
+                          src.velocity_c[2] == 0.0) ? 1 : 0;
+    // the lean variant has no wavelength plane in its queue: a source with a Doppler shift needs the full one
+    if (s->features == 0 && !s->lazy_wavelength) s->features = FT_MID;
     return XRT_OK;
 }
 
@@ -428,36 +622,52 @@ extern "C" int xrt_scene_create(const XrtSceneDesc *desc, XrtScene **scene) {
 
 // ---- launch helpers -------------------------------------------------------
 
-template <class K>
-static int occupancy(K kernel, int *blocks_per_sm, int *regs) {
-    cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, kernel));
-    if (regs) *regs = fa.numRegs;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, kBlock, 0));
-    if (*blocks_per_sm < 1) *blocks_per_sm = 1;
-    return XRT_OK;
-}
-
 typedef void (*TraceKernel)(const XrtSceneDesc, const uint64_t, const uint64_t, const uint64_t, const uint64_t,
-                            const XrtOutputs);
+                            const XrtOutputs, const int, const int);
 
-static TraceKernel trace_kernel(uint32_t ft) {
-    if (ft == 0) return k_trace<0>;
-    if (ft == FT_MID) return k_trace<FT_MID>;
-    return k_trace<FT_FULL>;
+template <uint32_t FT>
+static TraceKernel trace_kernel_ft(int split) {
+    switch (split) {
+    case 0: return k_trace<FT, 0>;
+    case 1: return k_trace<FT, 1>;
+    case 2: return k_trace<FT, 2>;
+    default: return k_trace<FT, -1>;
+    }
 }
 
-static int grid_for(const XrtScene *s, uint64_t n, int blocks_per_sm) {
-    uint64_t want = (n + kBlock - 1) / kBlock;
-    uint64_t cap = (uint64_t)s->sm_count * (uint64_t)blocks_per_sm;   // one resident wave, grid-stride beyond
-    if (want < 1) want = 1;
-    return (int)(want < cap ? want : cap);
+static TraceKernel trace_kernel(const XrtScene *s, size_t *smem) {
+    const size_t warps = kBlock / 32;
+    if (s->features == 0) {
+        *smem = warps * warp_queue_doubles<0>() * sizeof(double);
+        return trace_kernel_ft<0>(s->split);
+    }
+    if (s->features == FT_MID) {
+        *smem = warps * warp_queue_doubles<FT_MID>() * sizeof(double);
+        return trace_kernel_ft<FT_MID>(s->split);
+    }
+    *smem = warps * warp_queue_doubles<FT_FULL>() * sizeof(double);
+    return trace_kernel_ft<FT_FULL>(s->split);
+}
+
+static int trace_launch_config(const XrtScene *s, TraceKernel *kern, size_t *smem, int *blocks_per_sm, int *regs) {
+    *kern = trace_kernel(s, smem);
+    CU(cudaFuncSetAttribute(*kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    if (regs) {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, *kern));
+        *regs = fa.numRegs;
+    }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, *kern, kBlock, *smem));
+    if (*blocks_per_sm < 1) return fail(XRT_ECUDA, "fused kernel does not fit on an SM (%zu B shared memory)", *smem);
+    return XRT_OK;
 }
 
 extern "C" int xrt_launch_info(XrtScene *s, int32_t *grid, int32_t *block, int32_t *regs, int32_t *blocks_per_sm) {
     if (!s) return fail(XRT_EINVAL, "null scene");
+    TraceKernel kern;
+    size_t smem;
     int bps = 0, r = 0;
-    int rc = occupancy(trace_kernel(s->features), &bps, &r);
+    int rc = trace_launch_config(s, &kern, &smem, &bps, &r);
     if (rc != XRT_OK) return rc;
     if (grid) *grid = s->sm_count * bps;
     if (block) *block = kBlock;
@@ -470,12 +680,18 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
                          const XrtOutputs *out, void *stream) {
     if (!s || !out) return fail(XRT_EINVAL, "null argument");
     if (ray_count == 0) return XRT_OK;
-    TraceKernel kern = trace_kernel(s->features);
+    if (s->dev.n_optics < 1) return fail(XRT_EINVAL, "a scene needs at least one optic");
+    TraceKernel kern;
+    size_t smem;
     int bps = 0;
-    int rc = occupancy(kern, &bps, nullptr);
+    int rc = trace_launch_config(s, &kern, &smem, &bps, nullptr);
     if (rc != XRT_OK) return rc;
-    int grid = grid_for(s, ray_count, bps);
-    kern<<<grid, kBlock, 0, (cudaStream_t)stream>>>(s->dev, seed, stream_id, ray_begin, ray_count, *out);
+    // one resident wave of blocks, each warp strides over the ray ids
+    uint64_t want = (ray_count + kBlock - 1) / kBlock;
+    uint64_t cap = (uint64_t)s->sm_count * (uint64_t)bps;
+    int grid = (int)(want < cap ? want : cap);
+    kern<<<grid, kBlock, smem, (cudaStream_t)stream>>>(s->dev, seed, stream_id, ray_begin, ray_count, *out, s->split,
+                                                      s->lazy_wavelength);
     CU(cudaGetLastError());
     return XRT_OK;
 }

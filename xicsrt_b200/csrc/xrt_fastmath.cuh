@@ -1,0 +1,168 @@
+// xrt_fastmath.cuh -- the few FP64 transcendentals the ray code needs, written for
+// the argument ranges that occur there.
+//
+// Why not the CUDA math library: its sincos/log/exp/asin/acos materialise every
+// polynomial coefficient with two UMOV instructions (12.7 % of all issued
+// instructions in the first version of the fused kernel, profiles/r01_*), carry
+// range reduction and special-case paths for arguments that cannot occur here, and
+// sincos(2*pi*u) pays a Payne-Hanek stack frame.  Here the coefficients sit in
+// __constant__ tables (one LDCU.128 fetches two of them into uniform registers),
+// and the reductions are exact for the ranges in use.
+//
+// Accuracy (checked on the host against long double, tests/test_fastmath.py):
+// a few 1e-16 relative, far inside the 1e-9 parity tolerance.
+//
+// Every function is __host__ __device__ so the same source is exercised on the CPU.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define XRT_HD __host__ __device__ __forceinline__
+#else
+#define XRT_HD inline
+#define __constant__
+#endif
+
+#ifdef __CUDA_ARCH__
+#define XRT_TAB(name) name##_d
+#else
+#define XRT_TAB(name) name##_h
+#endif
+#define XRT_DEFINE_TABLE(name, n, ...)                       \
+    static __constant__ double name##_d[n] = {__VA_ARGS__};  \
+    static const double name##_h[n] = {__VA_ARGS__};
+
+namespace xrt {
+
+// sin(x) = x + x^3 (S[0] + z S[1] + ... + z^5 S[5]),  |x| <= pi/4   (fdlibm __kernel_sin)
+XRT_DEFINE_TABLE(kSin, 6,
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10)
+// cos(x) = 1 - z/2 + z^2 (C[0] + z C[1] + ... + z^5 C[5]),  |x| <= pi/4   (fdlibm __kernel_cos)
+XRT_DEFINE_TABLE(kCos, 6,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11)
+// log(1+f) = f - f^2/2 + s (f^2/2 + R(z)), s = f/(2+f), z = s^2, R = z Lg[0] + ... + z^7 Lg[6]  (fdlibm __ieee754_log)
+XRT_DEFINE_TABLE(kLog, 7,
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01)
+// exp(r) = sum r^k / k!, k = 0..13, |r| <= ln2/2  (truncation 4e-18)
+XRT_DEFINE_TABLE(kExp, 12,
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5)
+// constants
+XRT_DEFINE_TABLE(kMisc, 6,
+    1.57079632679489661923,        // pi/2
+    6.93147180369123816490e-01,    // ln2_hi
+    1.90821492927058770002e-10,    // ln2_lo
+    1.44269504088896338700,        // log2(e)
+    6.28318530717958647692,        // 2 pi
+    0.0)
+
+XRT_HD int32_t hi_word(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    int64_t b; memcpy(&b, &x, 8); return (int32_t)(b >> 32);
+#endif
+}
+XRT_HD int32_t lo_word(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    int64_t b; memcpy(&b, &x, 8); return (int32_t)(b & 0xffffffff);
+#endif
+}
+XRT_HD double from_words(int32_t hi, int32_t lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+XRT_HD double fm(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return fma(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+XRT_HD double round_even(double x) {
+#ifdef __CUDA_ARCH__
+    return rint(x);
+#else
+    return __builtin_rint(x);
+#endif
+}
+
+// sin(2 pi u), cos(2 pi u) for u in [0, 1].  Reduction: t = 4u, q = rint(t), r = t - q is
+// exact, x = r pi/2 in [-pi/4, pi/4]; quadrant from q mod 4.
+XRT_HD void sincos_2pi(double u, double &s, double &c) {
+    const double t = 4.0 * u;
+    const double q = round_even(t);
+    const double x = (t - q) * XRT_TAB(kMisc)[0];
+    const double z = x * x;
+    double ps = XRT_TAB(kSin)[5];
+    ps = fm(ps, z, XRT_TAB(kSin)[4]); ps = fm(ps, z, XRT_TAB(kSin)[3]); ps = fm(ps, z, XRT_TAB(kSin)[2]);
+    ps = fm(ps, z, XRT_TAB(kSin)[1]); ps = fm(ps, z, XRT_TAB(kSin)[0]);
+    const double sk = fm(x * z, ps, x);
+    double pc = XRT_TAB(kCos)[5];
+    pc = fm(pc, z, XRT_TAB(kCos)[4]); pc = fm(pc, z, XRT_TAB(kCos)[3]); pc = fm(pc, z, XRT_TAB(kCos)[2]);
+    pc = fm(pc, z, XRT_TAB(kCos)[1]); pc = fm(pc, z, XRT_TAB(kCos)[0]);
+    const double ck = fm(z * z, pc, fm(z, -0.5, 1.0));
+    const int iq = (int)q;
+    const double a = (iq & 1) ? ck : sk;      // |sin|
+    const double b = (iq & 1) ? sk : ck;      // |cos|
+    s = (iq & 2) ? -a : a;
+    c = ((iq + 1) & 2) ? -b : b;
+}
+
+// natural logarithm for normal, finite v > 0 (here v in [2^-53, 1])
+XRT_HD double log_pos(double v) {
+    int32_t hx = hi_word(v);
+    int32_t k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int32_t i = (hx + 0x95f64) & 0x100000;   // mantissa >= sqrt(2): use m/2, k+1
+    const double m = from_words(hx | (i ^ 0x3ff00000), lo_word(v));
+    k += (i >> 20);
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double dk = (double)k;
+    const double z = s * s;
+    double R = XRT_TAB(kLog)[6];
+    R = fm(R, z, XRT_TAB(kLog)[5]); R = fm(R, z, XRT_TAB(kLog)[4]); R = fm(R, z, XRT_TAB(kLog)[3]);
+    R = fm(R, z, XRT_TAB(kLog)[2]); R = fm(R, z, XRT_TAB(kLog)[1]); R = fm(R, z, XRT_TAB(kLog)[0]);
+    R = R * z;
+    const double hfsq = 0.5 * f * f;
+    return fm(dk, XRT_TAB(kMisc)[1], -((hfsq - fm(s, hfsq + R, dk * XRT_TAB(kMisc)[2])) - f));
+}
+
+// exp(-x) for 0 <= x <= 700
+XRT_HD double exp_neg(double x) {
+    const double y = -x;
+    const double kf = round_even(y * XRT_TAB(kMisc)[3]);
+    double r = fm(kf, -XRT_TAB(kMisc)[1], y);
+    r = fm(kf, -XRT_TAB(kMisc)[2], r);
+    double p = XRT_TAB(kExp)[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 1; j < 12; ++j) p = fm(p, r, XRT_TAB(kExp)[j]);
+    p = fm(p, r, 1.0);     // + r
+    p = fm(p, r, 1.0);     // + 1
+    const int32_t k = (int32_t)kf;
+    return from_words(hi_word(p) + k * 1048576, lo_word(p));   // p in [0.7, 1.42], result normal for x <= 700
+}
+
+// asin(w) for the difference of two angles: series for the small arguments that matter,
+// the library call otherwise.  |w| < 0.01: next term (35/1152) w^9 is below 4e-18 relative.
+XRT_HD double asin_small(double w) {
+    const double z = w * w;
+    double p = 15.0 / 336.0;
+    p = fm(p, z, 3.0 / 40.0);
+    p = fm(p, z, 1.0 / 6.0);
+    return fm(w * z, p, w);
+}
+
+}  // namespace xrt

@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 #include <math_constants.h>
+#include "xrt_fastmath.cuh"
 
 namespace xrt {
 
@@ -58,11 +59,11 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-// two independent standard normals from two uniforms (Box-Muller)
+// two independent standard normals from two uniforms (Box-Muller); 1 - u1 is in (0, 1]
 __device__ __forceinline__ void box_muller(double u1, double u2, double &z1, double &z2) {
-    double r = sqrt(-2.0 * log(1.0 - u1));     // 1 - u1 in (0, 1]
+    double r = sqrt(-2.0 * log_pos(1.0 - u1));
     double s, c;
-    sincospi(2.0 * u2, &s, &c);
+    sincos_2pi(u2, s, c);
     z1 = r * c;
     z2 = r * s;
 }

@@ -11,6 +11,7 @@
 #pragma once
 #include "../../include/xrt.h"
 #include "xrt_math.cuh"
+#include "xrt_fastmath.cuh"
 
 namespace xrt {
 
@@ -90,6 +91,9 @@ struct PhiloxDraws {
     __device__ __forceinline__ double bragg_u(int k, int layer) const {
         double a, b; pair(site_optic(k, layer, 0), a, b); return a;
     }
+    // Reflection probability below 2^-53: the ray passes only when the uniform is exactly 0
+    // (p >= u).  With Philox that draw is not made at all (probability 1.1e-16 per ray).
+    __device__ __forceinline__ bool bragg_u_is_zero(int, int) const { return false; }
     __device__ __forceinline__ void mosaic_xy(int k, int layer, double s, double &x, double &y) const {
         double a, b, z0, z1;
         pair(site_optic(k, layer, 1), a, b);
@@ -105,6 +109,7 @@ struct InjectedDraws {
     __device__ __forceinline__ double bragg_u(int k, int layer) const {
         return inj->u[k][(uint64_t)layer * n + i];
     }
+    __device__ __forceinline__ bool bragg_u_is_zero(int k, int layer) const { return bragg_u(k, layer) == 0.0; }
     __device__ __forceinline__ void mosaic_xy(int k, int layer, double, double &x, double &y) const {
         const double *p = inj->xy[k] + (uint64_t)layer * 2 * n;
         x = p[i]; y = p[n + i];
@@ -128,15 +133,24 @@ struct SourceInjectedDraws {
 // ---------------------------------------------------------------------------
 // source: one ray from the draws  (reference _XicsrtSourceGeneric.py:198-393,
 // _XicsrtSourceFocused.py:35-44, _XicsrtPlasmaGeneric.py:286-345)
+//
+// Split in two so that the fused kernel can draw the wavelength lazily: Philox is counter
+// based, so a ray's wavelength can be produced at the first optic that needs it (the Bragg
+// test) instead of at the source -- rays that miss the crystal never pay for it.
 
-template <uint32_t FT, class DR>
-__device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &dr, uint64_t index, Ray &r) {
-    V3 org = v3(s.origin);
-    double cos_spread = s.cone_par[0];
-    double wave_sigma = s.wave_par[1];
-    V3 vel = v3(s.velocity_c);
-    double ext0 = s.extent[0], ext1 = s.extent[1], ext2 = s.extent[2];
+// per-ray source parameters: the source itself, or the plasma bundle the ray belongs to
+struct SrcLocal {
+    V3 org, vel;
+    double cos_spread, wave_sigma, ext0, ext1, ext2;
+};
 
+template <uint32_t FT>
+__device__ __forceinline__ void source_local(const XrtSourceDesc &s, uint64_t index, SrcLocal &L) {
+    L.org = v3(s.origin);
+    L.vel = v3(s.velocity_c);
+    L.cos_spread = s.cone_par[0];
+    L.wave_sigma = s.wave_par[1];
+    L.ext0 = s.extent[0]; L.ext1 = s.extent[1]; L.ext2 = s.extent[2];
     if constexpr ((FT & FT_SRC_EXT) != 0) {
         if (s.kind == XRT_SRC_BUNDLES) {
             // bundle of this ray: first b with bundle_end[b] > index
@@ -146,45 +160,49 @@ __device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &d
                 if (__ldg(s.bundle_end + mid) > index) hi = mid; else lo = mid + 1;
             }
             const XrtBundle *b = s.bundles + lo;
-            org = v3(__ldg(&b->origin[0]), __ldg(&b->origin[1]), __ldg(&b->origin[2]));
-            cos_spread = __ldg(&b->cos_spread);
-            wave_sigma = __ldg(&b->wave_sigma);
-            vel = v3(__ldg(&b->velocity_c[0]), __ldg(&b->velocity_c[1]), __ldg(&b->velocity_c[2]));
-            ext0 = ext1 = ext2 = s.voxel_size;
+            L.org = v3(__ldg(&b->origin[0]), __ldg(&b->origin[1]), __ldg(&b->origin[2]));
+            L.cos_spread = __ldg(&b->cos_spread);
+            L.wave_sigma = __ldg(&b->wave_sigma);
+            L.vel = v3(__ldg(&b->velocity_c[0]), __ldg(&b->velocity_c[1]), __ldg(&b->velocity_c[2]));
+            L.ext0 = L.ext1 = L.ext2 = s.voxel_size;
         }
     }
+}
 
+// origin, direction and the source-level mask
+template <uint32_t FT, class DR>
+__device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const SrcLocal &L, const DR &dr, Ray &r) {
     // ---- origin (:229-255): three draws of U(-size/2, size/2), or N(0, sigma)
     double off[3] = {0.0, 0.0, 0.0};
     bool gauss = false;
     if constexpr ((FT & FT_SRC_EXT) != 0) gauss = (s.spatial == XRT_SPATIAL_GAUSSIAN);
     if (gauss) {
-        double sig[3] = {ext0, ext1, ext2};
+        double sig[3] = {L.ext0, L.ext1, L.ext2};
         dr.origin_gauss(sig, off);
-    } else if (ext0 != 0.0 || ext1 != 0.0 || ext2 != 0.0) {
+    } else if (L.ext0 != 0.0 || L.ext1 != 0.0 || L.ext2 != 0.0) {
         double u[3];
         dr.origin_uniform(u);
-        off[0] = -0.5 * ext0 + ext0 * u[0];
-        off[1] = -0.5 * ext1 + ext1 * u[1];
-        off[2] = -0.5 * ext2 + ext2 * u[2];
+        off[0] = -0.5 * L.ext0 + L.ext0 * u[0];
+        off[1] = -0.5 * L.ext1 + L.ext1 * u[1];
+        off[2] = -0.5 * L.ext2 + L.ext2 * u[2];
     }
     const double *R = s.orient;
-    r.o = v3(((org.x + off[0] * R[0]) + off[1] * R[3]) + off[2] * R[6],
-             ((org.y + off[0] * R[1]) + off[1] * R[4]) + off[2] * R[7],
-             ((org.z + off[0] * R[2]) + off[1] * R[5]) + off[2] * R[8]);
+    r.o = v3(((L.org.x + off[0] * R[0]) + off[1] * R[3]) + off[2] * R[6],
+             ((L.org.y + off[0] * R[1]) + off[1] * R[4]) + off[2] * R[7],
+             ((L.org.z + off[0] * R[2]) + off[1] * R[5]) + off[2] * R[8]);
 
     // ---- local cone vector (xicsrt_spread.py:80-294)
     V3 l;
     int cone = XRT_CONE_ISOTROPIC;
     if constexpr ((FT & FT_SRC_EXT) != 0) cone = s.cone;
     if (cone == XRT_CONE_ISOTROPIC) {
+        // z ~ U(cos(spread), 1), phi ~ U(0, 2 pi): (rho cos phi, rho sin phi, z)
         double a, b;
         dr.cone(0, a, b);
-        double z = cos_spread + (1.0 - cos_spread) * a;
-        double phi = 0.0 + (2.0 * CUDART_PI - 0.0) * b;
-        double rho = sqrt(1.0 - z * z);
+        double z = L.cos_spread + (1.0 - L.cos_spread) * a;
+        double rho = sqrt(fma(-z, z, 1.0));
         double sn, cs;
-        sincos(phi, &sn, &cs);
+        sincos_2pi(b, sn, cs);
         l = v3(rho * cs, rho * sn, z);
     } else if (cone == XRT_CONE_ISOTROPIC_XY) {
         // rejection from the enclosing circular cone (:130-196)
@@ -194,10 +212,9 @@ __device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &d
             double a, b;
             dr.cone(attempt, a, b);
             double z = cm + (1.0 - cm) * a;
-            double phi = (2.0 * CUDART_PI) * b;
-            double rho = sqrt(1.0 - z * z);
+            double rho = sqrt(fma(-z, z, 1.0));
             double sn, cs;
-            sincos(phi, &sn, &cs);
+            sincos_2pi(b, sn, cs);
             double x = rho * cs, y = rho * sn;
             double sx = x / sqrt(x * x + z * z);
             double sy = y / sqrt(y * y + z * z);
@@ -205,21 +222,20 @@ __device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &d
             if (sx > s.cone_par[0] && sx <= s.cone_par[1] && sy > s.cone_par[2] && sy <= s.cone_par[3]) break;
         }
     } else {
-        double a, b, a0, a1;
+        double a, b, a0, s1, c1;
         dr.cone(0, a, b);
         if (cone == XRT_CONE_FLAT) {
             double rr = sqrt(0.0 + (s.cone_par[0] - 0.0) * a);
-            a1 = (2.0 * CUDART_PI) * b;
+            sincos_2pi(b, s1, c1);
             a0 = atan(rr);
         } else {
             double x = s.cone_par[0] + (s.cone_par[1] - s.cone_par[0]) * a;
             double y = s.cone_par[2] + (s.cone_par[3] - s.cone_par[2]) * b;
             a0 = atan(sqrt(x * x + y * y));
-            a1 = atan2(y, x);
+            sincos(atan2(y, x), &s1, &c1);
         }
-        double s0, c0, s1, c1;
+        double s0, c0;
         sincos(a0, &s0, &c0);
-        sincos(a1, &s1, &c1);
         l = v3(c1 * s0, s1 * s0, c0);
     }
 
@@ -231,8 +247,7 @@ __device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &d
         o1 = v3(s.axis_basis[3], s.axis_basis[4], s.axis_basis[5]);
         ax = v3(s.axis_basis[6], s.axis_basis[7], s.axis_basis[8]);
     } else {
-        V3 t = v3(s.target) - r.o;
-        ax = t * (1.0 / sqrt(dot(t, t)));
+        ax = unit(v3(s.target) - r.o);
         V3 xa = v3(R[0], R[1], R[2]), za = v3(R[6], R[7], R[8]);
         o1 = unit(cross(ax, xa) + cross(ax, za));
         o2 = unit(cross(ax, o1));
@@ -240,21 +255,6 @@ __device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &d
     r.d = v3(l.x * o2.x + l.y * o1.x + l.z * ax.x,
              l.x * o2.y + l.y * o1.y + l.z * ax.y,
              l.x * o2.z + l.y * o1.z + l.z * ax.z);
-
-    // ---- wavelength (:295-367)
-    double w;
-    if (s.wave == XRT_WAVE_NORMAL) {
-        w = s.wave_par[0] + wave_sigma * dr.wave_z();
-    } else if (s.wave == XRT_WAVE_CONST) {
-        w = s.wave_par[0];
-    } else if (s.wave == XRT_WAVE_UNIFORM) {
-        w = s.wave_par[0] + (s.wave_par[1] - s.wave_par[0]) * dr.wave_u();
-    } else {
-        double y = s.wave_par[1] + (s.wave_par[2] - s.wave_par[1]) * dr.wave_u();
-        w = interp_inside(y, s.table_cdf, s.table_x, s.n_table) + s.wave_par[0];
-    }
-    if (vel.x != 0.0 || vel.y != 0.0 || vel.z != 0.0) w *= 1.0 - dot(vel, r.d);
-    r.w = w;
 
     // ---- source-level sightline filters (_XicsrtBundleFilterSightline.py:31-56)
     r.alive = true;
@@ -267,6 +267,38 @@ __device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &d
             r.alive = r.alive && (sl.radius >= sqrt(dot(perp, perp)));
         }
     }
+}
+
+// wavelength (:295-367); `dir` is the ray direction at the source (Doppler shift)
+template <class DR>
+__device__ __forceinline__ double generate_wavelength(const XrtSourceDesc &s, const SrcLocal &L, const DR &dr, V3 dir) {
+    double w;
+    if (s.wave == XRT_WAVE_NORMAL) {
+        w = s.wave_par[0] + L.wave_sigma * dr.wave_z();
+    } else if (s.wave == XRT_WAVE_CONST) {
+        w = s.wave_par[0];
+    } else if (s.wave == XRT_WAVE_UNIFORM) {
+        w = s.wave_par[0] + (s.wave_par[1] - s.wave_par[0]) * dr.wave_u();
+    } else {
+        double y = s.wave_par[1] + (s.wave_par[2] - s.wave_par[1]) * dr.wave_u();
+        w = interp_inside(y, s.table_cdf, s.table_x, s.n_table) + s.wave_par[0];
+    }
+    if (L.vel.x != 0.0 || L.vel.y != 0.0 || L.vel.z != 0.0) w *= 1.0 - dot(L.vel, dir);
+    return w;
+}
+
+// true when the wavelength does not depend on the direction at the source, i.e. it can be
+// drawn later from (seed, ray id) alone
+__device__ __forceinline__ bool wavelength_is_lazy(const XrtSourceDesc &s) {
+    return s.kind != XRT_SRC_BUNDLES && s.velocity_c[0] == 0.0 && s.velocity_c[1] == 0.0 && s.velocity_c[2] == 0.0;
+}
+
+template <uint32_t FT, class DR>
+__device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &dr, uint64_t index, Ray &r) {
+    SrcLocal L;
+    source_local<FT>(s, index, L);
+    generate_geometry<FT>(s, L, dr, r);
+    r.w = generate_wavelength(s, L, dr, r.d);
 }
 
 // ---------------------------------------------------------------------------
@@ -283,16 +315,17 @@ __device__ __forceinline__ bool hit_plane(const XrtOpticDesc &op, bool local, V3
     return t >= 0.0;
 }
 
-// _ShapeSphere.py:53-100 -- geometric solution; concave takes the larger root, no sign test
+// _ShapeSphere.py:53-100 -- geometric solution; concave takes the larger root, no sign test.
+// The reference forms d = sqrt(L.L - tca^2), tests d <= R and then uses d^2 again; here the
+// square is kept (d^2 < 0 is the reference's NaN -> miss), which saves one square root.
 __device__ __forceinline__ bool hit_sphere(const XrtOpticDesc &op, V3 o, V3 d, double &t) {
     V3 L = v3(op.center) - o;
     double tca = dot(L, d);
-    double dd = sqrt(dot(L, L) - tca * tca);
-    if (!(dd <= op.radius)) return false;
-    double thc = sqrt(op.radius * op.radius - dd * dd);
-    double t0 = tca - thc, t1 = tca + thc;
-    if (op.flags & XRT_F_CONVEX) t = (t0 < t1) ? t0 : t1;
-    else t = (t0 > t1) ? t0 : t1;
+    double d2 = fma(-tca, tca, dot(L, L));
+    double r2 = op.radius * op.radius;
+    if (!(d2 >= 0.0 && d2 <= r2)) return false;
+    double thc = sqrt(r2 - d2);
+    t = (op.flags & XRT_F_CONVEX) ? tca - thc : tca + thc;     // min / max of tca -+ thc (thc >= 0)
     return true;
 }
 
@@ -424,20 +457,30 @@ __device__ __forceinline__ bool aperture_fold(const XrtOpticDesc &op, double x, 
 
 // ---------------------------------------------------------------------------
 // Bragg reflection test (_InteractCrystal.py:96-196)
-
-__device__ __forceinline__ void bragg_angles(const XrtOpticDesc &op, const Ray &r, V3 n, double &tb, double &ti) {
-    tb = asin(r.w / op.two_d);
-    double dt = fabs(dot(r.d, v3(-n.x, -n.y, -n.z)));
-    ti = (CUDART_PI / 2.0) - acos(dt / sqrt(dot(r.d, r.d)));
+//
+// The reference forms theta_B = asin(lambda / 2d) and theta_i = pi/2 - acos(|D.n| / |D|) and
+// feeds theta_i - theta_B to the rocking curve.  With s = lambda / 2d and c = |D.n| / |D|
+// (both in [0, 1]) that difference is  asin(c) - asin(s) = asin(c sqrt(1 - s^2) - s sqrt(1 - c^2)),
+// an argument of order 1e-5..1e-3 wherever the rocking curve is not zero, for which asin is a
+// short series.  Two square roots replace an asin and an acos; 1 - x^2 is formed with one
+// fma, i.e. correctly rounded, so the conditioning is that of the reference's own acos.
+__device__ __forceinline__ double bragg_dtheta(const XrtOpticDesc &op, V3 d, double w, V3 n) {
+    double s = w * op.inv_two_d;
+    double c = fabs(dot(d, n)) * rsqrt(dot(d, d));
+    double x = c * sqrt(fma(-s, s, 1.0)) - s * sqrt(fma(-c, c, 1.0));
+    return (fabs(x) < 0.01) ? asin_small(x) : asin(x);      // NaN (lambda > 2d) goes to asin -> NaN
 }
 
-template <uint32_t FT>
-__device__ __forceinline__ double rocking_probability(const XrtOpticDesc &op, double ti, double tb) {
-    double dth = ti - tb;
+// true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).
+template <uint32_t FT, class DR>
+__device__ __forceinline__ bool bragg_pass(const XrtOpticDesc &op, int k, int layer, const DR &dr, double dth) {
     double p;
     if (op.rocking_type == XRT_ROCK_GAUSS) {
         // sigma = fwhm / (2 sqrt(2 ln 2)); p = exp(-dth^2 / (2 sigma^2))
-        p = exp(-(dth * dth) / op.rock_two_sigma2);
+        double x = (dth * dth) / op.rock_two_sigma2;
+        if (x >= 40.0) return dr.bragg_u_is_zero(k, layer);   // p < 2^-57: only u == 0 passes
+        if (!(x >= 0.0)) return false;                        // NaN
+        p = exp_neg(x);
     } else if (op.rocking_type == XRT_ROCK_STEP) {
         p = (fabs(dth) <= op.rocking_fwhm / 2.0) ? 1.0 : 0.0;
     } else {
@@ -450,8 +493,10 @@ __device__ __forceinline__ double rocking_probability(const XrtOpticDesc &op, do
                 p = op.rocking_mix * sg + (1.0 - op.rocking_mix) * pi;
             }
         }
+        if (!(dth == dth)) return false;
     }
-    return p * op.reflectivity;
+    p *= op.reflectivity;
+    return p >= dr.bragg_u(k, layer);
 }
 
 // _InteractMirror.py:29-42
@@ -465,16 +510,14 @@ __device__ __forceinline__ void reflect(Ray &r, V3 n) {
 
 // _ShapeSphere.py:102-106
 __device__ __forceinline__ V3 normal_sphere(const XrtOpticDesc &op, V3 X) {
-    V3 v = v3(op.center) - X;
-    return v * (1.0 / sqrt(dot(v, v)));
+    return unit(v3(op.center) - X);
 }
 
 // _ShapeCylinder.py:111-133 -- toward the point of the axis at the same x
 __device__ __forceinline__ V3 normal_cylinder(const XrtOpticDesc &op, V3 X) {
     V3 pa = v3(op.center), va = v3(op.orient);
     double s = dot(pa - X, va);
-    V3 v = (pa - va * s) - X;
-    return v * (1.0 / sqrt(dot(v, v)));
+    return unit((pa - va * s) - X);
 }
 
 // _ShapeTorus.py:186-216 -- away from the nearest point of the axis circle
@@ -482,9 +525,8 @@ __device__ __forceinline__ V3 normal_torus(const XrtOpticDesc &op, V3 X) {
     V3 C = v3(op.center), ya = v3(op.orient + 3);
     V3 p = X - C;
     p = p - ya * dot(p, ya);
-    V3 Q = C + p * (op.torus_major / sqrt(dot(p, p)));
-    V3 v = X - Q;
-    return v * (1.0 / sqrt(dot(v, v)));
+    V3 Q = C + p * (op.torus_major * rsqrt(dot(p, p)));
+    return unit(X - Q);
 }
 
 // ---------------------------------------------------------------------------
@@ -492,13 +534,12 @@ __device__ __forceinline__ V3 normal_torus(const XrtOpticDesc &op, V3 X) {
 // (_InteractMosaicCrystal.py:109-139, xicsrt_spread.py:297-339)
 
 __device__ __forceinline__ V3 mosaic_normal(V3 n, double x, double y) {
-    double inv = 1.0 / sqrt(x * x + y * y + 1.0);
+    double inv = rsqrt(x * x + y * y + 1.0);
     double lx = x * inv, ly = y * inv, lz = inv;
     // R0 = n x [1,0,0] + n x [0,0,1];  R1 = n x R0
     V3 r0 = v3(0.0 + n.y, n.z - n.x, -n.y + 0.0);
-    r0 = r0 * (1.0 / sqrt(dot(r0, r0)));
-    V3 r1 = cross(n, r0);
-    r1 = r1 * (1.0 / sqrt(dot(r1, r1)));
+    r0 = unit(r0);
+    V3 r1 = unit(cross(n, r0));
     return v3(lx * r0.x + ly * r1.x + lz * n.x,
               lx * r0.y + ly * r1.y + lz * n.y,
               lx * r0.z + ly * r1.z + lz * n.z);
@@ -534,25 +575,60 @@ __device__ __forceinline__ void pass_lost_ray(const XrtOpticDesc &op, Ray &r) {
 }
 
 // ---------------------------------------------------------------------------
-// one optic, start to end (_TraceObject.py:135-178).  `r` must be alive on entry.
-// On exit: r.alive = survived; r.o = intersection point (NaN when the surface was
-// missed), r.d reflected only for surviving rays -- exactly the state the
-// reference's history holds for this element.
+// one optic (_TraceObject.py:135-178), in two halves so that the fused kernel can
+// re-pack the surviving rays of a warp between them.
+//
+// geometry half: to-local, intersect, bounds / aperture.  On return r.o = intersection
+// point and r.d = direction, both in the frame the optic traces in (local when
+// trace_local), n = surface normal there.  Return value:
+//   HIT_MISS    surface missed: r.o = NaN, r.d back in external coordinates, r.alive = false
+//   HIT_OUTSIDE hit outside bounds / aperture: r.o, r.d in external coordinates, r.alive = false
+//   HIT_INSIDE  candidate for the interaction half (frame not yet converted back)
+enum { HIT_MISS = 0, HIT_OUTSIDE = 1, HIT_INSIDE = 2 };
 
-template <uint32_t FT, class DR>
-__device__ __forceinline__ void trace_optic(const XrtOpticDesc &op, int k, const DR &dr, Ray &r) {
-    V3 o = r.o, d = r.d;
-    bool local = false;
+template <uint32_t FT>
+__device__ __forceinline__ bool optic_is_local(const XrtOpticDesc &op) {
+    if constexpr ((FT & FT_LOCAL) != 0) return (op.flags & XRT_F_TRACE_LOCAL) != 0;
+    return false;
+}
+
+// surface normal of an analytic shape at X (tracing frame)
+template <uint32_t FT>
+__device__ __forceinline__ V3 analytic_normal(const XrtOpticDesc &op, V3 X) {
+    const int shape = op.shape;
+    // the plane normal is the element's (global) zaxis even when tracing in local
+    // coordinates -- _ShapePlane.py:55-62 does not transform it; replicated.
+    if (shape == XRT_SHAPE_PLANE) return v3(op.orient + 6);
+    if (shape == XRT_SHAPE_SPHERE) return normal_sphere(op, X);
+    V3 n = v3(0.0, 0.0, 1.0);
+    if constexpr ((FT & FT_CYL) != 0) { if (shape == XRT_SHAPE_CYLINDER) n = normal_cylinder(op, X); }
+    if constexpr ((FT & FT_TORUS) != 0) { if (shape == XRT_SHAPE_TORUS) n = normal_torus(op, X); }
+    return n;
+}
+
+template <uint32_t FT>
+__device__ __forceinline__ void frame_to_external(const XrtOpticDesc &op, bool local, Ray &r) {
     if constexpr ((FT & FT_LOCAL) != 0) {
-        local = (op.flags & XRT_F_TRACE_LOCAL) != 0;
+        if (local) {   // _GeometryObject.py:113-125
+            r.o = to_external(op.orient, r.o) + v3(op.origin);
+            r.d = to_external(op.orient, r.d);
+        }
+    }
+}
+
+template <uint32_t FT, bool WANT_NORMAL>
+__device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3 &n) {
+    V3 o = r.o, d = r.d;
+    const bool local = optic_is_local<FT>(op);
+    if constexpr ((FT & FT_LOCAL) != 0) {
         if (local) {   // _GeometryObject.py:127-141
             o = to_local(op.orient, o - v3(op.origin));
             d = to_local(op.orient, d);
         }
     }
 
-    // ---- intersect: distance, location, normal
-    V3 X, n;
+    // ---- intersect: distance, location (and normal for mesh shapes)
+    V3 X;
     bool ok;
     bool analytic = true;
     if constexpr ((FT & FT_MESH) != 0) {
@@ -571,26 +647,15 @@ __device__ __forceinline__ void trace_optic(const XrtOpticDesc &op, int k, const
             if constexpr ((FT & FT_CYL) != 0) { if (shape == XRT_SHAPE_CYLINDER) ok = hit_cylinder(op, o, d, t); }
             if constexpr ((FT & FT_TORUS) != 0) { if (shape == XRT_SHAPE_TORUS) ok = hit_torus(op, o, d, t); }
         }
-        if (ok) {
-            X = v3(o.x + d.x * t, o.y + d.y * t, o.z + d.z * t);   // _ShapeObject.py:69-81
-            // the plane normal is the element's (global) zaxis even when tracing in local
-            // coordinates -- _ShapePlane.py:55-62 does not transform it; replicated.
-            if (shape == XRT_SHAPE_PLANE) n = v3(op.orient + 6);
-            else if (shape == XRT_SHAPE_SPHERE) n = normal_sphere(op, X);
-            else {
-                n = v3(0.0, 0.0, 1.0);
-                if constexpr ((FT & FT_CYL) != 0) { if (shape == XRT_SHAPE_CYLINDER) n = normal_cylinder(op, X); }
-                if constexpr ((FT & FT_TORUS) != 0) { if (shape == XRT_SHAPE_TORUS) n = normal_torus(op, X); }
-            }
-        }
+        X = v3(fma(d.x, t, o.x), fma(d.y, t, o.y), fma(d.z, t, o.z));   // _ShapeObject.py:69-81
     }
+    r.alive = false;
     if (!ok) {
-        r.alive = false;
         r.o = nan3();
         // ray_to_external acts on every ray, hit or not (_TraceObject.py:135-155): the
         // direction makes the local round trip (visible when the axes are not exactly unit)
         if constexpr ((FT & FT_LOCAL) != 0) { if (local) r.d = to_external(op.orient, d); }
-        return;
+        return HIT_MISS;
     }
 
     // ---- bounds (_TraceObject.py:180-232): strict |x| < size/2, then apertures
@@ -604,65 +669,60 @@ __device__ __forceinline__ void trace_optic(const XrtOpticDesc &op, int k, const
     if constexpr ((FT & FT_APERTURE) != 0) {
         if (in && (op.flags & XRT_F_CHECK_APERTURE) && op.n_aperture > 0) in = aperture_fold(op, Xl.x, Xl.y);
     }
-
-    // ---- interaction
-    bool alive = in;
-    if (in) {
-        const int ia = op.interact;
-        if (ia == XRT_INTERACT_MIRROR) {
-            Ray q; q.d = d; reflect(q, n); d = q.d;
-        } else if (ia == XRT_INTERACT_CRYSTAL) {
-            bool pass = true;
-            if (op.flags & XRT_F_CHECK_BRAGG) {
-                Ray q; q.d = d; q.w = r.w;
-                double tb, ti;
-                bragg_angles(op, q, n, tb, ti);
-                double p = rocking_probability<FT>(op, ti, tb);
-                pass = (p >= dr.bragg_u(k, 0));
-            }
-            if (pass) { Ray q; q.d = d; reflect(q, n); d = q.d; }
-            alive = pass;
-        } else if (ia == XRT_INTERACT_MOSAIC) {
-            if constexpr ((FT & FT_MOSAIC) != 0) {
-                Ray q; q.d = d; q.w = r.w;
-                if (op.flags & XRT_F_MOSAIC_CUTOFF) {
-                    double tb, ti;
-                    bragg_angles(op, q, n, tb, ti);
-                    alive = fabs(tb - ti) < op.mosaic_angle_cut;
-                }
-                if (alive) {
-                    bool done = false;
-                    for (int layer = 0; layer < op.mosaic_depth && !done; ++layer) {
-                        double x, y;
-                        dr.mosaic_xy(k, layer, op.mosaic_sin_sigma, x, y);
-                        V3 nm = mosaic_normal(n, x, y);
-                        bool pass = true;
-                        if (op.flags & XRT_F_CHECK_BRAGG) {
-                            double tb, ti;
-                            bragg_angles(op, q, nm, tb, ti);
-                            double p = rocking_probability<FT>(op, ti, tb);
-                            pass = (p >= dr.bragg_u(k, layer));
-                        }
-                        if (pass) { reflect(q, nm); d = q.d; done = true; }
-                    }
-                    alive = done;
-                }
-            } else {
-                alive = false;
-            }
-        }
-    }
-
-    // ---- back to external coordinates (_GeometryObject.py:113-125)
-    if constexpr ((FT & FT_LOCAL) != 0) {
-        if (local) {
-            X = to_external(op.orient, X) + v3(op.origin);
-            d = to_external(op.orient, d);
-        }
-    }
     r.o = X;
     r.d = d;
+    if (!in) {
+        frame_to_external<FT>(op, local, r);
+        return HIT_OUTSIDE;
+    }
+    if constexpr (WANT_NORMAL) { if (analytic) n = analytic_normal<FT>(op, X); }
+    r.alive = true;
+    return HIT_INSIDE;
+}
+
+// interaction half (None / Mirror / Crystal / Mosaic) and the way back to external
+// coordinates.  r.o, r.d in the tracing frame, r.w valid, n = normal at r.o.
+template <uint32_t FT, class DR>
+__device__ __forceinline__ void optic_interact(const XrtOpticDesc &op, int k, const DR &dr, Ray &r, V3 n) {
+    bool alive = true;
+    const int ia = op.interact;
+    if (ia == XRT_INTERACT_MIRROR) {
+        reflect(r, n);
+    } else if (ia == XRT_INTERACT_CRYSTAL) {
+        if (op.flags & XRT_F_CHECK_BRAGG) alive = bragg_pass<FT>(op, k, 0, dr, bragg_dtheta(op, r.d, r.w, n));
+        if (alive) reflect(r, n);
+    } else if (ia == XRT_INTERACT_MOSAIC) {
+        if constexpr ((FT & FT_MOSAIC) != 0) {
+            // optional prefilter on the nominal normal (_InteractMosaicCrystal.py:67-75)
+            if (op.flags & XRT_F_MOSAIC_CUTOFF) alive = fabs(bragg_dtheta(op, r.d, r.w, n)) < op.mosaic_angle_cut;
+            if (alive) {
+                // layers of crystallites: the first one that satisfies Bragg reflects (:83-104)
+                bool done = false;
+                for (int layer = 0; layer < op.mosaic_depth && !done; ++layer) {
+                    double x, y;
+                    dr.mosaic_xy(k, layer, op.mosaic_sin_sigma, x, y);
+                    V3 nm = mosaic_normal(n, x, y);
+                    bool pass = true;
+                    if (op.flags & XRT_F_CHECK_BRAGG) pass = bragg_pass<FT>(op, k, layer, dr, bragg_dtheta(op, r.d, r.w, nm));
+                    if (pass) { reflect(r, nm); done = true; }
+                }
+                alive = done;
+            }
+        } else {
+            alive = false;
+        }
+    }
+    frame_to_external<FT>(op, optic_is_local<FT>(op), r);
     r.alive = alive;
+}
+
+// both halves.  `r` must be alive on entry.  On exit: r.alive = survived; r.o = intersection
+// point (NaN when the surface was missed), r.d reflected only for surviving rays -- exactly
+// the state the reference's history holds for this element.
+template <uint32_t FT, class DR>
+__device__ __forceinline__ void trace_optic(const XrtOpticDesc &op, int k, const DR &dr, Ray &r) {
+    V3 n;
+    if (optic_geometry<FT, true>(op, r, n) == HIT_INSIDE) optic_interact<FT>(op, k, dr, r, n);
 }
 
 }  // namespace xrt

@@ -259,6 +259,7 @@ def fill_optic(op, param, keep, image_offset):
         if param['check_bragg'] is not False:          # identity test, as _InteractCrystal.py:122
             flags |= L.F_CHECK_BRAGG
         op.two_d = 2 * float(param['crystal_spacing'])
+        op.inv_two_d = 1.0 / op.two_d if op.two_d != 0.0 else float('inf')
         op.reflectivity = float(param['reflectivity'])
         op.rocking_mix = float(param['rocking_mix'])
         rtype = param['rocking_type']
