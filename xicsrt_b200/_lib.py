@@ -128,7 +128,7 @@ class XrtError(RuntimeError):
         self.code = code
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libxrt.so')
+LIB_PATH = os.environ.get('XRT_LIB_PATH') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libxrt.so')
 
 # every symbol include/xrt.h declares: (restype, argtypes)
 _u64, _vp = C.c_uint64, C.c_void_p

@@ -25,7 +25,13 @@
 
 namespace xrt {
 
-constexpr int kBlock = 256;
+#ifndef XRT_BLOCK
+#define XRT_BLOCK 256
+#endif
+#ifndef XRT_MIN_BLOCKS
+#define XRT_MIN_BLOCKS 3
+#endif
+constexpr int kBlock = XRT_BLOCK;
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---------------------------------------------------------------------------
@@ -206,7 +212,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
 }
 
 template <uint32_t FT, int SPLIT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, XRT_MIN_BLOCKS)
 k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
         const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const int split_rt,
         const int lazy_rt) {
