@@ -66,13 +66,20 @@ def allreduce_packed(packed):
 
 
 class HostRandom:
-    """Host-side draws (Poisson ray counts, plasma bundle centres): numpy Philox keyed by the run seed."""
+    """
+    Host-side draws (Poisson ray counts, plasma bundle centres): numpy Philox keyed by the run
+    seed and a stream number (0 = run set-up, 1 + i = iteration i), so every rank of a multi-GPU
+    run builds the same tables.
+    """
 
-    def __init__(self, seed):
-        self.gen = np.random.Generator(np.random.Philox(key=int(seed) & U64_MAX))
+    def __init__(self, seed, stream=0):
+        self.gen = np.random.Generator(np.random.Philox(key=[int(seed) & U64_MAX, int(stream) & U64_MAX]))
 
     def poisson(self, lam):
         return int(self.gen.poisson(lam))
+
+    def poisson_array(self, lam):
+        return self.gen.poisson(lam).astype(np.int64)
 
     def uniform(self, lo, hi, n):
         return self.gen.uniform(lo, hi, n)
@@ -92,20 +99,13 @@ class Tracer:
         self.seed = int(seed) & U64_MAX
         self.host_rng = HostRandom(self.seed)
 
-        (self.config, self.source_name, source_param, source_filters,
-         optics) = xscene.prepare(config, poisson=self.host_rng.poisson)
-        bundles = None
-        if source_param['_kind'].startswith('plasma'):
-            from . import plasma
-            bundles = plasma.build_bundles(source_param, source_filters, self.host_rng)
-        desc, self.layout, keep = xscene.flatten(self.source_name, source_param, source_filters, optics,
-                                                 bundles=bundles)
-        with torch.cuda.device(self.device):
-            self.scene = xscene.DeviceScene(desc, self.layout)
-        del keep
+        (self.config, self.source_name, self.source_param, self.source_filters,
+         self.optics) = xscene.prepare(config, poisson=self.host_rng.poisson)
+        self.is_plasma = self.source_param['_kind'].startswith('plasma')
+        self.scene = None
+        self._upload(0)
         self.lib = self.scene.lib
         self.n_elem = 1 + len(self.layout.optic_names)
-        self.n_rays = self.layout.n_rays
 
         i64 = torch.int64
         # one packed buffer [counts | images] so that a multi-GPU run reduces it with one call
@@ -116,6 +116,30 @@ class Tracer:
         self.lost_keys = None
 
     # ------------------------------------------------------------------
+    def _upload(self, iteration):
+        """Flatten and upload the scene; plasma sources draw a fresh bundle table per iteration."""
+        bundles = None
+        if self.is_plasma:
+            from . import plasma
+            bundles = plasma.build_bundles(self.source_param, self.source_filters,
+                                           HostRandom(self.seed, 1 + iteration))
+        desc, self.layout, keep = xscene.flatten(self.source_name, self.source_param, self.source_filters,
+                                                 self.optics, bundles=bundles)
+        if self.scene is not None:
+            self.scene.close()
+        with self.torch.cuda.device(self.device):
+            self.scene = xscene.DeviceScene(desc, self.layout)
+        del keep
+        self.n_rays = self.layout.n_rays
+
+    def begin_iteration(self, iteration):
+        """
+        The reference re-runs setup_bundles in every generate_rays call
+        (_XicsrtPlasmaGeneric.py:384-393): new bundle centres and ray counts each iteration.
+        """
+        if self.is_plasma and iteration > 0:
+            self._upload(iteration)
+
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -251,6 +275,7 @@ def run_iteration(tracer, stream_id, keep_history=True, keep_images=True, keep_m
     reduced meta / images are still returned; histories hold the rank's own rays.
     """
     out = _skeleton(tracer.config)
+    tracer.begin_iteration(stream_id)
     names = tracer.layout.element_names
     if keep_history:
         lost_quota = max_lost if tracer.world == 1 else max(1, max_lost // tracer.world)

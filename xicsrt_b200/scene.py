@@ -145,7 +145,8 @@ def fill_source(src, param, filters, keep, bundles=None):
             raise NotImplementedError('plasma sources with a natural linewidth (per-bundle Voigt tables)')
         src.voxel_size = float(param['voxel_size'])
         src.n_bundles = len(bundles['end'])
-        src.bundles = keep.obj(bundles['table'])
+        table = keep.obj(np.ascontiguousarray(bundles['table']))
+        src.bundles = C.cast(table.ctypes.data, C.POINTER(L.XrtBundle))
         src.bundle_end = keep.arr(bundles['end'], np.uint64, C.c_uint64)
         _set(src.extent, [param['voxel_size']] * 3)
     else:
