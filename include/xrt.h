@@ -90,31 +90,35 @@ typedef struct XrtAperture {
     double vert[6];         /* triangle: x0 y0 x1 y1 x2 y2 (origin already added)          */
 } XrtAperture;
 
-/* triangle mesh tables of one ShapeMesh optic (xicsrt/optics/_ShapeMesh.py:198-287) */
+/* triangle mesh tables of one ShapeMesh optic (xicsrt/optics/_ShapeMesh.py:198-287).
+   All tables are built on the host at setup time (xicsrt_b200/mesh.py); the Clough-Tocher
+   interpolators of the reference (scipy objects) become plain coefficient tables. */
 typedef struct XrtMesh {
     int32_t n_points, n_faces;
     const double *points;        /* [n_points][3]                                        */
     const int32_t *faces;        /* [n_faces][3]                                         */
     const double *face_normals;  /* [n_faces][3]                                         */
+    const double *face_geom;     /* [n_faces][9]: p0, p1 - p0, p2 - p0 (Moeller-Trumbore) */
     int32_t n_coarse_points, n_coarse_faces;   /* 0 when there is no coarse mesh         */
     const double *coarse_points;
     const int32_t *coarse_faces;
+    const double *coarse_geom;   /* [n_coarse_faces][9]                                  */
     const int32_t *point_faces;  /* [8][n_points] faces around each fine point           */
     const uint8_t *point_faces_mask; /* [8][n_points]                                    */
     /* Clough-Tocher interpolation of z and the normal over the xy Delaunay triangulation */
     int32_t n_tri;               /* 0 when mesh_interpolate is off                       */
-    const int32_t *tri;          /* [n_tri][3] vertex ids                                */
-    const int32_t *tri_neighbors;/* [n_tri][3], -1 on the hull                           */
-    const double *tri_xy;        /* [n_points][2] (= points[:, 0:2])                     */
-    const double *values;        /* [n_points][4]  z, nx, ny, nz                         */
-    const double *grads;         /* [n_points][4][2] scipy's estimated vertex gradients  */
-    /* uniform xy lookup grid over the triangulation (built by the host side)            */
+    int32_t pad0;
+    const double *ct_coef;       /* [n_tri][4][19] Bezier control coefficients of the cubic
+                                    macro element, fields z, nx, ny, nz                  */
+    const double *tri_transform; /* [n_tri][3][2] barycentric transform (scipy layout:
+                                    rows 0,1 = inverse edge matrix, row 2 = third vertex) */
+    /* uniform xy grid over the mesh footprint                                           */
     int32_t grid_nx, grid_ny;
     double grid_x0, grid_y0, grid_inv_dx, grid_inv_dy;
-    const int32_t *grid_start;   /* [grid_nx*grid_ny + 1]                                */
+    const int32_t *grid_start;   /* [grid_nx*grid_ny + 1] triangles touching each cell   */
     const int32_t *grid_items;   /* triangle ids                                         */
-    /* kd-tree replacement: nearest fine vertex is found through the same grid           */
-    const int32_t *vgrid_start;  /* [grid_nx*grid_ny + 1] vertices per cell              */
+    const int32_t *vgrid_start;  /* [grid_nx*grid_ny + 1] vertices in each cell (nearest-
+                                    vertex query, replaces the reference's kd-tree)      */
     const int32_t *vgrid_items;
 } XrtMesh;
 

@@ -53,9 +53,82 @@ def plasma_datafile(seed=24):
     return assemble(src, {'crystal': crystal_G(radius=1.0, rocking_fwhm=2000e-6), 'detector': detector_G()}, seed)
 
 
+def _mesh_optic(class_name, **kw):
+    c = crystal_G(class_name, check_bragg=False, rocking_fwhm=2000e-6)
+    c.update(kw)
+    return c
+
+
+def mesh_torus(n=4000, seed=31, mesh_size=(21, 21), **kw):
+    """config 4: XicsrtOpticMeshToroidalCrystal, coarse -> fine refinement + Clough-Tocher interpolation."""
+    from oracle.scenes import source_G
+    c = _mesh_optic('XicsrtOpticMeshToroidalCrystal', radius_major=1.0, radius_minor=0.2,
+                    mesh_size=mesh_size, mesh_coarse_size=(5, 5), **kw)
+    return assemble(source_G(n), {'crystal': c, 'detector': detector_G(xsize=1.0, ysize=1.0, pixel_size=0.01)}, seed)
+
+
+def mesh_sphere(n=4000, seed=32):
+    from oracle.scenes import source_G
+    c = _mesh_optic('XicsrtOpticMeshSphericalCrystal', radius=1.0, mesh_size=(15, 15), mesh_coarse_size=(4, 4),
+                    check_bragg=True)
+    return assemble(source_G(n), {'crystal': c, 'detector': detector_G()}, seed)
+
+
+def mesh_cylinder(n=4000, seed=33):
+    from oracle.scenes import source_G
+    c = _mesh_optic('XicsrtOpticMeshCylindricalCrystal', radius=1.0, mesh_size=(13, 17), mesh_coarse_size=(5, 5))
+    return assemble(source_G(n), {'crystal': c, 'detector': detector_G(xsize=1.0, ysize=1.0, pixel_size=0.01)}, seed)
+
+
+def _user_mesh(nx=9, ny=7):
+    """A hand-made saddle surface in local coordinates with analytic normals."""
+    x = np.linspace(-0.1, 0.1, nx)
+    y = np.linspace(-0.1, 0.1, ny)
+    xx, yy = np.meshgrid(x, y, indexing='ij')
+    zz = 0.4 * xx**2 - 0.3 * yy**2 + 0.05 * xx * yy
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1)
+    nrm = np.stack([-(0.8 * xx + 0.05 * yy).ravel(), -(-0.6 * yy + 0.05 * xx).ravel(), np.ones(xx.size)], axis=1)
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    return pts, nrm
+
+
+def mesh_user_flat(n=4000, seed=34):
+    """XicsrtOpticMeshMirror with user points only: all faces tested, flat face normals, no interpolation."""
+    from oracle.scenes import source_G
+    pts, _ = _user_mesh()
+    m = {'class_name': 'XicsrtOpticMeshMirror', 'origin': [0.0, 0.0, 0.80374151],
+         'zaxis': [0.0, 0.59497864, -0.80374151], 'xsize': 0.2, 'ysize': 0.2, 'trace_local': True,
+         'mesh_points': pts}
+    return assemble(source_G(n), {'mirror': m, 'detector': detector_G(xsize=1.0, ysize=1.0, pixel_size=0.01)}, seed)
+
+
+def mesh_user_interp(n=4000, seed=35):
+    """XicsrtOpticMeshCrystal with user points + normals (interpolation on, no coarse mesh)."""
+    from oracle.scenes import source_G
+    pts, nrm = _user_mesh(11, 11)
+    c = _mesh_optic('XicsrtOpticMeshCrystal', trace_local=True, mesh_points=pts, mesh_normals=nrm)
+    return assemble(source_G(n), {'crystal': c, 'detector': detector_G(xsize=1.0, ysize=1.0, pixel_size=0.01)}, seed)
+
+
+def mesh_mosaic(n=3000, seed=36):
+    """XicsrtOpticMeshMosaicCrystal on user points + normals."""
+    from oracle.scenes import source_G
+    pts, nrm = _user_mesh(11, 11)
+    c = _mesh_optic('XicsrtOpticMeshMosaicCrystal', trace_local=True, mesh_points=pts, mesh_normals=nrm,
+                    check_bragg=True, mosaic_spread=np.radians(0.4), mosaic_depth=4, rocking_fwhm=2000e-6)
+    return assemble(source_G(n), {'crystal': c, 'detector': detector_G(xsize=1.0, ysize=1.0, pixel_size=0.01)}, seed)
+
+
 EXTRA = {
     'plasma_cubic': plasma_cubic,
     'plasma_cubic_poisson': plasma_cubic_poisson,
     'plasma_toroidal': plasma_toroidal,
     'plasma_datafile': plasma_datafile,
+    'mesh_torus': mesh_torus,
+    'mesh_torus_convex': lambda: mesh_torus(seed=37, convex=[True, False], mesh_size=(15, 15)),
+    'mesh_sphere': mesh_sphere,
+    'mesh_cylinder': mesh_cylinder,
+    'mesh_user_flat': mesh_user_flat,
+    'mesh_user_interp': mesh_user_interp,
+    'mesh_mosaic': mesh_mosaic,
 }

@@ -178,7 +178,8 @@ def test_runs_use_cumulative_seeds_and_combine(torch):
 
 
 @pytest.mark.parametrize('name', ['sphere', 'sphere_step_box', 'apertures', 'mosaic_sphere', 'torus_bragg',
-                                  'local_frames', 'plane_mirror', 'sphere_voigt'])
+                                  'local_frames', 'plane_mirror', 'sphere_voigt', 'mesh_torus', 'mesh_user_flat',
+                                  'mesh_mosaic', 'plasma_toroidal'])
 def test_fused_kernel_equals_replay_kernel(torch, name):
     """
     The staged fused kernel (queues, lazy wavelength) and the straight per-ray replay kernel
@@ -186,10 +187,13 @@ def test_fused_kernel_equals_replay_kernel(torch, name):
     identical, ray for ray.
     """
     from xicsrt_b200 import _driver, config as xconfig, elements
-    n = 300000
     cfg = scenes.get(name)
-    cfg['sources']['source']['intensity'] = n
+    if name.startswith('plasma'):
+        cfg['sources']['source']['time_resolution'] *= 500
+    else:
+        cfg['sources']['source']['intensity'] = 300000
     tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), seed=99)
+    n = tracer.n_rays
     found, lost = tracer.select_ids(5, 500)
     meta, image = tracer.counts_and_images(True)
     ids = torch.arange(n, dtype=torch.int64, device=tracer.device)

@@ -468,23 +468,24 @@ static int upload(XrtScene *s, const T *host, size_t count, const T **dev) {
 
 static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     XrtMesh m = *host;
-    UP(m.points, 3 * (size_t)m.n_points);
-    UP(m.faces, 3 * (size_t)m.n_faces);
-    UP(m.face_normals, 3 * (size_t)m.n_faces);
-    UP(m.coarse_points, 3 * (size_t)m.n_coarse_points);
-    UP(m.coarse_faces, 3 * (size_t)m.n_coarse_faces);
-    UP(m.point_faces, 8 * (size_t)m.n_points);
-    UP(m.point_faces_mask, 8 * (size_t)m.n_points);
-    UP(m.tri, 3 * (size_t)m.n_tri);
-    UP(m.tri_neighbors, 3 * (size_t)m.n_tri);
-    UP(m.tri_xy, m.n_tri ? 2 * (size_t)m.n_points : 0);
-    UP(m.values, m.n_tri ? 4 * (size_t)m.n_points : 0);
-    UP(m.grads, m.n_tri ? 8 * (size_t)m.n_points : 0);
+    if (m.n_points <= 0 || m.n_faces <= 0 || !m.points || !m.faces || !m.face_normals || !m.face_geom)
+        return fail(XRT_EINVAL, "mesh: points / faces missing");
     size_t cells = (size_t)m.grid_nx * (size_t)m.grid_ny;
     int32_t n_items = 0, n_vitems = 0;
     if (cells && m.grid_start) n_items = m.grid_start[cells];
     if (cells && m.vgrid_start) n_vitems = m.vgrid_start[cells];
-    UP(m.grid_start, cells ? cells + 1 : 0);
+    UP(m.points, 3 * (size_t)m.n_points);
+    UP(m.faces, 3 * (size_t)m.n_faces);
+    UP(m.face_normals, 3 * (size_t)m.n_faces);
+    UP(m.face_geom, 9 * (size_t)m.n_faces);
+    UP(m.coarse_points, 3 * (size_t)m.n_coarse_points);
+    UP(m.coarse_faces, 3 * (size_t)m.n_coarse_faces);
+    UP(m.coarse_geom, 9 * (size_t)m.n_coarse_faces);
+    UP(m.point_faces, 8 * (size_t)m.n_points);
+    UP(m.point_faces_mask, 8 * (size_t)m.n_points);
+    UP(m.ct_coef, 4 * 19 * (size_t)m.n_tri);
+    UP(m.tri_transform, 6 * (size_t)m.n_tri);
+    UP(m.grid_start, (cells && m.grid_start) ? cells + 1 : 0);
     UP(m.grid_items, n_items);
     UP(m.vgrid_start, (cells && m.vgrid_start) ? cells + 1 : 0);
     UP(m.vgrid_items, n_vitems);
@@ -577,6 +578,12 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         UP(m.rock_p, tab ? m.n_rock : 0);
         if (m.shape == XRT_SHAPE_MESH) {
             if (!m.mesh) return fail(XRT_EINVAL, "optic %d: mesh tables missing", k);
+            if ((m.flags & XRT_F_MESH_REFINE) && (m.mesh->n_coarse_faces <= 0 || !m.mesh->coarse_geom ||
+                                                  !m.mesh->vgrid_start || !m.mesh->point_faces))
+                return fail(XRT_EINVAL, "optic %d: mesh refinement needs the coarse mesh and the vertex grid", k);
+            if ((m.flags & XRT_F_MESH_INTERP) && (m.mesh->n_tri <= 0 || !m.mesh->ct_coef || !m.mesh->tri_transform ||
+                                                  !m.mesh->grid_start))
+                return fail(XRT_EINVAL, "optic %d: mesh interpolation needs the Clough-Tocher tables", k);
             int rc = upload_mesh(s, m.mesh, &m.mesh);
             if (rc != XRT_OK) return rc;
         } else {

@@ -1,17 +1,187 @@
 // xrt_mesh.cuh -- triangle-mesh optics (xicsrt/optics/_ShapeMesh.py).
+//
+// The reference intersects a mesh in up to four steps, each restated here per ray:
+//   1. Moeller-Trumbore against every face of the mesh -- of the coarse mesh when
+//      mesh_refine is set (:289-348).  No test on t; a later face overwrites an earlier hit.
+//   2. (refine) nearest fine vertex of the coarse hit point (cKDTree.query, :464-475) and the
+//      <= 8 faces around it.
+//   3. (refine) ray/plane point for each candidate face, inside test by area sum with a 1e-10
+//      tolerance, t >= 0, first passing candidate wins (:350-426).
+//   4. (interpolate) z and the normal from Clough-Tocher interpolators over the xy Delaunay
+//      triangulation (:172-196); otherwise the flat normal of the face that was hit (:428-432).
+//
+// Tables come from xicsrt_b200/mesh.py.  All lanes of a warp walk the face list in the same
+// order, so the face operands are warp-uniform loads (one L1 transaction per load).
 #pragma once
 #include "../../include/xrt.h"
 #include "xrt_math.cuh"
 
 namespace xrt {
 
-// Filled in with the mesh row of the scope table; until then a scene holding a
-// mesh optic is refused by xrt_scene_create (XRT_EUNSUPPORTED), so this is
-// never reached.
-__device__ __forceinline__ bool mesh_intersect(const XrtOpticDesc &, V3, V3, V3 &X, V3 &n) {
+__device__ __forceinline__ V3 ld3(const double *p) { return v3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+
+// step 1.  geom: [n_faces][9] = p0, edge1, edge2.  Returns the index of the last face hit or -1.
+__device__ __forceinline__ int mesh_all_faces(const double *__restrict__ geom, int n_faces, V3 o, V3 d, V3 &X) {
+    const double eps = 1e-15;
+    int hit = -1;
+    for (int f = 0; f < n_faces; ++f) {
+        const double *g = geom + 9 * f;
+        const V3 p0 = ld3(g), e1 = ld3(g + 3), e2 = ld3(g + 6);
+        const V3 h = cross(d, e2);
+        double a = dot(e1, h);
+        if (a > -eps && a < eps) continue;
+        a = 1.0 / a;
+        const V3 s = o - p0;
+        const double u = a * dot(s, h);
+        if (u < 0.0 || u > 1.0) continue;
+        const V3 q = cross(s, e1);
+        const double v = a * dot(d, q);
+        if (v < 0.0 || u + v > 1.0) continue;
+        const double t = a * dot(e2, q);
+        hit = f;
+        X = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    }
+    return hit;
+}
+
+// step 2: exact nearest vertex through the uniform xy grid -- rings of cells around the query
+// cell until no unvisited cell can hold a closer vertex (the xy distance to the ring bounds
+// the 3-D distance from below).
+__device__ __forceinline__ int mesh_nearest_vertex(const XrtMesh &m, V3 q) {
+    const int nx = m.grid_nx, ny = m.grid_ny;
+    const double dx = 1.0 / m.grid_inv_dx, dy = 1.0 / m.grid_inv_dy;
+    int cx = (int)floor((q.x - m.grid_x0) * m.grid_inv_dx);
+    int cy = (int)floor((q.y - m.grid_y0) * m.grid_inv_dy);
+    cx = min(max(cx, 0), nx - 1);
+    cy = min(max(cy, 0), ny - 1);
+    int best = -1;
+    double best_d2 = CUDART_INF;
+    const int max_ring = max(nx, ny);
+    for (int ring = 0; ring <= max_ring; ++ring) {
+        if (ring > 0) {
+            const double ox = fmin(q.x - (m.grid_x0 + (cx - ring + 1) * dx), (m.grid_x0 + (cx + ring) * dx) - q.x);
+            const double oy = fmin(q.y - (m.grid_y0 + (cy - ring + 1) * dy), (m.grid_y0 + (cy + ring) * dy) - q.y);
+            const double bound = fmax(fmin(ox, oy), 0.0);
+            if (bound * bound > best_d2) break;
+        }
+        for (int yy = cy - ring; yy <= cy + ring; ++yy) {
+            if (yy < 0 || yy >= ny) continue;
+            const bool edge_row = (yy == cy - ring) || (yy == cy + ring);
+            const int step = edge_row ? 1 : 2 * ring;       // interior rows: only the two end cells
+            for (int xx = cx - ring; xx <= cx + ring; xx += (step > 0 ? step : 1)) {
+                if (xx < 0 || xx >= nx) continue;
+                const int c = yy * nx + xx;
+                const int b = __ldg(m.vgrid_start + c), e = __ldg(m.vgrid_start + c + 1);
+                for (int k = b; k < e; ++k) {
+                    const int v = __ldg(m.vgrid_items + k);
+                    const V3 p = ld3(m.points + 3 * v) - q;
+                    const double d2 = dot(p, p);
+                    if (d2 < best_d2) { best_d2 = d2; best = v; }
+                }
+            }
+        }
+    }
+    return best;
+}
+
+// step 3: the faces around vertex `vert`
+__device__ __forceinline__ int mesh_candidate_faces(const XrtMesh &m, int vert, V3 o, V3 d, V3 &X) {
+    for (int k = 0; k < 8; ++k) {
+        if (!__ldg(m.point_faces_mask + (size_t)k * m.n_points + vert)) continue;
+        const int f = __ldg(m.point_faces + (size_t)k * m.n_points + vert);
+        const int i0 = __ldg(m.faces + 3 * f), i1 = __ldg(m.faces + 3 * f + 1), i2 = __ldg(m.faces + 3 * f + 2);
+        const V3 p0 = ld3(m.points + 3 * i0), p1 = ld3(m.points + 3 * i1), p2 = ld3(m.points + 3 * i2);
+        const V3 n = ld3(m.face_normals + 3 * f);
+        const double dist = dot(p0 - o, n) / dot(d, n);
+        const V3 P = v3(d.x * dist + o.x, d.y * dist + o.y, d.z * dist + o.z);
+        const V3 a = P - p0, b = P - p1, c = P - p2;
+        const V3 bc = cross(b, c), ca = cross(c, a), ab = cross(a, b), area = cross(p0 - p1, p0 - p2);
+        const double diff = sqrt(dot(bc, bc)) + sqrt(dot(ca, ca)) + sqrt(dot(ab, ab)) - sqrt(dot(area, area));
+        if (diff < 1e-10 && dist >= 0.0) {
+            X = P;
+            return f;
+        }
+    }
+    return -1;
+}
+
+// step 4: triangle of the xy Delaunay triangulation that holds (x, y): scipy's containment
+// rule (all barycentric coordinates within [-eps, 1 + eps], eps = 100 DBL_EPSILON) on the
+// triangles registered in the point's grid cell.  -1 = outside the hull (scipy returns NaN).
+__device__ __forceinline__ int mesh_find_triangle(const XrtMesh &m, double x, double y, double &b0, double &b1, double &b2) {
+    if (!(x == x) || !(y == y)) return -1;
+    int cx = (int)floor((x - m.grid_x0) * m.grid_inv_dx);
+    int cy = (int)floor((y - m.grid_y0) * m.grid_inv_dy);
+    cx = min(max(cx, 0), m.grid_nx - 1);
+    cy = min(max(cy, 0), m.grid_ny - 1);
+    const int c = cy * m.grid_nx + cx;
+    const int b = __ldg(m.grid_start + c), e = __ldg(m.grid_start + c + 1);
+    const double eps = 100.0 * 2.220446049250313e-16;
+    for (int k = b; k < e; ++k) {
+        const int t = __ldg(m.grid_items + k);
+        const double *T = m.tri_transform + 6 * (size_t)t;
+        const double ddx = x - __ldg(T + 4), ddy = y - __ldg(T + 5);
+        b0 = __ldg(T + 0) * ddx + __ldg(T + 1) * ddy;
+        b1 = __ldg(T + 2) * ddx + __ldg(T + 3) * ddy;
+        b2 = 1.0 - b0 - b1;
+        if (b0 >= -eps && b0 <= 1.0 + eps && b1 >= -eps && b1 <= 1.0 + eps && b2 >= -eps && b2 <= 1.0 + eps) return t;
+    }
+    return -1;
+}
+
+// the cubic of one field: coefficient order of xicsrt_b200/mesh.py CT_NAMES
+//  0 c3000  1 c0300  2 c0030  3 c0003  4 c2100  5 c2010  6 c2001  7 c1200  8 c0210  9 c0201
+// 10 c1020 11 c0120 12 c0021 13 c1002 14 c0102 15 c0012 16 c1101 17 c1011 18 c0111
+__device__ __forceinline__ double ct_cubic(const double *__restrict__ c, double b1, double b2, double b3, double b4) {
+    const double b11 = b1 * b1, b22 = b2 * b2, b33 = b3 * b3, b44 = b4 * b4;
+    double w = b11 * b1 * __ldg(c + 0) + b22 * b2 * __ldg(c + 1) + b33 * b3 * __ldg(c + 2) + b44 * b4 * __ldg(c + 3);
+    w += 3.0 * (b11 * (b2 * __ldg(c + 4) + b3 * __ldg(c + 5) + b4 * __ldg(c + 6))
+                + b22 * (b1 * __ldg(c + 7) + b3 * __ldg(c + 8) + b4 * __ldg(c + 9))
+                + b33 * (b1 * __ldg(c + 10) + b2 * __ldg(c + 11) + b4 * __ldg(c + 12))
+                + b44 * (b1 * __ldg(c + 13) + b2 * __ldg(c + 14) + b3 * __ldg(c + 15)));
+    w += 6.0 * (b1 * b2 * b4 * __ldg(c + 16) + b1 * b3 * b4 * __ldg(c + 17) + b2 * b3 * b4 * __ldg(c + 18));
+    return w;
+}
+
+// ShapeMesh.intersect (:135-170).  o, d in the optic's tracing frame.
+__device__ __forceinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n) {
+    const XrtMesh &m = *op.mesh;
     X = nan3();
     n = nan3();
-    return false;
+    int face;
+    if (!(op.flags & XRT_F_MESH_REFINE)) {
+        face = mesh_all_faces(m.face_geom, m.n_faces, o, d, X);
+    } else {
+        V3 Xc = nan3();
+        face = mesh_all_faces(m.coarse_geom, m.n_coarse_faces, o, d, Xc);
+        if (face >= 0) {
+            const int vert = mesh_nearest_vertex(m, Xc);
+            face = (vert >= 0) ? mesh_candidate_faces(m, vert, o, d, X) : -1;
+        }
+    }
+    if (face < 0) return false;
+
+    if (op.flags & XRT_F_MESH_INTERP) {
+        // outside the triangulation's hull scipy returns NaN for z and the normal; the ray
+        // stays "hit" and carries the NaNs on, exactly as in the reference
+        double b0, b1, b2;
+        const int t = mesh_find_triangle(m, X.x, X.y, b0, b1, b2);
+        if (t < 0) {
+            X.z = CUDART_NAN;
+            n = nan3();
+        } else {
+            const double mn = fmin(b0, fmin(b1, b2));
+            const double e1 = b0 - mn, e2 = b1 - mn, e3 = b2 - mn, e4 = 3.0 * mn;
+            const double *c = m.ct_coef + (size_t)t * 76;
+            X.z = ct_cubic(c, e1, e2, e3, e4);
+            V3 nn = v3(ct_cubic(c + 19, e1, e2, e3, e4), ct_cubic(c + 38, e1, e2, e3, e4), ct_cubic(c + 57, e1, e2, e3, e4));
+            const double inv = 1.0 / sqrt(dot(nn, nn));
+            n = nn * inv;
+        }
+    } else {
+        n = ld3(m.face_normals + 3 * face);
+    }
+    return true;
 }
 
 }  // namespace xrt
