@@ -63,6 +63,36 @@ def spectrometer(n_rays, seed=0, history=False):
     }
 
 
+def workload_config(name, n_rays, seed=0, history=False):
+    """The BASELINE.json configs: config2 is the headline; the others are measured with --workload."""
+    cfg = spectrometer(n_rays, seed=seed, history=history)
+    crystal = cfg['optics']['crystal']
+    if name == 'config2':
+        return cfg
+    if name == 'config3':          # mosaic HOPG crystal, random mosaic normals, per-ray reflectivity mask
+        crystal.update({'class_name': 'XicsrtOpticSphericalMosaicCrystal', 'mosaic_spread': float(np.radians(0.4)),
+                        'mosaic_depth': 15, 'rocking_fwhm': 200e-6})
+        return cfg
+    if name == 'config4':          # mesh-defined toroidal crystal, coarse/fine refinement + interpolation
+        crystal.pop('radius')
+        crystal.update({'class_name': 'XicsrtOpticMeshToroidalCrystal', 'radius_major': 1.0, 'radius_minor': 0.2,
+                        'mesh_size': (41, 41), 'mesh_coarse_size': (5, 5), 'check_bragg': False})
+        return cfg
+    if name == 'config5':          # extended plasma source -> crystal -> detector
+        # E[rays] = emissivity * dt * bundle_volume * Omega/4pi * volume / (bundle_count * bundle_volume)
+        spread = float(np.radians(2.0))
+        omega = np.sin(spread / 2)**2
+        volume, bundle_count = 0.1**3, 100000
+        cfg['sources']['source'] = {
+            'class_name': 'XicsrtPlasmaCubic', 'origin': [0.0, 0.0, 0.0], 'xsize': 0.1, 'ysize': 0.1, 'zsize': 0.1,
+            'target': [0.0, 0.0, 0.80374151], 'spread': spread, 'bundle_type': 'voxel', 'bundle_volume': 1e-9,
+            'bundle_count': bundle_count, 'use_poisson': True, 'time_resolution': 1.0,
+            'emissivity': float(n_rays) / (omega * volume), 'temperature': 1000.0, 'mass_number': 39.948,
+            'wavelength': 3.9492, 'linewidth': 0.0, 'max_rays': int(4 * n_rays) + 1000}
+        return cfg
+    raise KeyError(name)
+
+
 # ---------------------------------------------------------------------------
 # clocks
 
@@ -200,9 +230,10 @@ def run_gpu_arm(args):
 
     rays_per_gpu = int(args.rays)
     total_rays = rays_per_gpu * world if args.scaling == 'weak' else rays_per_gpu
-    cfg = spectrometer(total_rays, seed=0, history=False)
+    cfg = workload_config(args.workload, total_rays, seed=0, history=False)
     full = xconfig.get_config(xconfig.to_numpy(cfg))
     tracer = xrt.Tracer(full, seed=0, rank=rank, world=world)
+    headline = args.workload == 'config2'
     info = tracer.scene.launch_info()
     lib = tracer.lib
 
@@ -214,6 +245,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     def step(it):
+        tracer.begin_iteration(it)
         tracer.trace(it, keep_images=True)
         tracer.allreduce()
 
@@ -247,6 +279,7 @@ def run_gpu_arm(args):
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the events)
+        tracer.begin_iteration(k)           # plasma sources: new bundle table (host work, outside the events)
         starts[k].record()
         tracer.trace(k, keep_images=True)
         kstops[k].record()
@@ -261,28 +294,30 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     t_steps, t_kernel = (float(v) for v in t_dev.cpu())
-    value = total_rays * args.steps / t_steps
+    launched = tracer.n_rays if tracer.is_plasma else total_rays     # plasma: Poisson total of the last step
+    value = launched * args.steps / t_steps
 
     meta, _ = tracer.counts_and_images(True)
     f_reflect = meta['crystal'] / meta['source']
     n_detected = meta['detector']
 
     # fraction inside the crystal bounds: same scene with the Bragg test off (1e7 rays, untimed)
-    cfg_b = spectrometer(10_000_000, seed=1)
-    cfg_b['optics']['crystal']['check_bragg'] = False
-    tb = xrt.Tracer(xconfig.get_config(xconfig.to_numpy(cfg_b)), seed=1)
-    tb.trace(0)
-    mb, _ = tb.counts_and_images(False)
-    f_bounds = mb['crystal'] / mb['source']
-    tb.close()
-    F = flops_per_ray(f_bounds, f_reflect)
-    kernel_rays_per_s = rays_per_gpu * args.steps / t_kernel if args.scaling == 'weak' else \
-        (total_rays / world) * args.steps / t_kernel
-    achieved = kernel_rays_per_s * F / 1e12
+    f_bounds, F = None, None
+    if headline:
+        cfg_b = spectrometer(10_000_000, seed=1)
+        cfg_b['optics']['crystal']['check_bragg'] = False
+        tb = xrt.Tracer(xconfig.get_config(xconfig.to_numpy(cfg_b)), seed=1)
+        tb.trace(0)
+        mb, _ = tb.counts_and_images(False)
+        f_bounds = mb['crystal'] / mb['source']
+        tb.close()
+        F = flops_per_ray(f_bounds, f_reflect)
+    kernel_rays_per_s = (launched / world) * args.steps / t_kernel
+    achieved = kernel_rays_per_s * F / 1e12 if F else None
 
     # ---- history pass (HBM bound): replay 2^24 ray ids with every element stored
     hist_line = None
-    if rank == 0:
+    if rank == 0 and headline:
         n_h = 1 << 24
         ids = torch.arange(n_h, dtype=torch.int64, device=dev)
         tracer.history(0, ids)
@@ -307,27 +342,28 @@ def run_gpu_arm(args):
     tracer.close()
 
     # ---- end to end through the public API (host dict in, host dict out)
-    e2e_cfg = spectrometer(total_rays, seed=0, history=False)
     for w in range(min(args.warmup, 2)):
-        c = spectrometer(total_rays, seed=50 + w, history=False)
+        c = workload_config(args.workload, total_rays, seed=50 + w, history=False)
         xicsrt_b200.raytrace(c)
     barrier()
     t0 = time.perf_counter()
+    e2e_rays = 0
     for k in range(args.steps):
-        c = spectrometer(total_rays, seed=k, history=False)
+        c = workload_config(args.workload, total_rays, seed=k, history=False)
         res = xicsrt_b200.raytrace(c)
+        e2e_rays += int(res['total']['meta']['source']['num_out'])
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = total_rays * args.steps / float(t_e2e.cpu()[0])
+    e2e_value = e2e_rays / float(t_e2e.cpu()[0])
     n_elem = 3
     d2h = 8 * (n_elem + 100 * 100 + 100 * 50)
     h2d = C.sizeof(L.XrtSceneDesc)
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and headline:
         cores = os.cpu_count() or 1
         procs = min(cores, 64)
         cpu_reference_step(200000, procs, procs, seed=7)          # warm the pool / imports
@@ -341,7 +377,7 @@ def run_gpu_arm(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * t_steps / args.steps, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'rays_per_step': total_rays, 'rays_per_gpu_per_step': total_rays // world,
+            'config': {'workload': WORKLOAD if headline else args.workload, 'rays_per_step': launched, 'rays_per_gpu_per_step': total_rays // world,
                        'history': False, 'images': True, 'parallelism': f'ray-id ranges over {world} GPU(s)',
                        'l2': 'flushed between timed steps (256 MiB memset outside the events); the kernel has no global inputs',
                        'launch': info},
@@ -350,10 +386,10 @@ def run_gpu_arm(args):
                     'api': 'xicsrt_b200.raytrace(config)'},
             'gpu_launches': args.steps,
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / fp64_peak, 'traffic': None,
+                         'frac': (achieved / fp64_peak) if achieved else None, 'traffic': None,
                          'flop_equiv_per_ray': F, 'f_bounds': f_bounds, 'f_reflect': f_reflect,
                          'peak_source': 'DFMA-chain microbenchmark (xrt_fp64_burn) measured in this run',
-                         'kernel': 'k_trace<0>', 'kernel_ms_per_step': 1e3 * t_kernel / args.steps},
+                         'kernel': 'k_trace', 'kernel_ms_per_step': 1e3 * t_kernel / args.steps},
             'roofline_history': hist_line,
             'cpu_baseline': cpu,
             'detected_per_step': n_detected,
@@ -373,6 +409,8 @@ def main():
     ap.add_argument('--scaling', choices=['weak', 'strong'], default='weak')
     ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--workload', choices=['config2', 'config3', 'config4', 'config5'], default='config2',
+                    help='BASELINE.json config; config2 (default) is the headline')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -140,6 +140,7 @@ typedef struct XrtOpticDesc {
     double reflectivity;
     double rocking_fwhm;
     double rock_two_sigma2;  /* gaussian: 2 sigma^2 with sigma = fwhm / (2 sqrt(2 ln 2))         */
+    double rock_inv_two_sigma2; /* 1 / rock_two_sigma2                                            */
     double rocking_mix;
     double mosaic_spread;    /* fwhm of crystallite normals [rad]                                */
     double mosaic_sin_sigma; /* sin(sigma) of the crystallite (x, y) offsets, sigma = hwhm/sqrt(2 ln 2) */

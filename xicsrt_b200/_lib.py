@@ -62,7 +62,7 @@ class XrtOpticDesc(C.Structure):
                 ('torus_major', C.c_double), ('torus_minor', C.c_double),
                 ('root_idx', C.c_int32), ('mosaic_depth', C.c_int32),
                 ('two_d', C.c_double), ('inv_two_d', C.c_double), ('reflectivity', C.c_double), ('rocking_fwhm', C.c_double),
-                ('rock_two_sigma2', C.c_double), ('rocking_mix', C.c_double),
+                ('rock_two_sigma2', C.c_double), ('rock_inv_two_sigma2', C.c_double), ('rocking_mix', C.c_double),
                 ('mosaic_spread', C.c_double), ('mosaic_sin_sigma', C.c_double), ('mosaic_angle_cut', C.c_double),
                 ('n_aperture', C.c_int32), ('n_rock', C.c_int32),
                 ('apertures', C.POINTER(XrtAperture)),

@@ -158,7 +158,7 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
 }
 
 // ---- stage B: interaction of the split optic for `cnt` rays popped from queue 1
-template <uint32_t FT>
+template <uint32_t FT, uint32_t KN>
 __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
                                         const WarpCtx &c, int split, bool lazy, uint64_t seed, uint64_t stream_id,
                                         const double *q1, int first, int cnt, double *q2, int &n2) {
@@ -183,14 +183,14 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     if (active) {
         if (lazy) {
             SrcLocal L;
-            source_local<0>(sc.source, id, L);
-            r.w = generate_wavelength(sc.source, L, dr, r.d);
+            source_local<0, KN>(sc.source, id, L);
+            r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
         }
         bool analytic = true;
         if constexpr ((FT & FT_MESH) != 0) analytic = ops.shape != XRT_SHAPE_MESH;
-        if (analytic) n = analytic_normal<FT>(ops, r.o);
-        optic_interact<FT>(ops, split, dr, r, n);
-        if (r.alive && (ops.flags & XRT_F_IMAGE) && out.images) add_pixel(out, ops, r, c.lt_mask);
+        if (analytic) n = analytic_normal<FT, KN>(ops, r.o);
+        optic_interact<FT, PhiloxDraws, KN>(ops, split, dr, r, n);
+        if (r.alive && (flags_of<KN>(ops) & XRT_F_IMAGE) && out.images) add_pixel(out, ops, r, c.lt_mask);
     }
     count_alive(c, split + 1, r.alive);
     emit_lost(out, c, dr, active && !r.alive, id);
@@ -211,7 +211,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     __syncwarp();
 }
 
-template <uint32_t FT, int SPLIT>
+template <uint32_t FT, int SPLIT, uint32_t KN>
 __global__ void __launch_bounds__(kBlock, XRT_MIN_BLOCKS)
 k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
         const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const int split_rt,
@@ -252,7 +252,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         if (n1 >= 32 || (!more && n1 > 0)) {
             const int cnt = n1 < 32 ? n1 : 32;
             n1 -= cnt;
-            stage_b<FT>(sc, ops, out, c, split, lazy, seed, stream_id, q1, n1, cnt, q2, n2);
+            stage_b<FT, KN>(sc, ops, out, c, split, lazy, seed, stream_id, q1, n1, cnt, q2, n2);
             continue;
         }
         if (!more) break;
@@ -269,9 +269,9 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         r.w = 0.0;
         if (valid) {
             SrcLocal L;
-            source_local<FT>(sc.source, id, L);
-            generate_geometry<FT>(sc.source, L, dr, r);
-            if (!lazy) r.w = generate_wavelength(sc.source, L, dr, r.d);
+            source_local<FT, KN>(sc.source, id, L);
+            generate_geometry<FT, PhiloxDraws, KN>(sc.source, L, dr, r);
+            if (!lazy) r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
         }
         count_alive(c, 0, r.alive);
         for (int k = 0; k < split; ++k) {
@@ -284,7 +284,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         }
         V3 n = v3(0.0, 0.0, 1.0);
         bool cand = false;
-        if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0>(ops, r, n) == HIT_INSIDE;
+        if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n) == HIT_INSIDE;
         emit_lost(out, c, dr, valid && !cand, id);
 
         const unsigned m = __ballot_sync(kFull, cand);
@@ -427,6 +427,7 @@ struct XrtScene {
     uint32_t features;
     int split;                      // first crystal of the train (0 if none): the kernel's re-pack point
     int lazy_wavelength;            // wavelength independent of the source direction: drawn at the crystal
+    uint32_t known;                 // KN_* facts that hold for this scene (source + split optic)
     int device;
     int sm_count;
 };
@@ -602,6 +603,19 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
                           src.velocity_c[2] == 0.0) ? 1 : 0;
     // the lean variant has no wavelength plane in its queue: a source with a Doppler shift needs the full one
     if (s->features == 0 && !s->lazy_wavelength) s->features = FT_MID;
+    s->known = 0;
+    if (d.n_optics > 0) {
+        const XrtOpticDesc &o = d.optics[s->split];
+        if (src.kind == XRT_SRC_FIXED_AXIS && src.extent[0] == 0.0 && src.extent[1] == 0.0 && src.extent[2] == 0.0)
+            s->known |= KN_POINT_SOURCE;
+        if (src.wave == XRT_WAVE_NORMAL) s->known |= KN_WAVE_NORMAL;
+        if (o.shape == XRT_SHAPE_SPHERE && !(o.flags & XRT_F_CONVEX)) s->known |= KN_SPHERE;
+        const uint32_t size_bits = XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE | XRT_F_HAS_ZSIZE;
+        if ((o.flags & size_bits) == (XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE)) s->known |= KN_BOUNDS_XY;
+        if (o.interact == XRT_INTERACT_CRYSTAL && (o.flags & XRT_F_CHECK_BRAGG) && o.rocking_type == XRT_ROCK_GAUSS)
+            s->known |= KN_CRYSTAL_GAUSS;
+        if (o.flags & XRT_F_IMAGE) s->known |= KN_IMAGE;
+    }
     return XRT_OK;
 }
 
@@ -641,10 +655,10 @@ typedef void (*TraceKernel)(const XrtSceneDesc, const uint64_t, const uint64_t, 
 template <uint32_t FT>
 static TraceKernel trace_kernel_ft(int split) {
     switch (split) {
-    case 0: return k_trace<FT, 0>;
-    case 1: return k_trace<FT, 1>;
-    case 2: return k_trace<FT, 2>;
-    default: return k_trace<FT, -1>;
+    case 0: return k_trace<FT, 0, 0>;
+    case 1: return k_trace<FT, 1, 0>;
+    case 2: return k_trace<FT, 2, 0>;
+    default: return k_trace<FT, -1, 0>;
     }
 }
 
@@ -652,6 +666,9 @@ static TraceKernel trace_kernel(const XrtScene *s, size_t *smem) {
     const size_t warps = kBlock / 32;
     if (s->features == 0) {
         *smem = warps * warp_queue_doubles<0>() * sizeof(double);
+        // pre-instantiated structure: point source with a Gaussian line on a concave spherical
+        // Bragg crystal as first optic -- the spherical-crystal spectrometer
+        if (s->split == 0 && (s->known & KN_SPECTROMETER) == KN_SPECTROMETER) return k_trace<0, 0, KN_SPECTROMETER>;
         return trace_kernel_ft<0>(s->split);
     }
     if (s->features == FT_MID) {

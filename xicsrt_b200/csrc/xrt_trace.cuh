@@ -28,6 +28,39 @@ enum : uint32_t {
     FT_FULL = FT_MID | FT_MESH,
 };
 
+// Known-structure mask KN: facts about the source and the split optic that a pre-instantiated
+// kernel variant may assume at compile time (the host checks them at scene creation).  The
+// generic code reads the same facts from the descriptor; with a KN bit set the accessor
+// returns the constant, so the branch on it -- and the code of the other cases -- disappears.
+enum : uint32_t {
+    KN_POINT_SOURCE = 1u << 0,   // source.kind == FIXED_AXIS and a zero-size origin box
+    KN_WAVE_NORMAL = 1u << 1,    // source.wave == XRT_WAVE_NORMAL
+    KN_SPHERE = 1u << 2,         // split optic: concave sphere
+    KN_BOUNDS_XY = 1u << 3,      // split optic: check_size with xsize and ysize, no zsize
+    KN_CRYSTAL_GAUSS = 1u << 4,  // split optic: crystal with Bragg test, Gaussian rocking curve
+    KN_IMAGE = 1u << 5,          // split optic: has a pixel grid
+    KN_SPECTROMETER = KN_POINT_SOURCE | KN_WAVE_NORMAL | KN_SPHERE | KN_BOUNDS_XY | KN_CRYSTAL_GAUSS | KN_IMAGE,
+};
+
+template <uint32_t KN> __device__ __forceinline__ int shape_of(const XrtOpticDesc &op) {
+    if constexpr ((KN & KN_SPHERE) != 0) return XRT_SHAPE_SPHERE; else return op.shape;
+}
+template <uint32_t KN> __device__ __forceinline__ int interact_of(const XrtOpticDesc &op) {
+    if constexpr ((KN & KN_CRYSTAL_GAUSS) != 0) return XRT_INTERACT_CRYSTAL; else return op.interact;
+}
+template <uint32_t KN> __device__ __forceinline__ int rocking_of(const XrtOpticDesc &op) {
+    if constexpr ((KN & KN_CRYSTAL_GAUSS) != 0) return XRT_ROCK_GAUSS; else return op.rocking_type;
+}
+template <uint32_t KN> __device__ __forceinline__ uint32_t flags_of(const XrtOpticDesc &op) {
+    uint32_t f = op.flags;
+    if constexpr ((KN & KN_SPHERE) != 0) f &= ~(uint32_t)XRT_F_CONVEX;
+    if constexpr ((KN & KN_BOUNDS_XY) != 0)
+        f = (f | XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE) & ~(uint32_t)XRT_F_HAS_ZSIZE;
+    if constexpr ((KN & KN_CRYSTAL_GAUSS) != 0) f |= XRT_F_CHECK_BRAGG;
+    if constexpr ((KN & KN_IMAGE) != 0) f |= XRT_F_IMAGE;
+    return f;
+}
+
 struct Ray {
     V3 o, d;
     double w;
@@ -144,13 +177,14 @@ struct SrcLocal {
     double cos_spread, wave_sigma, ext0, ext1, ext2;
 };
 
-template <uint32_t FT>
+template <uint32_t FT, uint32_t KN = 0>
 __device__ __forceinline__ void source_local(const XrtSourceDesc &s, uint64_t index, SrcLocal &L) {
     L.org = v3(s.origin);
     L.vel = v3(s.velocity_c);
     L.cos_spread = s.cone_par[0];
     L.wave_sigma = s.wave_par[1];
-    L.ext0 = s.extent[0]; L.ext1 = s.extent[1]; L.ext2 = s.extent[2];
+    if constexpr ((KN & KN_POINT_SOURCE) != 0) { L.ext0 = L.ext1 = L.ext2 = 0.0; }
+    else { L.ext0 = s.extent[0]; L.ext1 = s.extent[1]; L.ext2 = s.extent[2]; }
     if constexpr ((FT & FT_SRC_EXT) != 0) {
         if (s.kind == XRT_SRC_BUNDLES) {
             // bundle of this ray: first b with bundle_end[b] > index
@@ -170,7 +204,7 @@ __device__ __forceinline__ void source_local(const XrtSourceDesc &s, uint64_t in
 }
 
 // origin, direction and the source-level mask
-template <uint32_t FT, class DR>
+template <uint32_t FT, class DR, uint32_t KN = 0>
 __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const SrcLocal &L, const DR &dr, Ray &r) {
     // ---- origin (:229-255): three draws of U(-size/2, size/2), or N(0, sigma)
     double off[3] = {0.0, 0.0, 0.0};
@@ -241,7 +275,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
 
     // ---- cone axis and basis (:262-293): rows (o_2, o_1, axis)
     V3 ax, o1, o2;
-    if (s.kind == XRT_SRC_FIXED_AXIS) {
+    if (((KN & KN_POINT_SOURCE) != 0) || s.kind == XRT_SRC_FIXED_AXIS) {
         // constant for every ray: precomputed on the host with the reference's formula
         o2 = v3(s.axis_basis[0], s.axis_basis[1], s.axis_basis[2]);
         o1 = v3(s.axis_basis[3], s.axis_basis[4], s.axis_basis[5]);
@@ -270,10 +304,10 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
 }
 
 // wavelength (:295-367); `dir` is the ray direction at the source (Doppler shift)
-template <class DR>
+template <class DR, uint32_t KN = 0>
 __device__ __forceinline__ double generate_wavelength(const XrtSourceDesc &s, const SrcLocal &L, const DR &dr, V3 dir) {
     double w;
-    if (s.wave == XRT_WAVE_NORMAL) {
+    if (((KN & KN_WAVE_NORMAL) != 0) || s.wave == XRT_WAVE_NORMAL) {
         w = s.wave_par[0] + L.wave_sigma * dr.wave_z();
     } else if (s.wave == XRT_WAVE_CONST) {
         w = s.wave_par[0];
@@ -318,14 +352,14 @@ __device__ __forceinline__ bool hit_plane(const XrtOpticDesc &op, bool local, V3
 // _ShapeSphere.py:53-100 -- geometric solution; concave takes the larger root, no sign test.
 // The reference forms d = sqrt(L.L - tca^2), tests d <= R and then uses d^2 again; here the
 // square is kept (d^2 < 0 is the reference's NaN -> miss), which saves one square root.
-__device__ __forceinline__ bool hit_sphere(const XrtOpticDesc &op, V3 o, V3 d, double &t) {
+__device__ __forceinline__ bool hit_sphere(const XrtOpticDesc &op, bool convex, V3 o, V3 d, double &t) {
     V3 L = v3(op.center) - o;
     double tca = dot(L, d);
     double d2 = fma(-tca, tca, dot(L, L));
     double r2 = op.radius * op.radius;
     if (!(d2 >= 0.0 && d2 <= r2)) return false;
     double thc = sqrt(r2 - d2);
-    t = (op.flags & XRT_F_CONVEX) ? tca - thc : tca + thc;     // min / max of tca -+ thc (thc >= 0)
+    t = convex ? tca - thc : tca + thc;     // min / max of tca -+ thc (thc >= 0)
     return true;
 }
 
@@ -472,16 +506,17 @@ __device__ __forceinline__ double bragg_dtheta(const XrtOpticDesc &op, V3 d, dou
 }
 
 // true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).
-template <uint32_t FT, class DR>
+template <uint32_t FT, class DR, uint32_t KN = 0>
 __device__ __forceinline__ bool bragg_pass(const XrtOpticDesc &op, int k, int layer, const DR &dr, double dth) {
     double p;
-    if (op.rocking_type == XRT_ROCK_GAUSS) {
+    const int rocking = rocking_of<KN>(op);
+    if (rocking == XRT_ROCK_GAUSS) {
         // sigma = fwhm / (2 sqrt(2 ln 2)); p = exp(-dth^2 / (2 sigma^2))
-        double x = (dth * dth) / op.rock_two_sigma2;
+        double x = (dth * dth) * op.rock_inv_two_sigma2;
         if (x >= 40.0) return dr.bragg_u_is_zero(k, layer);   // p < 2^-57: only u == 0 passes
         if (!(x >= 0.0)) return false;                        // NaN
         p = exp_neg(x);
-    } else if (op.rocking_type == XRT_ROCK_STEP) {
+    } else if (rocking == XRT_ROCK_STEP) {
         p = (fabs(dth) <= op.rocking_fwhm / 2.0) ? 1.0 : 0.0;
     } else {
         p = 0.0;
@@ -593,9 +628,9 @@ __device__ __forceinline__ bool optic_is_local(const XrtOpticDesc &op) {
 }
 
 // surface normal of an analytic shape at X (tracing frame)
-template <uint32_t FT>
+template <uint32_t FT, uint32_t KN = 0>
 __device__ __forceinline__ V3 analytic_normal(const XrtOpticDesc &op, V3 X) {
-    const int shape = op.shape;
+    const int shape = shape_of<KN>(op);
     // the plane normal is the element's (global) zaxis even when tracing in local
     // coordinates -- _ShapePlane.py:55-62 does not transform it; replicated.
     if (shape == XRT_SHAPE_PLANE) return v3(op.orient + 6);
@@ -616,9 +651,10 @@ __device__ __forceinline__ void frame_to_external(const XrtOpticDesc &op, bool l
     }
 }
 
-template <uint32_t FT, bool WANT_NORMAL>
+template <uint32_t FT, bool WANT_NORMAL, uint32_t KN = 0>
 __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3 &n) {
     V3 o = r.o, d = r.d;
+    const uint32_t flags = flags_of<KN>(op);
     const bool local = optic_is_local<FT>(op);
     if constexpr ((FT & FT_LOCAL) != 0) {
         if (local) {   // _GeometryObject.py:127-141
@@ -632,16 +668,16 @@ __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3
     bool ok;
     bool analytic = true;
     if constexpr ((FT & FT_MESH) != 0) {
-        if (op.shape == XRT_SHAPE_MESH) {
+        if (shape_of<KN>(op) == XRT_SHAPE_MESH) {
             analytic = false;
             ok = mesh_intersect(op, o, d, X, n);
         }
     }
     if (analytic) {
         double t = 0.0;
-        const int shape = op.shape;
+        const int shape = shape_of<KN>(op);
         if (shape == XRT_SHAPE_PLANE) ok = hit_plane(op, local, o, d, t);
-        else if (shape == XRT_SHAPE_SPHERE) ok = hit_sphere(op, o, d, t);
+        else if (shape == XRT_SHAPE_SPHERE) ok = hit_sphere(op, (flags & XRT_F_CONVEX) != 0, o, d, t);
         else {
             ok = false;
             if constexpr ((FT & FT_CYL) != 0) { if (shape == XRT_SHAPE_CYLINDER) ok = hit_cylinder(op, o, d, t); }
@@ -661,13 +697,13 @@ __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3
     // ---- bounds (_TraceObject.py:180-232): strict |x| < size/2, then apertures
     V3 Xl = local ? X : to_local(op.orient, X - v3(op.origin));
     bool in = true;
-    if (op.flags & XRT_F_CHECK_SIZE) {
-        if (op.flags & XRT_F_HAS_XSIZE) in = in && (fabs(Xl.x) < op.half_size[0]);
-        if (op.flags & XRT_F_HAS_YSIZE) in = in && (fabs(Xl.y) < op.half_size[1]);
-        if (op.flags & XRT_F_HAS_ZSIZE) in = in && (fabs(Xl.z) < op.half_size[2]);
+    if (flags & XRT_F_CHECK_SIZE) {
+        if (flags & XRT_F_HAS_XSIZE) in = in && (fabs(Xl.x) < op.half_size[0]);
+        if (flags & XRT_F_HAS_YSIZE) in = in && (fabs(Xl.y) < op.half_size[1]);
+        if (flags & XRT_F_HAS_ZSIZE) in = in && (fabs(Xl.z) < op.half_size[2]);
     }
     if constexpr ((FT & FT_APERTURE) != 0) {
-        if (in && (op.flags & XRT_F_CHECK_APERTURE) && op.n_aperture > 0) in = aperture_fold(op, Xl.x, Xl.y);
+        if (in && (flags & XRT_F_CHECK_APERTURE) && op.n_aperture > 0) in = aperture_fold(op, Xl.x, Xl.y);
     }
     r.o = X;
     r.d = d;
@@ -675,26 +711,27 @@ __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3
         frame_to_external<FT>(op, local, r);
         return HIT_OUTSIDE;
     }
-    if constexpr (WANT_NORMAL) { if (analytic) n = analytic_normal<FT>(op, X); }
+    if constexpr (WANT_NORMAL) { if (analytic) n = analytic_normal<FT, KN>(op, X); }
     r.alive = true;
     return HIT_INSIDE;
 }
 
 // interaction half (None / Mirror / Crystal / Mosaic) and the way back to external
 // coordinates.  r.o, r.d in the tracing frame, r.w valid, n = normal at r.o.
-template <uint32_t FT, class DR>
+template <uint32_t FT, class DR, uint32_t KN = 0>
 __device__ __forceinline__ void optic_interact(const XrtOpticDesc &op, int k, const DR &dr, Ray &r, V3 n) {
     bool alive = true;
-    const int ia = op.interact;
+    const int ia = interact_of<KN>(op);
+    const uint32_t flags = flags_of<KN>(op);
     if (ia == XRT_INTERACT_MIRROR) {
         reflect(r, n);
     } else if (ia == XRT_INTERACT_CRYSTAL) {
-        if (op.flags & XRT_F_CHECK_BRAGG) alive = bragg_pass<FT>(op, k, 0, dr, bragg_dtheta(op, r.d, r.w, n));
+        if (flags & XRT_F_CHECK_BRAGG) alive = bragg_pass<FT, DR, KN>(op, k, 0, dr, bragg_dtheta(op, r.d, r.w, n));
         if (alive) reflect(r, n);
     } else if (ia == XRT_INTERACT_MOSAIC) {
         if constexpr ((FT & FT_MOSAIC) != 0) {
             // optional prefilter on the nominal normal (_InteractMosaicCrystal.py:67-75)
-            if (op.flags & XRT_F_MOSAIC_CUTOFF) alive = fabs(bragg_dtheta(op, r.d, r.w, n)) < op.mosaic_angle_cut;
+            if (flags & XRT_F_MOSAIC_CUTOFF) alive = fabs(bragg_dtheta(op, r.d, r.w, n)) < op.mosaic_angle_cut;
             if (alive) {
                 // layers of crystallites: the first one that satisfies Bragg reflects (:83-104)
                 bool done = false;
@@ -703,7 +740,7 @@ __device__ __forceinline__ void optic_interact(const XrtOpticDesc &op, int k, co
                     dr.mosaic_xy(k, layer, op.mosaic_sin_sigma, x, y);
                     V3 nm = mosaic_normal(n, x, y);
                     bool pass = true;
-                    if (op.flags & XRT_F_CHECK_BRAGG) pass = bragg_pass<FT>(op, k, layer, dr, bragg_dtheta(op, r.d, r.w, nm));
+                    if (flags & XRT_F_CHECK_BRAGG) pass = bragg_pass<FT, DR, KN>(op, k, layer, dr, bragg_dtheta(op, r.d, r.w, nm));
                     if (pass) { reflect(r, nm); done = true; }
                 }
                 alive = done;

@@ -273,6 +273,7 @@ def fill_optic(op, param, keep, image_offset):
                 op.rocking_fwhm = float(param['rocking_fwhm'])
                 sigma = param['rocking_fwhm'] / (2 * np.sqrt(2 * np.log(2)))
                 op.rock_two_sigma2 = float(2 * sigma**2)
+                op.rock_inv_two_sigma2 = 1.0 / op.rock_two_sigma2 if op.rock_two_sigma2 != 0.0 else float('inf')
             elif 'file' in rtype:
                 op.rocking_type = L.ROCK['table']
                 tab = rocking.load_table(param['rocking_file'], param['rocking_filetype'])
