@@ -143,7 +143,7 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
         r.alive = true;
     }
     __syncwarp();
-    dr.init(seed, stream_id, id);
+    dr.init(seed, stream_id, id, split);
     const int nopt = sc.n_optics;
     for (int k = split + 1; k < nopt; ++k) {
         const XrtOpticDesc &op = sc.optics[k];
@@ -161,7 +161,7 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
 template <uint32_t FT, uint32_t KN>
 __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
                                         const WarpCtx &c, int split, bool lazy, uint64_t seed, uint64_t stream_id,
-                                        const double *q1, int first, int cnt, double *q2, int &n2) {
+                                        const double *q1, int first, int cnt, double *q2, int &n2, unsigned &n_split) {
     constexpr int P = kQ1Cap;
     const bool active = (int)c.lane < cnt;
     Ray r;
@@ -179,7 +179,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     }
     __syncwarp();
     PhiloxDraws dr;
-    dr.init(seed, stream_id, id);
+    dr.init(seed, stream_id, id, split);
     if (active) {
         if (lazy) {
             SrcLocal L;
@@ -192,14 +192,15 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
         optic_interact<FT, PhiloxDraws, KN>(ops, split, dr, r, n);
         if (r.alive && (flags_of<KN>(ops) & XRT_F_IMAGE) && out.images) add_pixel(out, ops, r, c.lt_mask);
     }
-    count_alive(c, split + 1, r.alive);
+    const unsigned m = __ballot_sync(kFull, r.alive);
+    n_split += __popc(m);                  // survivors of the split optic: per-warp register counter
     emit_lost(out, c, dr, active && !r.alive, id);
 
     if (split + 1 >= sc.n_optics) {        // the split optic is the last one: survivors are found
         emit_found(out, c, r.alive, id);
         return;
     }
-    const unsigned m = __ballot_sync(kFull, r.alive);     // the caller keeps n2 <= kQ2Cap - 32
+    // the caller keeps n2 <= kQ2Cap - 32
     if (r.alive) {
         double *p = q2 + n2 + __popc(m & c.lt_mask);
         p[0] = __longlong_as_double((long long)id);
@@ -234,6 +235,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
     const XrtOpticDesc &ops = sc.optics[split];
     const bool lazy = (FT == 0) ? true : (lazy_rt != 0);
     int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
+    unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
 
     const uint64_t n_warps = (uint64_t)gridDim.x * (kBlock / 32);
     const uint64_t warp_global = (uint64_t)blockIdx.x * (kBlock / 32) + warp;
@@ -252,7 +254,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         if (n1 >= 32 || (!more && n1 > 0)) {
             const int cnt = n1 < 32 ? n1 : 32;
             n1 -= cnt;
-            stage_b<FT, KN>(sc, ops, out, c, split, lazy, seed, stream_id, q1, n1, cnt, q2, n2);
+            stage_b<FT, KN>(sc, ops, out, c, split, lazy, seed, stream_id, q1, n1, cnt, q2, n2, n_split);
             continue;
         }
         if (!more) break;
@@ -263,7 +265,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         const bool valid = i < ray_count;
         const uint64_t id = ray_begin + i;
         PhiloxDraws dr;
-        dr.init(seed, stream_id, id);
+        dr.init(seed, stream_id, id, split);
         Ray r;
         r.alive = false;
         r.w = 0.0;
@@ -273,7 +275,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
             generate_geometry<FT, PhiloxDraws, KN>(sc.source, L, dr, r);
             if (!lazy) r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
         }
-        count_alive(c, 0, r.alive);
+        n_src += __popc(__ballot_sync(kFull, r.alive));
         for (int k = 0; k < split; ++k) {
             const XrtOpticDesc &op = sc.optics[k];
             if (r.alive) {
@@ -300,6 +302,10 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         __syncwarp();
     }
 
+    if (c.lane == 0) {
+        if (n_src) atomicAdd(&s_cnt[0], (unsigned long long)n_src);
+        if (n_split) atomicAdd(&s_cnt[split + 1], (unsigned long long)n_split);
+    }
     __syncthreads();
     if ((int)threadIdx.x <= sc.n_optics && out.counts) {
         unsigned long long cc = s_cnt[threadIdx.x];
@@ -327,7 +333,7 @@ template <uint32_t FT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
          const uint64_t *__restrict__ ids, const uint64_t ray_begin, const uint64_t n,
-         const XrtRaysIn in, const XrtInject inj, const XrtOutputs out, const XrtHistory hist) {
+         const XrtRaysIn in, const XrtInject inj, const XrtOutputs out, const XrtHistory hist, const int split) {
     const int nopt = sc.n_optics;
     const uint64_t stride = (uint64_t)gridDim.x * kBlock;
     for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
@@ -336,7 +342,7 @@ k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uin
         InjectedDraws idr;
         if constexpr (MODE == REC_PHILOX) {
             const uint64_t id = ids ? ids[i] : ray_begin + i;
-            pdr.init(seed, stream_id, id);
+            pdr.init(seed, stream_id, id, split);
             generate_ray<FT>(sc.source, pdr, id, r);
         } else {
             r.o = v3(in.origin + 3 * i);
@@ -381,7 +387,7 @@ k_source(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uin
         Ray r;
         if constexpr (MODE == REC_PHILOX) {
             PhiloxDraws dr;
-            dr.init(seed, stream_id, ray_begin + i);
+            dr.init(seed, stream_id, ray_begin + i, -1);
             generate_ray<FT_FULL>(sc.source, dr, ray_begin + i, r);
         } else {
             SourceInjectedDraws dr;
@@ -739,11 +745,11 @@ static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const u
     int grid = (int)(want < cap ? want : cap);
     cudaStream_t st = (cudaStream_t)stream;
     if (s->features == 0)
-        k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist);
+        k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == FT_MID)
-        k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist);
+        k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else
-        k_record<FT_FULL, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist);
+        k_record<FT_FULL, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     CU(cudaGetLastError());
     return XRT_OK;
 }

@@ -53,10 +53,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
-// 53-bit uniform in [0, 1) from two 32-bit words (same construction as numpy's
-// random_sample: (a >> 5) * 2^26 + (b >> 6), scaled by 2^-53)
+// Uniform in [0, 1) from two 32-bit words: the 52 mantissa bits of a double in [1, 2) are
+// filled with random bits and 1 is subtracted (two integer ops and one DADD; the
+// int -> double conversions of the textbook construction run on the quarter-rate XU pipe).
 __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
-    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+    return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)((a << 20) | (b >> 12))) - 1.0;
+}
+// the same with 40 random bits (a: 32, top 8 of b) and with the low 24 bits of b
+__device__ __forceinline__ double u01_40(uint32_t a, uint32_t b) {
+    return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)((a << 20) | ((b >> 24) << 12))) - 1.0;
+}
+__device__ __forceinline__ double u01_24(uint32_t b) {
+    return __hiloint2double((int)(0x3ff00000u | ((b & 0xffffffu) >> 4)), (int)(b << 28)) - 1.0;
 }
 
 // two independent standard normals from two uniforms (Box-Muller); 1 - u1 is in (0, 1]

@@ -80,12 +80,14 @@ enum : uint32_t { SITE_ORIGIN_XY = 0, SITE_ORIGIN_Z = 1, SITE_CONE = 2, SITE_WAV
 struct PhiloxDraws {
     uint2 key;
     uint32_t ray_lo, ray_hi, stream;
+    int k_shared;     // the crystal whose first rocking-curve uniform shares the wavelength's Philox block
 
-    __device__ __forceinline__ void init(uint64_t seed, uint64_t stream_id, uint64_t ray) {
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t stream_id, uint64_t ray, int shared_optic) {
         key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
         stream = (uint32_t)stream_id;
         ray_lo = (uint32_t)ray;
         ray_hi = (uint32_t)(ray >> 32);
+        k_shared = shared_optic;
     }
     __device__ __forceinline__ uint4 raw(uint32_t site) const {
         return philox4x32_10(make_uint4(ray_lo, ray_hi, site, stream), key);
@@ -112,9 +114,18 @@ struct PhiloxDraws {
     __device__ __forceinline__ void cone(int attempt, double &a, double &b) const {
         pair(attempt == 0 ? SITE_CONE : SITE_CONE_RETRY + (uint32_t)attempt, a, b);
     }
-    __device__ __forceinline__ double wave_u() const { double a, b; pair(SITE_WAVE, a, b); return a; }
+    // One Philox block per ray serves the wavelength and the rocking-curve test of the first
+    // crystal: words x, y -> wavelength (a 53-bit uniform, or a normal from a 40-bit radius
+    // uniform -- tail cut at 7.4 sigma, probability 1.4e-13 -- and a 24-bit angle), words
+    // z, w -> the 53-bit uniform of (optic k_shared, layer 0).  The block is a pure function of
+    // (key, ray, site), so the two users below share one evaluation after inlining.
+    __device__ __forceinline__ double wave_u() const { uint4 r = raw(SITE_WAVE); return u01(r.x, r.y); }
     __device__ __forceinline__ double wave_z() const {
-        double a, b, z0, z1; pair(SITE_WAVE, a, b); box_muller(a, b, z0, z1); return z0;
+        uint4 r = raw(SITE_WAVE);
+        double rad = sqrt(-2.0 * log_pos(1.0 - u01_40(r.x, r.y)));
+        double s, c;
+        sincos_2pi(u01_24(r.y), s, c);
+        return rad * c;
     }
     __device__ __forceinline__ uint64_t lost_key() const {
         uint4 r = raw(SITE_LOSTKEY);
@@ -122,9 +133,10 @@ struct PhiloxDraws {
     }
     // ---- optic sites
     __device__ __forceinline__ double bragg_u(int k, int layer) const {
+        if (k == k_shared && layer == 0) { uint4 r = raw(SITE_WAVE); return u01(r.z, r.w); }
         double a, b; pair(site_optic(k, layer, 0), a, b); return a;
     }
-    // Reflection probability below 2^-53: the ray passes only when the uniform is exactly 0
+    // Reflection probability below 2^-57: the ray passes only when the uniform is exactly 0
     // (p >= u).  With Philox that draw is not made at all (probability 1.1e-16 per ray).
     __device__ __forceinline__ bool bragg_u_is_zero(int, int) const { return false; }
     __device__ __forceinline__ void mosaic_xy(int k, int layer, double s, double &x, double &y) const {
