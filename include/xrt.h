@@ -99,6 +99,7 @@ typedef struct XrtMesh {
     const int32_t *faces;        /* [n_faces][3]                                         */
     const double *face_normals;  /* [n_faces][3]                                         */
     const double *face_geom;     /* [n_faces][9]: p0, p1 - p0, p2 - p0 (Moeller-Trumbore) */
+    const double *face_area;     /* [n_faces]: |(p0 - p1) x (p0 - p2)| (area-sum inside test) */
     int32_t n_coarse_points, n_coarse_faces;   /* 0 when there is no coarse mesh         */
     const double *coarse_points;
     const int32_t *coarse_faces;

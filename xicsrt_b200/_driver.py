@@ -178,15 +178,23 @@ class Tracer:
                                        C.byref(out), self._stream()))
         return ray_begin, ray_count
 
-    def history(self, stream_id, ids):
-        """Replay the given global ray ids (int64 device tensor); returns (rays[E,7,n], mask[E,n]) on device."""
+    def history(self, stream_id, ids, out=None):
+        """
+        Replay the given global ray ids (int64 device tensor); returns (rays[E,7,n], mask[E,n]) on
+        device.  ``out`` = (rays, mask) tensors of a previous call may be passed to reuse their memory.
+        """
         torch = self.torch
         n = int(ids.numel())
-        rays = torch.empty((self.n_elem, 7, max(n, 1)), dtype=torch.float64, device=self.device)
-        mask = torch.empty((self.n_elem, max(n, 1)), dtype=torch.uint8, device=self.device)
+        cap = max(n, 1)
+        if out is not None and out[0].shape[2] >= cap and out[0].shape[0] == self.n_elem:
+            rays, mask = out
+            cap = rays.shape[2]
+        else:
+            rays = torch.empty((self.n_elem, 7, cap), dtype=torch.float64, device=self.device)
+            mask = torch.empty((self.n_elem, cap), dtype=torch.uint8, device=self.device)
         if n:
             h = L.XrtHistory()
-            h.rays, h.mask, h.capacity = rays.data_ptr(), mask.data_ptr(), max(n, 1)
+            h.rays, h.mask, h.capacity = rays.data_ptr(), mask.data_ptr(), cap
             with torch.cuda.device(self.device):
                 L.check(self.lib.xrt_trace_history(self.scene.handle, self.seed, int(stream_id), ids.data_ptr(),
                                                    0, n, C.byref(h), self._stream()))

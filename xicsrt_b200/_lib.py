@@ -42,7 +42,7 @@ class XrtAperture(C.Structure):
 
 class XrtMesh(C.Structure):
     _fields_ = [('n_points', C.c_int32), ('n_faces', C.c_int32),
-                ('points', _pd), ('faces', _pi32), ('face_normals', _pd), ('face_geom', _pd),
+                ('points', _pd), ('faces', _pi32), ('face_normals', _pd), ('face_geom', _pd), ('face_area', _pd),
                 ('n_coarse_points', C.c_int32), ('n_coarse_faces', C.c_int32),
                 ('coarse_points', _pd), ('coarse_faces', _pi32), ('coarse_geom', _pd),
                 ('point_faces', _pi32), ('point_faces_mask', _pu8),

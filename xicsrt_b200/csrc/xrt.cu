@@ -66,6 +66,12 @@ template <uint32_t FT> __host__ __device__ constexpr int warp_queue_doubles() {
     return q1_planes<FT>() * kQ1Cap + kQ2Planes * kQ2Cap;
 }
 
+// shared-memory copy of the step-1 face operands of a mesh split optic (<= kStageFaces faces)
+constexpr int kStageFaces = 256;
+template <uint32_t FT> __host__ __device__ constexpr size_t block_smem_bytes() {
+    return ((size_t)(XRT_BLOCK / 32) * warp_queue_doubles<FT>() + ((FT & FT_MESH) != 0 ? 9 * kStageFaces : 0)) * sizeof(double);
+}
+
 struct WarpCtx {
     unsigned lane, lt_mask;
     unsigned long long *s_cnt;
@@ -212,8 +218,9 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     __syncwarp();
 }
 
+// mesh variants keep many more values live (face loops, Clough-Tocher cubics): 2 blocks / SM
 template <uint32_t FT, int SPLIT, uint32_t KN>
-__global__ void __launch_bounds__(kBlock, XRT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, ((FT & FT_MESH) != 0 && XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS)
 k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
         const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const int split_rt,
         const int lazy_rt) {
@@ -234,6 +241,21 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
     const int split = (SPLIT >= 0) ? SPLIT : split_rt;
     const XrtOpticDesc &ops = sc.optics[split];
     const bool lazy = (FT == 0) ? true : (lazy_rt != 0);
+
+    // mesh split optic: stage the face operands every ray is tested against in shared memory
+    const double *staged = nullptr;
+    if constexpr ((FT & FT_MESH) != 0) {
+        if (ops.shape == XRT_SHAPE_MESH) {
+            const double *geom;
+            const int nf = mesh_stage1_faces(ops, geom);
+            if (nf <= kStageFaces) {
+                double *dst = s_queue + (size_t)(kBlock / 32) * warp_queue_doubles<FT>();
+                for (int i = threadIdx.x; i < 9 * nf; i += kBlock) dst[i] = __ldg(geom + i);
+                staged = dst;
+            }
+        }
+        __syncthreads();
+    }
     int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
     unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
 
@@ -286,7 +308,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         }
         V3 n = v3(0.0, 0.0, 1.0);
         bool cand = false;
-        if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n) == HIT_INSIDE;
+        if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
         emit_lost(out, c, dr, valid && !cand, id);
 
         const unsigned m = __ballot_sync(kFull, cand);
@@ -316,13 +338,14 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
 // ---------------------------------------------------------------------------
 // recording kernel: history of every element, optional counters / images
 
+// streaming stores (evict-first): history planes are written once and read back by the host
 __device__ __forceinline__ void store_history(const XrtHistory &h, int elem, uint64_t slot, const Ray &r) {
     if (h.rays) {
         double *p = h.rays + ((uint64_t)elem * 7) * h.capacity + slot;
         const uint64_t c = h.capacity;
-        p[0] = r.o.x; p[c] = r.o.y; p[2 * c] = r.o.z;
-        p[3 * c] = r.d.x; p[4 * c] = r.d.y; p[5 * c] = r.d.z;
-        p[6 * c] = r.w;
+        __stcs(p, r.o.x); __stcs(p + c, r.o.y); __stcs(p + 2 * c, r.o.z);
+        __stcs(p + 3 * c, r.d.x); __stcs(p + 4 * c, r.d.y); __stcs(p + 5 * c, r.d.z);
+        __stcs(p + 6 * c, r.w);
     }
     if (h.mask) h.mask[(uint64_t)elem * h.capacity + slot] = r.alive ? 1 : 0;
 }
@@ -475,7 +498,7 @@ static int upload(XrtScene *s, const T *host, size_t count, const T **dev) {
 
 static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     XrtMesh m = *host;
-    if (m.n_points <= 0 || m.n_faces <= 0 || !m.points || !m.faces || !m.face_normals || !m.face_geom)
+    if (m.n_points <= 0 || m.n_faces <= 0 || !m.points || !m.faces || !m.face_normals || !m.face_geom || !m.face_area)
         return fail(XRT_EINVAL, "mesh: points / faces missing");
     size_t cells = (size_t)m.grid_nx * (size_t)m.grid_ny;
     int32_t n_items = 0, n_vitems = 0;
@@ -485,6 +508,7 @@ static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     UP(m.faces, 3 * (size_t)m.n_faces);
     UP(m.face_normals, 3 * (size_t)m.n_faces);
     UP(m.face_geom, 9 * (size_t)m.n_faces);
+    UP(m.face_area, (size_t)m.n_faces);
     UP(m.coarse_points, 3 * (size_t)m.n_coarse_points);
     UP(m.coarse_faces, 3 * (size_t)m.n_coarse_faces);
     UP(m.coarse_geom, 9 * (size_t)m.n_coarse_faces);
@@ -521,9 +545,10 @@ static uint32_t scene_features(const XrtSceneDesc &d) {
             (op.interact == XRT_INTERACT_CRYSTAL || op.interact == XRT_INTERACT_MOSAIC))
             ft |= FT_ROCKTAB;
     }
-    // three compiled variants: lean spectrometer, all analytic features, everything
+    // compiled variants: lean spectrometer, all analytic features, lean mesh, everything
     if (ft == 0) return 0;
     if ((ft & ~FT_MID) == 0) return FT_MID;
+    if ((ft & ~FT_MESHLEAN) == 0) return FT_MESHLEAN;
     return FT_FULL;
 }
 
@@ -669,19 +694,22 @@ static TraceKernel trace_kernel_ft(int split) {
 }
 
 static TraceKernel trace_kernel(const XrtScene *s, size_t *smem) {
-    const size_t warps = kBlock / 32;
     if (s->features == 0) {
-        *smem = warps * warp_queue_doubles<0>() * sizeof(double);
+        *smem = block_smem_bytes<0>();
         // pre-instantiated structure: point source with a Gaussian line on a concave spherical
         // Bragg crystal as first optic -- the spherical-crystal spectrometer
         if (s->split == 0 && (s->known & KN_SPECTROMETER) == KN_SPECTROMETER) return k_trace<0, 0, KN_SPECTROMETER>;
         return trace_kernel_ft<0>(s->split);
     }
     if (s->features == FT_MID) {
-        *smem = warps * warp_queue_doubles<FT_MID>() * sizeof(double);
+        *smem = block_smem_bytes<FT_MID>();
         return trace_kernel_ft<FT_MID>(s->split);
     }
-    *smem = warps * warp_queue_doubles<FT_FULL>() * sizeof(double);
+    if (s->features == FT_MESHLEAN) {
+        *smem = block_smem_bytes<FT_MESHLEAN>();
+        return trace_kernel_ft<FT_MESHLEAN>(s->split);
+    }
+    *smem = block_smem_bytes<FT_FULL>();
     return trace_kernel_ft<FT_FULL>(s->split);
 }
 
@@ -748,6 +776,8 @@ static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const u
         k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == FT_MID)
         k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+    else if (s->features == FT_MESHLEAN)
+        k_record<FT_MESHLEAN, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else
         k_record<FT_FULL, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     CU(cudaGetLastError());

@@ -20,24 +20,36 @@ namespace xrt {
 
 __device__ __forceinline__ V3 ld3(const double *p) { return v3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 
-// step 1.  geom: [n_faces][9] = p0, edge1, edge2.  Returns the index of the last face hit or -1.
+// step 1.  geom: [n_faces][9] = p0, edge1, edge2 (global memory, or the block's shared-memory
+// copy when STAGED).  Returns the index of the last face hit or -1.
+//
+// The reference divides first (f = 1/a, u = f (s.h), v = f (D.q)) and then rejects u < 0, u > 1,
+// v < 0, u + v > 1.  Almost every face is rejected by u, so the sign of u (= sign(a) sign(s.h),
+// exact) and |s.h| > |a| are tested before the division is paid; the two forms can differ only
+// for a hit within rounding of a triangle edge.
+template <bool STAGED>
 __device__ __forceinline__ int mesh_all_faces(const double *__restrict__ geom, int n_faces, V3 o, V3 d, V3 &X) {
     const double eps = 1e-15;
     int hit = -1;
     for (int f = 0; f < n_faces; ++f) {
         const double *g = geom + 9 * f;
-        const V3 p0 = ld3(g), e1 = ld3(g + 3), e2 = ld3(g + 6);
+        V3 p0, e1, e2;
+        if constexpr (STAGED) { p0 = v3(g); e1 = v3(g + 3); e2 = v3(g + 6); }
+        else { p0 = ld3(g); e1 = ld3(g + 3); e2 = ld3(g + 6); }
         const V3 h = cross(d, e2);
-        double a = dot(e1, h);
+        const double a = dot(e1, h);
         if (a > -eps && a < eps) continue;
-        a = 1.0 / a;
         const V3 s = o - p0;
-        const double u = a * dot(s, h);
+        const double sh = dot(s, h);
+        if ((sh < 0.0) != (a < 0.0) && sh != 0.0) continue;        // u < 0
+        if (fabs(sh) > fabs(a)) continue;                           // u > 1
+        const double inv = 1.0 / a;
+        const double u = inv * sh;
         if (u < 0.0 || u > 1.0) continue;
         const V3 q = cross(s, e1);
-        const double v = a * dot(d, q);
+        const double v = inv * dot(d, q);
         if (v < 0.0 || u + v > 1.0) continue;
-        const double t = a * dot(e2, q);
+        const double t = inv * dot(e2, q);
         hit = f;
         X = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
     }
@@ -84,20 +96,22 @@ __device__ __forceinline__ int mesh_nearest_vertex(const XrtMesh &m, V3 q) {
     return best;
 }
 
-// step 3: the faces around vertex `vert`
+// step 3: the faces around vertex `vert`.  face_geom gives p0 and the two edges, face_area the
+// constant |(p0 - p1) x (p0 - p2)| of the reference's area-sum test.
 __device__ __forceinline__ int mesh_candidate_faces(const XrtMesh &m, int vert, V3 o, V3 d, V3 &X) {
     for (int k = 0; k < 8; ++k) {
         if (!__ldg(m.point_faces_mask + (size_t)k * m.n_points + vert)) continue;
         const int f = __ldg(m.point_faces + (size_t)k * m.n_points + vert);
-        const int i0 = __ldg(m.faces + 3 * f), i1 = __ldg(m.faces + 3 * f + 1), i2 = __ldg(m.faces + 3 * f + 2);
-        const V3 p0 = ld3(m.points + 3 * i0), p1 = ld3(m.points + 3 * i1), p2 = ld3(m.points + 3 * i2);
+        const double *g = m.face_geom + 9 * (size_t)f;
+        const V3 p0 = ld3(g), e1 = ld3(g + 3), e2 = ld3(g + 6);
         const V3 n = ld3(m.face_normals + 3 * f);
         const double dist = dot(p0 - o, n) / dot(d, n);
+        if (!(dist >= 0.0)) continue;
         const V3 P = v3(d.x * dist + o.x, d.y * dist + o.y, d.z * dist + o.z);
-        const V3 a = P - p0, b = P - p1, c = P - p2;
-        const V3 bc = cross(b, c), ca = cross(c, a), ab = cross(a, b), area = cross(p0 - p1, p0 - p2);
-        const double diff = sqrt(dot(bc, bc)) + sqrt(dot(ca, ca)) + sqrt(dot(ab, ab)) - sqrt(dot(area, area));
-        if (diff < 1e-10 && dist >= 0.0) {
+        const V3 a = P - p0, b = a - e1, c = a - e2;
+        const V3 bc = cross(b, c), ca = cross(c, a), ab = cross(a, b);
+        const double diff = sqrt(dot(bc, bc)) + sqrt(dot(ca, ca)) + sqrt(dot(ab, ab)) - __ldg(m.face_area + f);
+        if (diff < 1e-10) {
             X = P;
             return f;
         }
@@ -143,17 +157,29 @@ __device__ __forceinline__ double ct_cubic(const double *__restrict__ c, double 
     return w;
 }
 
-// ShapeMesh.intersect (:135-170).  o, d in the optic's tracing frame.
-__device__ __forceinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n) {
+// number of faces step 1 walks (the coarse mesh when refining) and their operands
+__device__ __forceinline__ int mesh_stage1_faces(const XrtOpticDesc &op, const double *&geom) {
+    const XrtMesh &m = *op.mesh;
+    if (op.flags & XRT_F_MESH_REFINE) { geom = m.coarse_geom; return m.n_coarse_faces; }
+    geom = m.face_geom;
+    return m.n_faces;
+}
+
+// ShapeMesh.intersect (:135-170).  o, d in the optic's tracing frame.  `staged` (optional) is a
+// shared-memory copy of the step-1 face operands.
+__device__ __forceinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
+                                               const double *staged = nullptr) {
     const XrtMesh &m = *op.mesh;
     X = nan3();
     n = nan3();
+    const double *geom;
+    const int n1 = mesh_stage1_faces(op, geom);
     int face;
     if (!(op.flags & XRT_F_MESH_REFINE)) {
-        face = mesh_all_faces(m.face_geom, m.n_faces, o, d, X);
+        face = staged ? mesh_all_faces<true>(staged, n1, o, d, X) : mesh_all_faces<false>(geom, n1, o, d, X);
     } else {
         V3 Xc = nan3();
-        face = mesh_all_faces(m.coarse_geom, m.n_coarse_faces, o, d, Xc);
+        face = staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
         if (face >= 0) {
             const int vert = mesh_nearest_vertex(m, Xc);
             face = (vert >= 0) ? mesh_candidate_faces(m, vert, o, d, X) : -1;

@@ -26,6 +26,7 @@ enum : uint32_t {
     FT_SRC_EXT = 1u << 7,   // anything beyond box + isotropic cone + const/uniform/normal line
     FT_MID = FT_LOCAL | FT_CYL | FT_TORUS | FT_APERTURE | FT_MOSAIC | FT_ROCKTAB | FT_SRC_EXT,
     FT_FULL = FT_MID | FT_MESH,
+    FT_MESHLEAN = FT_MESH | FT_LOCAL,   // mesh optics (traced in local coordinates) + plane / sphere, box source
 };
 
 // Known-structure mask KN: facts about the source and the split optic that a pre-instantiated
@@ -664,7 +665,7 @@ __device__ __forceinline__ void frame_to_external(const XrtOpticDesc &op, bool l
 }
 
 template <uint32_t FT, bool WANT_NORMAL, uint32_t KN = 0>
-__device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3 &n) {
+__device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3 &n, const double *staged_mesh = nullptr) {
     V3 o = r.o, d = r.d;
     const uint32_t flags = flags_of<KN>(op);
     const bool local = optic_is_local<FT>(op);
@@ -682,7 +683,7 @@ __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3
     if constexpr ((FT & FT_MESH) != 0) {
         if (shape_of<KN>(op) == XRT_SHAPE_MESH) {
             analytic = false;
-            ok = mesh_intersect(op, o, d, X, n);
+            ok = mesh_intersect(op, o, d, X, n, staged_mesh);
         }
     }
     if (analytic) {

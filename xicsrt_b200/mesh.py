@@ -375,11 +375,18 @@ def face_geometry(points, faces):
     return np.ascontiguousarray(np.concatenate([p0, p1 - p0, p2 - p0], axis=1), dtype=np.float64)
 
 
+def face_area(points, faces):
+    """|(p0 - p1) x (p0 - p2)| per face: the constant of the area-sum inside test (_ShapeMesh.py:405-409)."""
+    p0, p1, p2 = points[faces[:, 0]], points[faces[:, 1]], points[faces[:, 2]]
+    return np.ascontiguousarray(np.linalg.norm(np.cross(p0 - p1, p0 - p2), axis=1), dtype=np.float64)
+
+
 def device_tables(param):
     """Everything fill_mesh uploads, as numpy arrays (also used by the CPU tests of the tables)."""
     m = param['mesh']
     t = {'points': np.ascontiguousarray(m['points'], dtype=np.float64),
          'face_geom': face_geometry(np.asarray(m['points'], dtype=np.float64), np.asarray(m['faces'])),
+         'face_area': face_area(np.asarray(m['points'], dtype=np.float64), np.asarray(m['faces'])),
          'faces': np.ascontiguousarray(m['faces'], dtype=np.int32),
          'face_normals': np.ascontiguousarray(m['faces_normal'], dtype=np.float64),
          'point_faces': np.ascontiguousarray(m['p_faces_idx'], dtype=np.int32),
@@ -418,6 +425,7 @@ def fill_mesh(param, keep):
     m.faces = keep.arr(t['faces'], np.int32, C.c_int32)
     m.face_normals = keep.f64(t['face_normals'])
     m.face_geom = keep.f64(t['face_geom'])
+    m.face_area = keep.f64(t['face_area'])
     m.point_faces = keep.arr(t['point_faces'], np.int32, C.c_int32)
     m.point_faces_mask = keep.arr(t['point_faces_mask'], np.uint8, C.c_uint8)
     if 'coarse_points' in t:
