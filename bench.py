@@ -111,7 +111,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100',
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '20',
                  '-i', str(self.gpu_index)], stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -368,9 +368,9 @@ def run_gpu_arm(args):
         cores = os.cpu_count() or 1
         procs = min(cores, 64)
         cpu_reference_step(200000, procs, procs, seed=7)          # warm the pool / imports
-        n, dt = cpu_reference_step(1_000_000, 2 * procs, procs, seed=8)
+        n, dt = cpu_reference_step(1_000_000, 8 * procs, procs, seed=8)
         cpu = {'value': n / dt, 'unit': UNIT, 'cores': procs, 'kind': 'port',
-               'sample': f'{2 * procs} runs x 1e6 rays over {procs} processes, {dt:.1f} s '
+               'sample': f'{8 * procs} runs x 1e6 rays over {procs} processes, {dt:.1f} s '
                          f'(oracle port of the NumPy path; reference scheme xicsrt_multiprocessing)'}
 
     if rank == 0:
@@ -404,7 +404,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--rays', type=float, default=1e9, help='rays per GPU per step')
     ap.add_argument('--scaling', choices=['weak', 'strong'], default='weak')
