@@ -213,3 +213,82 @@ def test_fused_kernel_equals_replay_kernel(torch, name):
         ref = ooptics.bin_image(param, np.ascontiguousarray(rays[e, 0:3].T), mask[e])
         assert np.array_equal(image[elem], ref), f'{name}/{elem}: image'
     tracer.close()
+
+
+def _long_train(n_apertures):
+    """n pass-through apertures in front of the crystal: the split optic moves down the train."""
+    cfg = scenes.get('sphere')
+    optics = {}
+    for i in range(n_apertures):
+        optics[f'ap{i}'] = {'class_name': 'XicsrtOpticAperture', 'origin': [0.0, 0.0, 0.1 + 0.1 * i],
+                            'zaxis': [0.0, 0.0, -1.0], 'xsize': 0.5, 'ysize': 0.5,
+                            'aperture': {'shape': 'circle', 'size': [0.2 - 0.01 * i]}}
+    optics.update(cfg['optics'])
+    cfg['optics'] = optics
+    return cfg
+
+
+@pytest.mark.parametrize('n_apertures', [2, 3, 5])
+def test_split_optic_deep_in_the_train(torch, n_apertures):
+    """Crystal as 3rd, 4th, 6th optic: compile-time split index 2 and the run-time fallback."""
+    from xicsrt_b200 import _driver, config as xconfig
+    cfg = _long_train(n_apertures)
+    cfg['sources']['source']['intensity'] = 200000
+    tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), seed=3)
+    n = tracer.n_rays
+    found, lost = tracer.select_ids(0, 100)
+    meta, image = tracer.counts_and_images(True)
+    rays, mask = tracer.history(0, torch.arange(n, dtype=torch.int64, device=tracer.device))
+    mask = mask.cpu().numpy().astype(bool)
+    for e, elem in enumerate(tracer.layout.element_names):
+        assert int(mask[e].sum()) == meta[elem], elem
+    assert np.array_equal(np.flatnonzero(mask[-1]), found.cpu().numpy())
+    assert meta['detector'] > 1000
+    tracer.close()
+    # and the oracle agrees statistically
+    cfg['general']['keep_history'] = False
+    ref = oracle.raytrace(copy.deepcopy(cfg))
+    for elem in ref['total']['meta']:
+        k1, k2 = meta[elem], ref['total']['meta'][elem]['num_out']
+        if k1 == n and k2 == n:
+            continue
+        assert abs(binomial_z(k1, n, k2, n)) < 4.5, elem
+
+
+@pytest.mark.parametrize('n', [1, 31, 33, 1000, 4097])
+def test_ragged_ray_counts_and_large_id_offsets(torch, n):
+    """Partial warps, a single ray, and id ranges beyond 2^32 give the same rays as the replay kernel."""
+    from xicsrt_b200 import _driver, config as xconfig
+    cfg = scenes.get('sphere')
+    cfg['sources']['source']['intensity'] = 10
+    tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), seed=21)
+    begin = (1 << 33) + 12345
+    tracer.trace(7, ray_begin=begin, ray_count=n)
+    meta, image = tracer.counts_and_images(True)
+    ids = torch.arange(begin, begin + n, dtype=torch.int64, device=tracer.device)
+    rays, mask = tracer.history(7, ids)
+    mask = mask.cpu().numpy().astype(bool)
+    assert meta['source'] == n
+    for e, elem in enumerate(tracer.layout.element_names):
+        assert int(mask[e].sum()) == meta[elem]
+    # a different id window gives different rays
+    other, _ = tracer.history(7, ids - 5)
+    assert not torch.equal(other, rays)
+    tracer.close()
+
+
+def test_single_optic_scene_and_no_image_optic(torch):
+    """One optic only (the split optic is also the last); an optic without a pixel grid returns image None."""
+    import xicsrt_b200
+    cfg = scenes.get('sphere')
+    cfg['optics'] = {'crystal': cfg['optics']['crystal']}
+    cfg['sources']['source']['intensity'] = 100000
+    res = xicsrt_b200.raytrace(cfg)
+    n_found = res['total']['meta']['crystal']['num_out']
+    assert 500 < n_found < 3000 and len(res['found']['history']['crystal']['mask']) == n_found
+    cfg = scenes.get('sphere')
+    del cfg['optics']['crystal']['xsize']
+    cfg['optics']['crystal']['check_size'] = False
+    cfg['sources']['source']['intensity'] = 50000
+    res = xicsrt_b200.raytrace(cfg)
+    assert res['total']['image']['crystal'] is None and res['total']['image']['detector'] is not None
