@@ -100,12 +100,15 @@ typedef struct XrtMesh {
     const double *face_normals;  /* [n_faces][3]                                         */
     const double *face_geom;     /* [n_faces][9]: p0, p1 - p0, p2 - p0 (Moeller-Trumbore) */
     const double *face_area;     /* [n_faces]: |(p0 - p1) x (p0 - p2)| (area-sum inside test) */
+    const double *face_rec;      /* [n_faces][16]: p0, e1, e2, unit normal, area, pad -- one
+                                    128-byte record per face for the candidate-face test  */
     int32_t n_coarse_points, n_coarse_faces;   /* 0 when there is no coarse mesh         */
     const double *coarse_points;
     const int32_t *coarse_faces;
     const double *coarse_geom;   /* [n_coarse_faces][9]                                  */
     const int32_t *point_faces;  /* [8][n_points] faces around each fine point           */
     const uint8_t *point_faces_mask; /* [8][n_points]                                    */
+    const int32_t *vertex_faces; /* [n_points][8] the same, vertex-major, -1 = no face   */
     /* Clough-Tocher interpolation of z and the normal over the xy Delaunay triangulation */
     int32_t n_tri;               /* 0 when mesh_interpolate is off                       */
     int32_t pad0;
@@ -121,6 +124,7 @@ typedef struct XrtMesh {
     const int32_t *vgrid_start;  /* [grid_nx*grid_ny + 1] vertices in each cell (nearest-
                                     vertex query, replaces the reference's kd-tree)      */
     const int32_t *vgrid_items;
+    const double *vgrid_xyz;     /* [items][4]: x, y, z of vgrid_items[k] (cell-ordered), pad */
 } XrtMesh;
 
 typedef struct XrtOpticDesc {

@@ -42,17 +42,17 @@ class XrtAperture(C.Structure):
 
 class XrtMesh(C.Structure):
     _fields_ = [('n_points', C.c_int32), ('n_faces', C.c_int32),
-                ('points', _pd), ('faces', _pi32), ('face_normals', _pd), ('face_geom', _pd), ('face_area', _pd),
+                ('points', _pd), ('faces', _pi32), ('face_normals', _pd), ('face_geom', _pd), ('face_area', _pd), ('face_rec', _pd),
                 ('n_coarse_points', C.c_int32), ('n_coarse_faces', C.c_int32),
                 ('coarse_points', _pd), ('coarse_faces', _pi32), ('coarse_geom', _pd),
-                ('point_faces', _pi32), ('point_faces_mask', _pu8),
+                ('point_faces', _pi32), ('point_faces_mask', _pu8), ('vertex_faces', _pi32),
                 ('n_tri', C.c_int32), ('pad0', C.c_int32),
                 ('ct_coef', _pd), ('tri_transform', _pd),
                 ('grid_nx', C.c_int32), ('grid_ny', C.c_int32),
                 ('grid_x0', C.c_double), ('grid_y0', C.c_double),
                 ('grid_inv_dx', C.c_double), ('grid_inv_dy', C.c_double),
                 ('grid_start', _pi32), ('grid_items', _pi32),
-                ('vgrid_start', _pi32), ('vgrid_items', _pi32)]
+                ('vgrid_start', _pi32), ('vgrid_items', _pi32), ('vgrid_xyz', _pd)]
 
 
 class XrtOpticDesc(C.Structure):

@@ -498,7 +498,7 @@ static int upload(XrtScene *s, const T *host, size_t count, const T **dev) {
 
 static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     XrtMesh m = *host;
-    if (m.n_points <= 0 || m.n_faces <= 0 || !m.points || !m.faces || !m.face_normals || !m.face_geom || !m.face_area)
+    if (m.n_points <= 0 || m.n_faces <= 0 || !m.points || !m.faces || !m.face_normals || !m.face_geom || !m.face_area || !m.face_rec || !m.vertex_faces)
         return fail(XRT_EINVAL, "mesh: points / faces missing");
     size_t cells = (size_t)m.grid_nx * (size_t)m.grid_ny;
     int32_t n_items = 0, n_vitems = 0;
@@ -509,6 +509,8 @@ static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     UP(m.face_normals, 3 * (size_t)m.n_faces);
     UP(m.face_geom, 9 * (size_t)m.n_faces);
     UP(m.face_area, (size_t)m.n_faces);
+    UP(m.face_rec, 16 * (size_t)m.n_faces);
+    UP(m.vertex_faces, 8 * (size_t)m.n_points);
     UP(m.coarse_points, 3 * (size_t)m.n_coarse_points);
     UP(m.coarse_faces, 3 * (size_t)m.n_coarse_faces);
     UP(m.coarse_geom, 9 * (size_t)m.n_coarse_faces);
@@ -520,6 +522,7 @@ static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     UP(m.grid_items, n_items);
     UP(m.vgrid_start, (cells && m.vgrid_start) ? cells + 1 : 0);
     UP(m.vgrid_items, n_vitems);
+    UP(m.vgrid_xyz, (cells && m.vgrid_start && m.vgrid_xyz) ? 4 * (size_t)n_vitems : 0);
     const XrtMesh *d = nullptr;
     int rc = upload(s, &m, 1, &d);
     if (rc != XRT_OK) return rc;
@@ -611,7 +614,7 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         if (m.shape == XRT_SHAPE_MESH) {
             if (!m.mesh) return fail(XRT_EINVAL, "optic %d: mesh tables missing", k);
             if ((m.flags & XRT_F_MESH_REFINE) && (m.mesh->n_coarse_faces <= 0 || !m.mesh->coarse_geom ||
-                                                  !m.mesh->vgrid_start || !m.mesh->point_faces))
+                                                  !m.mesh->vgrid_start || !m.mesh->vgrid_xyz))
                 return fail(XRT_EINVAL, "optic %d: mesh refinement needs the coarse mesh and the vertex grid", k);
             if ((m.flags & XRT_F_MESH_INTERP) && (m.mesh->n_tri <= 0 || !m.mesh->ct_coef || !m.mesh->tri_transform ||
                                                   !m.mesh->grid_start))

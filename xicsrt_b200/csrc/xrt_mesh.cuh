@@ -27,31 +27,52 @@ __device__ __forceinline__ V3 ld3(const double *p) { return v3(__ldg(p), __ldg(p
 // v < 0, u + v > 1.  Almost every face is rejected by u, so the sign of u (= sign(a) sign(s.h),
 // exact) and |s.h| > |a| are tested before the division is paid; the two forms can differ only
 // for a hit within rounding of a triangle edge.
+//
+// Two passes per group of 32 faces: the cheap rejection marks the few faces a lane can hit in a
+// bit mask, then each lane completes only its own candidates (in ascending face order, so the
+// last face still wins).  A warp therefore pays the full test a couple of times per ray instead
+// of once per face, although every face is hit by some lane of the warp.
+template <bool STAGED>
+__device__ __forceinline__ void mesh_face_operands(const double *__restrict__ g, V3 &p0, V3 &e1, V3 &e2) {
+    if constexpr (STAGED) { p0 = v3(g); e1 = v3(g + 3); e2 = v3(g + 6); }
+    else { p0 = ld3(g); e1 = ld3(g + 3); e2 = ld3(g + 6); }
+}
+
 template <bool STAGED>
 __device__ __forceinline__ int mesh_all_faces(const double *__restrict__ geom, int n_faces, V3 o, V3 d, V3 &X) {
     const double eps = 1e-15;
     int hit = -1;
-    for (int f = 0; f < n_faces; ++f) {
-        const double *g = geom + 9 * f;
-        V3 p0, e1, e2;
-        if constexpr (STAGED) { p0 = v3(g); e1 = v3(g + 3); e2 = v3(g + 6); }
-        else { p0 = ld3(g); e1 = ld3(g + 3); e2 = ld3(g + 6); }
-        const V3 h = cross(d, e2);
-        const double a = dot(e1, h);
-        if (a > -eps && a < eps) continue;
-        const V3 s = o - p0;
-        const double sh = dot(s, h);
-        if ((sh < 0.0) != (a < 0.0) && sh != 0.0) continue;        // u < 0
-        if (fabs(sh) > fabs(a)) continue;                           // u > 1
-        const double inv = 1.0 / a;
-        const double u = inv * sh;
-        if (u < 0.0 || u > 1.0) continue;
-        const V3 q = cross(s, e1);
-        const double v = inv * dot(d, q);
-        if (v < 0.0 || u + v > 1.0) continue;
-        const double t = inv * dot(e2, q);
-        hit = f;
-        X = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    for (int base = 0; base < n_faces; base += 32) {
+        const int cnt = min(32, n_faces - base);
+        unsigned cand = 0u;
+        for (int j = 0; j < cnt; ++j) {
+            V3 p0, e1, e2;
+            mesh_face_operands<STAGED>(geom + 9 * (base + j), p0, e1, e2);
+            const V3 h = cross(d, e2);
+            const double a = dot(e1, h);
+            const double sh = dot(o - p0, h);
+            const bool degenerate = (a > -eps && a < eps);
+            const bool u_neg = ((sh < 0.0) != (a < 0.0)) && sh != 0.0;       // u < 0
+            const bool u_big = fabs(sh) > fabs(a);                           // u > 1
+            if (!(degenerate || u_neg || u_big)) cand |= 1u << j;
+        }
+        while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            V3 p0, e1, e2;
+            mesh_face_operands<STAGED>(geom + 9 * (base + j), p0, e1, e2);
+            const V3 h = cross(d, e2);
+            const double inv = 1.0 / dot(e1, h);
+            const V3 s = o - p0;
+            const double u = inv * dot(s, h);
+            if (u < 0.0 || u > 1.0) continue;
+            const V3 q = cross(s, e1);
+            const double v = inv * dot(d, q);
+            if (v < 0.0 || u + v > 1.0) continue;
+            const double t = inv * dot(e2, q);
+            hit = base + j;
+            X = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+        }
     }
     return hit;
 }
@@ -84,33 +105,43 @@ __device__ __forceinline__ int mesh_nearest_vertex(const XrtMesh &m, V3 q) {
                 if (xx < 0 || xx >= nx) continue;
                 const int c = yy * nx + xx;
                 const int b = __ldg(m.vgrid_start + c), e = __ldg(m.vgrid_start + c + 1);
-                for (int k = b; k < e; ++k) {
-                    const int v = __ldg(m.vgrid_items + k);
-                    const V3 p = ld3(m.points + 3 * v) - q;
+                for (int k = b; k < e; ++k) {       // coordinates stored cell-ordered: no index hop
+                    const double2 xy = __ldg((const double2 *)(m.vgrid_xyz + 4 * (size_t)k));
+                    const double z = __ldg(m.vgrid_xyz + 4 * (size_t)k + 2);
+                    const V3 p = v3(xy.x, xy.y, z) - q;
                     const double d2 = dot(p, p);
-                    if (d2 < best_d2) { best_d2 = d2; best = v; }
+                    if (d2 < best_d2) { best_d2 = d2; best = k; }
                 }
             }
         }
     }
-    return best;
+    return best >= 0 ? __ldg(m.vgrid_items + best) : -1;
 }
 
 // step 3: the faces around vertex `vert`.  face_geom gives p0 and the two edges, face_area the
 // constant |(p0 - p1) x (p0 - p2)| of the reference's area-sum test.
 __device__ __forceinline__ int mesh_candidate_faces(const XrtMesh &m, int vert, V3 o, V3 d, V3 &X) {
+    // the <= 8 face ids of the vertex in two 16-byte loads, then one 128-byte record per face
+    const int4 fa = __ldg((const int4 *)(m.vertex_faces + 8 * (size_t)vert));
+    const int4 fb = __ldg((const int4 *)(m.vertex_faces + 8 * (size_t)vert + 4));
+    const int ids[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
     for (int k = 0; k < 8; ++k) {
-        if (!__ldg(m.point_faces_mask + (size_t)k * m.n_points + vert)) continue;
-        const int f = __ldg(m.point_faces + (size_t)k * m.n_points + vert);
-        const double *g = m.face_geom + 9 * (size_t)f;
-        const V3 p0 = ld3(g), e1 = ld3(g + 3), e2 = ld3(g + 6);
-        const V3 n = ld3(m.face_normals + 3 * f);
+        const int f = ids[k];
+        if (f < 0) continue;
+        const double2 *g = (const double2 *)(m.face_rec + 16 * (size_t)f);
+        const double2 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3), g4 = __ldg(g + 4),
+                      g5 = __ldg(g + 5), g6 = __ldg(g + 6);
+        const V3 p0 = v3(g0.x, g0.y, g1.x), e1 = v3(g1.y, g2.x, g2.y), e2 = v3(g3.x, g3.y, g4.x);
+        const V3 n = v3(g4.y, g5.x, g5.y);
+        const double area = g6.x;
         const double dist = dot(p0 - o, n) / dot(d, n);
         if (!(dist >= 0.0)) continue;
         const V3 P = v3(d.x * dist + o.x, d.y * dist + o.y, d.z * dist + o.z);
         const V3 a = P - p0, b = a - e1, c = a - e2;
-        const V3 bc = cross(b, c), ca = cross(c, a), ab = cross(a, b);
-        const double diff = sqrt(dot(bc, bc)) + sqrt(dot(ca, ca)) + sqrt(dot(ab, ab)) - __ldg(m.face_area + f);
+        // P lies in the face plane, so b x c, c x a and a x b are parallel to the unit normal n:
+        // their lengths are |(.) . n| -- the reference's three norms without a square root
+        const double diff = fabs(dot(cross(b, c), n)) + fabs(dot(cross(c, a), n)) + fabs(dot(cross(a, b), n)) - area;
         if (diff < 1e-10) {
             X = P;
             return f;
@@ -201,8 +232,7 @@ __device__ __forceinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 
             const double *c = m.ct_coef + (size_t)t * 76;
             X.z = ct_cubic(c, e1, e2, e3, e4);
             V3 nn = v3(ct_cubic(c + 19, e1, e2, e3, e4), ct_cubic(c + 38, e1, e2, e3, e4), ct_cubic(c + 57, e1, e2, e3, e4));
-            const double inv = 1.0 / sqrt(dot(nn, nn));
-            n = nn * inv;
+            n = nn * rsqrt(dot(nn, nn));
         }
     } else {
         n = ld3(m.face_normals + 3 * face);

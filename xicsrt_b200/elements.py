@@ -79,14 +79,46 @@ def _convex_pair(value):
     return bool(v[0]), bool(v[1])
 
 
+_mesh_cache = {}
+
+
+def _cache_key(cfg):
+    """Hashable image of a config dict (arrays by content); None when something is not hashable."""
+    import hashlib
+    items = []
+    for key in sorted(cfg):
+        val = cfg[key]
+        if isinstance(val, np.ndarray):
+            items.append((key, val.shape, str(val.dtype), hashlib.sha1(np.ascontiguousarray(val)).hexdigest()))
+        elif isinstance(val, (list, tuple, dict)):
+            try:
+                items.append((key, repr(np.asarray(val).tolist()) if not isinstance(val, dict) else repr(sorted(val.items()))))
+            except Exception:
+                return None
+        else:
+            items.append((key, repr(val)))
+    return tuple(items)
+
+
 def prepare_optic(config_user, strict=True):
     """
     Returns (config, param) for one optic.  ``param`` additionally carries
     ``_interact`` and ``_shape`` (kinds from the registry).
+
+    Prepared mesh optics (Delaunay triangulations, Clough-Tocher gradients, lookup tables:
+    about a second of setup) are cached by config content, so repeated runs of one scene
+    pay for them once.
     """
     cfg = build_config(config_user, strict=strict)
     _check_geometry_config(cfg)
     interact, shape = registry.OPTICS[cfg['class_name']]
+    key = None
+    if shape.startswith('mesh'):
+        key = _cache_key(xconfig.to_numpy(dict(cfg)))
+        if key is not None and key in _mesh_cache:
+            return copy.deepcopy(cfg), _mesh_cache[key]
+        if len(_mesh_cache) > 16:
+            _mesh_cache.clear()
 
     param = _param_from_config(cfg)
     param['_interact'] = interact
@@ -141,6 +173,8 @@ def prepare_optic(config_user, strict=True):
     if interact in ('crystal', 'mosaic'):
         param['rocking_type'] = str.lower(param['rocking_type'])
 
+    if key is not None:
+        _mesh_cache[key] = param
     return cfg, param
 
 

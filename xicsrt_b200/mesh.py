@@ -230,7 +230,25 @@ CT_NAMES = ('c3000', 'c0300', 'c0030', 'c0003', 'c2100', 'c2010', 'c2001', 'c120
             'c1020', 'c0120', 'c0021', 'c1002', 'c0102', 'c0012', 'c1101', 'c1011', 'c0111')
 
 
-def ct_coefficients(tri, values, grad):
+def barycentric_transforms(points, simplices):
+    """
+    (n_tri, 3, 2) in scipy's Delaunay.transform layout: rows 0, 1 = inverse of the matrix whose
+    columns are p0 - p2 and p1 - p2, row 2 = p2.  Closed-form 2x2 inverse (scipy's lazily computed
+    property costs ~1 s for a few thousand triangles; results agree to rounding, checked in
+    tests/test_mesh_tables.py).
+    """
+    p0, p1, p2 = points[simplices[:, 0]], points[simplices[:, 1]], points[simplices[:, 2]]
+    a, b = p0[:, 0] - p2[:, 0], p1[:, 0] - p2[:, 0]
+    c, d = p0[:, 1] - p2[:, 1], p1[:, 1] - p2[:, 1]
+    det = a * d - b * c
+    T = np.empty((len(simplices), 3, 2))
+    T[:, 0, 0], T[:, 0, 1] = d / det, -b / det
+    T[:, 1, 0], T[:, 1, 1] = -c / det, a / det
+    T[:, 2, :] = p2
+    return T
+
+
+def ct_coefficients(tri, values, grad, transform=None):
     """
     Control coefficients of scipy's Clough-Tocher cubic for every triangle (vectorised restatement of
     scipy/interpolate/interpnd.pyx ``_clough_tocher_2d_single``): vertex values and scipy's estimated
@@ -265,7 +283,7 @@ def ct_coefficients(tri, values, grad):
     c['c0021'] = (c['c1020'] + c['c0120'] + c['c0030']) / 3
 
     g = np.full((len(simp), 3), -0.5)
-    T = tri.transform
+    T = barycentric_transforms(pts, simp) if transform is None else transform
     for k in range(3):
         nb = tri.neighbors[:, k]
         has = nb != -1
@@ -391,6 +409,10 @@ def device_tables(param):
          'face_normals': np.ascontiguousarray(m['faces_normal'], dtype=np.float64),
          'point_faces': np.ascontiguousarray(m['p_faces_idx'], dtype=np.int32),
          'point_faces_mask': np.ascontiguousarray(m['p_faces_mask'], dtype=np.uint8)}
+    t['vertex_faces'] = np.ascontiguousarray(np.where(m['p_faces_mask'], m['p_faces_idx'], -1).T, dtype=np.int32)
+    rec = np.zeros((len(t['faces']), 16))
+    rec[:, 0:9], rec[:, 9:12], rec[:, 12] = t['face_geom'], t['face_normals'], t['face_area']
+    t['face_rec'] = rec
     refine = bool(param['mesh_refine'])
     if refine:
         mc = param['mesh_coarse']
@@ -401,23 +423,29 @@ def device_tables(param):
     tri = None
     if interp:
         tri = m['interp']['z'].tri
+        transform = barycentric_transforms(tri.points, tri.simplices)
         coef = []
         for key in ('z', 'normal_x', 'normal_y', 'normal_z'):
             ip = m['interp'][key]
-            coef.append(ct_coefficients(ip.tri, np.asarray(ip.values)[:, 0], np.asarray(ip.grad)[:, 0, :]))
+            coef.append(ct_coefficients(ip.tri, np.asarray(ip.values)[:, 0], np.asarray(ip.grad)[:, 0, :], transform))
         t['ct_coef'] = np.ascontiguousarray(np.stack(coef, axis=1), dtype=np.float64)      # (n_tri, 4, 19)
-        t['tri_transform'] = np.ascontiguousarray(tri.transform, dtype=np.float64)         # (n_tri, 3, 2)
+        t['tri_transform'] = np.ascontiguousarray(transform, dtype=np.float64)             # (n_tri, 3, 2)
         simplices = tri.simplices
     else:
         simplices = np.zeros((0, 3), dtype=np.int32)
     if interp or refine:
         t['grid'] = lookup_grids(t['points'][:, 0:2], simplices)
+        xyz = np.zeros((len(t['grid']['vert_items']), 4))
+        xyz[:, 0:3] = t['points'][t['grid']['vert_items']]
+        t['grid']['vert_xyz'] = xyz
     return t
 
 
 def fill_mesh(param, keep):
-    """-> (POINTER(XrtMesh), optic flag bits)."""
-    t = device_tables(param)
+    """-> (POINTER(XrtMesh), optic flag bits).  The tables are built once per prepared optic."""
+    t = param.get('_device_tables')
+    if t is None:
+        t = param['_device_tables'] = device_tables(param)
     m = L.XrtMesh()
     flags = 0
     m.n_points, m.n_faces = len(t['points']), len(t['faces'])
@@ -426,6 +454,8 @@ def fill_mesh(param, keep):
     m.face_normals = keep.f64(t['face_normals'])
     m.face_geom = keep.f64(t['face_geom'])
     m.face_area = keep.f64(t['face_area'])
+    m.face_rec = keep.f64(t['face_rec'])
+    m.vertex_faces = keep.arr(t['vertex_faces'], np.int32, C.c_int32)
     m.point_faces = keep.arr(t['point_faces'], np.int32, C.c_int32)
     m.point_faces_mask = keep.arr(t['point_faces_mask'], np.uint8, C.c_uint8)
     if 'coarse_points' in t:
@@ -447,5 +477,6 @@ def fill_mesh(param, keep):
         m.grid_items = keep.arr(g['tri_items'], np.int32, C.c_int32)
         m.vgrid_start = keep.arr(g['vert_start'], np.int32, C.c_int32)
         m.vgrid_items = keep.arr(g['vert_items'], np.int32, C.c_int32)
+        m.vgrid_xyz = keep.f64(g['vert_xyz'])
     keep.obj(m)
     return C.pointer(m), flags
