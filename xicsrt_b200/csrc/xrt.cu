@@ -478,14 +478,29 @@ static int fail(int code, const char *fmt, ...) {
             return fail(XRT_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Scene tables come from the device's stream-ordered memory pool (cudaMallocAsync): a scene is
+// created and destroyed per run, and plain cudaMalloc / cudaFree cost milliseconds each and
+// synchronise the device (100 ms per run for a plasma bundle table).  The pool keeps freed
+// blocks for the next scene.
+static int pool_keep_memory(int device) {
+    static thread_local int configured_for = -1;
+    if (configured_for == device) return XRT_OK;
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    configured_for = device;
+    return XRT_OK;
+}
+
 template <class T>
 static int upload(XrtScene *s, const T *host, size_t count, const T **dev) {
     *dev = nullptr;
     if (host == nullptr || count == 0) return XRT_OK;
     void *p = nullptr;
-    CU(cudaMalloc(&p, count * sizeof(T)));
+    CU(cudaMallocAsync(&p, count * sizeof(T), (cudaStream_t)0));
     s->allocs.push_back(p);
-    CU(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, (cudaStream_t)0));
     *dev = (const T *)p;
     return XRT_OK;
 }
@@ -561,7 +576,8 @@ extern "C" const char *xrt_last_error(void) { return g_err; }
 
 extern "C" int xrt_scene_destroy(XrtScene *s) {
     if (!s) return XRT_OK;
-    for (void *p : s->allocs) cudaFree(p);
+    // stream-ordered on the legacy stream: waits for kernels of every blocking stream that still read the tables
+    for (void *p : s->allocs) cudaFreeAsync(p, (cudaStream_t)0);
     delete s;
     return XRT_OK;
 }
@@ -672,7 +688,10 @@ extern "C" int xrt_scene_create(const XrtSceneDesc *desc, XrtScene **scene) {
         delete s;
         return fail(XRT_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
     }
-    int rc = scene_build(s, desc);
+    int rc = pool_keep_memory(s->device);
+    if (rc == XRT_OK) rc = scene_build(s, desc);
+    // host tables may be released by the caller as soon as this returns
+    if (rc == XRT_OK && cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) rc = fail(XRT_ECUDA, "scene upload failed");
     if (rc != XRT_OK) {
         xrt_scene_destroy(s);
         return rc;
