@@ -281,11 +281,12 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         }
         if (!more) break;
 
-        // ---- stage A
-        const uint64_t i = base + c.lane;
+        // ---- stage A (64-bit id arithmetic kept warp-uniform: one add per lane)
+        const uint64_t left = ray_count - base;
+        const unsigned n_valid = left < 32 ? (unsigned)left : 32u;
+        const uint64_t id = ray_begin + base + c.lane;
+        const bool valid = c.lane < n_valid;
         base += n_warps * 32;
-        const bool valid = i < ray_count;
-        const uint64_t id = ray_begin + i;
         PhiloxDraws dr;
         dr.init(seed, stream_id, id, split);
         Ray r;

@@ -124,9 +124,7 @@ struct PhiloxDraws {
     __device__ __forceinline__ double wave_z() const {
         uint4 r = raw(SITE_WAVE);
         double rad = sqrt(-2.0 * log_pos(1.0 - u01_40(r.x, r.y)));
-        double s, c;
-        sincos_2pi(u01_24(r.y), s, c);
-        return rad * c;
+        return rad * cos_2pi(u01_24(r.y));
     }
     __device__ __forceinline__ uint64_t lost_key() const {
         uint4 r = raw(SITE_LOSTKEY);
@@ -234,9 +232,13 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
         off[2] = -0.5 * L.ext2 + L.ext2 * u[2];
     }
     const double *R = s.orient;
-    r.o = v3(((L.org.x + off[0] * R[0]) + off[1] * R[3]) + off[2] * R[6],
-             ((L.org.y + off[0] * R[1]) + off[1] * R[4]) + off[2] * R[7],
-             ((L.org.z + off[0] * R[2]) + off[1] * R[5]) + off[2] * R[8]);
+    if constexpr ((KN & KN_POINT_SOURCE) != 0) {
+        r.o = L.org;      // origin + 0 x + 0 y + 0 z: the same value (finite axes)
+    } else {
+        r.o = v3(((L.org.x + off[0] * R[0]) + off[1] * R[3]) + off[2] * R[6],
+                 ((L.org.y + off[0] * R[1]) + off[1] * R[4]) + off[2] * R[7],
+                 ((L.org.z + off[0] * R[2]) + off[1] * R[5]) + off[2] * R[8]);
+    }
 
     // ---- local cone vector (xicsrt_spread.py:80-294)
     V3 l;
