@@ -373,6 +373,13 @@ def run_gpu_arm(args):
                'sample': f'{8 * procs} runs x 1e6 rays over {procs} processes, {dt:.1f} s '
                          f'(oracle port of the NumPy path; reference scheme xicsrt_multiprocessing)'}
 
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))['k_trace']['dram_bytes_per_launch']
+    except (OSError, KeyError, ValueError):
+        pass
+
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -387,7 +394,7 @@ def run_gpu_arm(args):
                     'api': 'xicsrt_b200.raytrace(config)'},
             'gpu_launches': args.steps,
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                         'frac': (achieved / fp64_peak) if achieved else None, 'traffic': None,
+                         'frac': (achieved / fp64_peak) if achieved else None, 'traffic': traffic,
                          'flop_equiv_per_ray': F, 'f_bounds': f_bounds, 'f_reflect': f_reflect,
                          'peak_source': 'DFMA-chain microbenchmark (xrt_fp64_burn) measured in this run',
                          'kernel': 'k_trace', 'kernel_ms_per_step': 1e3 * t_kernel / args.steps},

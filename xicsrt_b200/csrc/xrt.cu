@@ -353,7 +353,8 @@ __device__ __forceinline__ void store_history(const XrtHistory &h, int elem, uin
 
 enum { REC_PHILOX = 0, REC_INJECT = 1 };
 
-template <uint32_t FT, int MODE>
+// KN != 0: the scene has the known structure (split optic = optic 0), see k_trace
+template <uint32_t FT, int MODE, uint32_t KN = 0>
 __global__ void __launch_bounds__(kBlock)
 k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
          const uint64_t *__restrict__ ids, const uint64_t ray_begin, const uint64_t n,
@@ -367,7 +368,7 @@ k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uin
         if constexpr (MODE == REC_PHILOX) {
             const uint64_t id = ids ? ids[i] : ray_begin + i;
             pdr.init(seed, stream_id, id, split);
-            generate_ray<FT>(sc.source, pdr, id, r);
+            generate_ray<FT, PhiloxDraws, KN>(sc.source, pdr, id, r);
         } else {
             r.o = v3(in.origin + 3 * i);
             r.d = v3(in.direction + 3 * i);
@@ -383,8 +384,12 @@ k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uin
         for (int k = 0; k < nopt; ++k) {
             const XrtOpticDesc &op = sc.optics[k];
             if (r.alive) {
-                if constexpr (MODE == REC_PHILOX) trace_optic<FT>(op, k, pdr, r);
-                else trace_optic<FT>(op, k, idr, r);
+                if constexpr (MODE == REC_PHILOX) {
+                    if (KN != 0 && k == 0) trace_optic<FT, PhiloxDraws, KN>(op, k, pdr, r);
+                    else trace_optic<FT>(op, k, pdr, r);
+                } else {
+                    trace_optic<FT>(op, k, idr, r);
+                }
                 if (r.alive) {
                     if (out.counts) atomicAdd((unsigned long long *)(out.counts + k + 1), 1ull);
                     uint32_t pix;
@@ -795,7 +800,10 @@ static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const u
     uint64_t cap = (uint64_t)s->sm_count * 8;
     int grid = (int)(want < cap ? want : cap);
     cudaStream_t st = (cudaStream_t)stream;
-    if (s->features == 0)
+    if (s->features == 0 && MODE == REC_PHILOX && s->split == 0 && (s->known & KN_SPECTROMETER) == KN_SPECTROMETER)
+        k_record<0, MODE, (MODE == REC_PHILOX ? (uint32_t)KN_SPECTROMETER : 0u)><<<grid, kBlock, 0, st>>>(
+            s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+    else if (s->features == 0)
         k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == FT_MID)
         k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);

@@ -342,12 +342,12 @@ __device__ __forceinline__ bool wavelength_is_lazy(const XrtSourceDesc &s) {
     return s.kind != XRT_SRC_BUNDLES && s.velocity_c[0] == 0.0 && s.velocity_c[1] == 0.0 && s.velocity_c[2] == 0.0;
 }
 
-template <uint32_t FT, class DR>
+template <uint32_t FT, class DR, uint32_t KN = 0>
 __device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &dr, uint64_t index, Ray &r) {
     SrcLocal L;
-    source_local<FT>(s, index, L);
-    generate_geometry<FT>(s, L, dr, r);
-    r.w = generate_wavelength(s, L, dr, r.d);
+    source_local<FT, KN>(s, index, L);
+    generate_geometry<FT, DR, KN>(s, L, dr, r);
+    r.w = generate_wavelength<DR, KN>(s, L, dr, r.d);
 }
 
 // ---------------------------------------------------------------------------
@@ -771,10 +771,10 @@ __device__ __forceinline__ void optic_interact(const XrtOpticDesc &op, int k, co
 // both halves.  `r` must be alive on entry.  On exit: r.alive = survived; r.o = intersection
 // point (NaN when the surface was missed), r.d reflected only for surviving rays -- exactly
 // the state the reference's history holds for this element.
-template <uint32_t FT, class DR>
+template <uint32_t FT, class DR, uint32_t KN = 0>
 __device__ __forceinline__ void trace_optic(const XrtOpticDesc &op, int k, const DR &dr, Ray &r) {
     V3 n;
-    if (optic_geometry<FT, true>(op, r, n) == HIT_INSIDE) optic_interact<FT>(op, k, dr, r, n);
+    if (optic_geometry<FT, true, KN>(op, r, n) == HIT_INSIDE) optic_interact<FT, DR, KN>(op, k, dr, r, n);
 }
 
 }  // namespace xrt
