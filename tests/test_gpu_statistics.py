@@ -292,3 +292,22 @@ def test_single_optic_scene_and_no_image_optic(torch):
     cfg['sources']['source']['intensity'] = 50000
     res = xicsrt_b200.raytrace(cfg)
     assert res['total']['image']['crystal'] is None and res['total']['image']['detector'] is not None
+
+
+def test_fused_iterations_equal_separate_iterations(torch):
+    """History off: iterations enqueued back to back give the sums that combine_raytrace forms."""
+    import xicsrt_b200
+    from xicsrt_b200 import _driver, config as xconfig
+    cfg = scenes.get('sphere')
+    cfg['sources']['source']['intensity'] = 150000
+    cfg['general'].update({'keep_history': False, 'number_of_iter': 7, 'random_seed': 31})
+    res = xicsrt_b200.raytrace(cfg)
+    tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), 31)
+    parts = [_driver.run_iteration(tracer, it, keep_history=False) for it in range(7)]
+    tracer.close()
+    one = _driver.combine_raytrace(parts)
+    assert res['total']['meta'] == one['total']['meta']
+    assert res['total']['meta']['source']['num_out'] == 7 * 150000
+    for elem in ('crystal', 'detector'):
+        assert np.array_equal(res['total']['image'][elem], one['total']['image'][elem])
+    assert res['found']['history'] == {} and res['lost']['history'] == {}

@@ -323,6 +323,27 @@ def _gather_histories(out, names):
         out['lost']['history'] = merge_histories([b[1] for b in box], names)
 
 
+def run_iterations_fused(tracer, num_iter, keep_images=True):
+    """
+    History off: what ``combine_raytrace`` makes of the iterations is the sum of their counters and
+    images (xicsrt_raytrace.py:327-356), and those are already accumulated on the device.  All
+    iterations are therefore enqueued back to back into the same packed buffer -- no host
+    round trip between them -- and reduced and read back once.  (A 1e6-ray iteration is 25 us of
+    kernel time; a per-iteration device->host read would cost ten times that.)
+    """
+    out = _skeleton(tracer.config)
+    names = tracer.layout.element_names
+    for it in range(num_iter):
+        tracer.begin_iteration(it)
+        tracer.trace(it, keep_images, zero=(it == 0))
+    tracer.allreduce()
+    meta, image = tracer.counts_and_images(keep_images)
+    out['total']['meta'] = {name: {'num_out': meta[name]} for name in names}
+    if keep_images:
+        out['total']['image'] = image
+    return out
+
+
 def combine_raytrace(input_list, keep_images=True, components=None):
     """Sum meta and images, concatenate histories (xicsrt_raytrace.py:281-393)."""
     out = _skeleton(input_list[0]['config'])
@@ -410,12 +431,15 @@ def raytrace_single(config, _internal=False):
 
     tracer = Tracer(config, _resolve_seed(g['random_seed'], world), rank=rank, world=world)
     try:
-        parts = [run_iteration(tracer, it, keep_history=g['keep_history'], keep_images=g['keep_images'],
-                               keep_meta=g['keep_meta'], max_lost=max_lost_iter)
-                 for it in range(num_iter)]
+        if not g['keep_history'] and g['keep_meta']:
+            output = run_iterations_fused(tracer, num_iter, keep_images=g['keep_images'])
+        else:
+            parts = [run_iteration(tracer, it, keep_history=g['keep_history'], keep_images=g['keep_images'],
+                                   keep_meta=g['keep_meta'], max_lost=max_lost_iter)
+                     for it in range(num_iter)]
+            output = combine_raytrace(parts)
     finally:
         tracer.close()
-    output = combine_raytrace(parts)
     if _internal is False:
         _finish(output, g, single=True)
     return output

@@ -190,7 +190,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
         if (lazy) {
             SrcLocal L;
             source_local<0, KN>(sc.source, id, L);
-            r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
+            r.w = generate_wavelength<PhiloxDraws, KN, false>(sc.source, L, dr, r.d);   // lazy = no Doppler shift
         }
         bool analytic = true;
         if constexpr ((FT & FT_MESH) != 0) analytic = ops.shape != XRT_SHAPE_MESH;

@@ -152,10 +152,15 @@ XRT_HD double log_pos(double v) {
     const double s = f / (2.0 + f);
     const double dk = (double)k;
     const double z = s * s;
-    double R = XRT_TAB(kLog)[6];
-    R = fm(R, z, XRT_TAB(kLog)[5]); R = fm(R, z, XRT_TAB(kLog)[4]); R = fm(R, z, XRT_TAB(kLog)[3]);
-    R = fm(R, z, XRT_TAB(kLog)[2]); R = fm(R, z, XRT_TAB(kLog)[1]); R = fm(R, z, XRT_TAB(kLog)[0]);
-    R = R * z;
+    // two interleaved Horner chains in w = z^2 (odd and even coefficients, as fdlibm's t1 / t2):
+    // half the dependent-issue latency of one seven-term chain
+    const double w = z * z;
+    double t1 = XRT_TAB(kLog)[5];
+    double t2 = XRT_TAB(kLog)[6];
+    t1 = fm(t1, w, XRT_TAB(kLog)[3]); t2 = fm(t2, w, XRT_TAB(kLog)[4]);
+    t1 = fm(t1, w, XRT_TAB(kLog)[1]); t2 = fm(t2, w, XRT_TAB(kLog)[2]);
+    t1 = t1 * w;                      t2 = fm(t2, w, XRT_TAB(kLog)[0]);
+    double R = fm(t2, z, t1);
     const double hfsq = 0.5 * f * f;
     return fm(dk, XRT_TAB(kMisc)[1], -((hfsq - fm(s, hfsq + R, dk * XRT_TAB(kMisc)[2])) - f));
 }
@@ -166,13 +171,17 @@ XRT_HD double exp_neg(double x) {
     const double kf = round_even(y * XRT_TAB(kMisc)[3]);
     double r = fm(kf, -XRT_TAB(kMisc)[1], y);
     r = fm(kf, -XRT_TAB(kMisc)[2], r);
-    double p = XRT_TAB(kExp)[0];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 1; j < 12; ++j) p = fm(p, r, XRT_TAB(kExp)[j]);
-    p = fm(p, r, 1.0);     // + r
-    p = fm(p, r, 1.0);     // + 1
+    // sum_{k<=13} r^k / k! as two interleaved Horner chains in r^2 (even and odd powers)
+    const double r2 = r * r;
+    double pe = XRT_TAB(kExp)[1];      // 1/12!
+    double po = XRT_TAB(kExp)[0];      // 1/13!
+    pe = fm(pe, r2, XRT_TAB(kExp)[3]);  po = fm(po, r2, XRT_TAB(kExp)[2]);    // 1/10!, 1/11!
+    pe = fm(pe, r2, XRT_TAB(kExp)[5]);  po = fm(po, r2, XRT_TAB(kExp)[4]);    // 1/8!,  1/9!
+    pe = fm(pe, r2, XRT_TAB(kExp)[7]);  po = fm(po, r2, XRT_TAB(kExp)[6]);    // 1/6!,  1/7!
+    pe = fm(pe, r2, XRT_TAB(kExp)[9]);  po = fm(po, r2, XRT_TAB(kExp)[8]);    // 1/4!,  1/5!
+    pe = fm(pe, r2, XRT_TAB(kExp)[11]); po = fm(po, r2, XRT_TAB(kExp)[10]);   // 1/2!,  1/3!
+    pe = fm(pe, r2, 1.0);               po = fm(po, r2, 1.0);                 // 1,     r^1 coefficient
+    double p = fm(po, r, pe);
     const int32_t k = (int32_t)kf;
     return from_words(hi_word(p) + k * 1048576, lo_word(p));   // p in [0.7, 1.42], result normal for x <= 700
 }

@@ -319,7 +319,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
 }
 
 // wavelength (:295-367); `dir` is the ray direction at the source (Doppler shift)
-template <class DR, uint32_t KN = 0>
+template <class DR, uint32_t KN = 0, bool DOPPLER = true>
 __device__ __forceinline__ double generate_wavelength(const XrtSourceDesc &s, const SrcLocal &L, const DR &dr, V3 dir) {
     double w;
     if (((KN & KN_WAVE_NORMAL) != 0) || s.wave == XRT_WAVE_NORMAL) {
@@ -332,7 +332,9 @@ __device__ __forceinline__ double generate_wavelength(const XrtSourceDesc &s, co
         double y = s.wave_par[1] + (s.wave_par[2] - s.wave_par[1]) * dr.wave_u();
         w = interp_inside(y, s.table_cdf, s.table_x, s.n_table) + s.wave_par[0];
     }
-    if (L.vel.x != 0.0 || L.vel.y != 0.0 || L.vel.z != 0.0) w *= 1.0 - dot(L.vel, dir);
+    if constexpr (DOPPLER) {
+        if (L.vel.x != 0.0 || L.vel.y != 0.0 || L.vel.z != 0.0) w *= 1.0 - dot(L.vel, dir);
+    }
     return w;
 }
 
