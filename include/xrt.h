@@ -176,6 +176,39 @@ typedef struct XrtBundle {
     double velocity_c[3];    /* velocity / c                                                     */
 } XrtBundle;
 
+/* Per-iteration bundle table of a plasma source, built on the device: setup_bundles,
+   bundle_filter, bundle_generate and the per-bundle ray counts of create_sources
+   (xicsrt/sources/_XicsrtPlasmaGeneric.py:176-345; _XicsrtPlasmaCubic.py:23-35;
+   _XicsrtPlasmaToroidal.py:34-78; _XicsrtPlasmaToroidalDatafile.py:30-45;
+   xicsrt/filters/_XicsrtBundleFilterSightline.py:31-56). */
+enum { XRT_PLASMA_GENERIC = 0, XRT_PLASMA_CUBIC = 1, XRT_PLASMA_TOROIDAL = 2, XRT_PLASMA_DATAFILE = 3 };
+
+typedef struct XrtPlasmaDesc {
+    int32_t kind;            /* XRT_PLASMA_*                                                     */
+    int32_t use_poisson;     /* ray count = Poisson(intensity), else trunc(intensity)            */
+    int32_t use_spread_radius; /* spread = atan(spread_radius / |origin - target|)               */
+    int32_t n_sightlines;
+    int32_t n_profile_t, n_profile_e;   /* DATAFILE: lengths of the rho -> value tables          */
+    int32_t thermal_line;    /* 1: wave_sigma = sqrt(T) * sigma_factor (Doppler-broadened line)  */
+    int32_t pad0;
+    double origin[3];
+    double orient[9];
+    double size[3];          /* xsize, ysize, zsize of the plasma box                            */
+    double target[3];
+    double spread, spread_radius;
+    double temperature, emissivity;     /* CUBIC / TOROIDAL constants                            */
+    double velocity[3];                 /* TOROIDAL constant                                     */
+    double temperature_scale, emissivity_scale, velocity_scale;
+    double major_radius, minor_radius, torus_origin[3];
+    double intensity_factor; /* time_resolution * bundle_volume / (4 pi) * volume / (bundle_count * bundle_volume) */
+    double sigma_factor;     /* sqrt(1 / mass_number / amu / c^2 * eV) * wavelength              */
+    double inv_c;            /* 1 / speed of light                                               */
+    const double *profile_t_rho, *profile_t_val;   /* DEVICE pointers, caller-owned              */
+    const double *profile_e_rho, *profile_e_val;
+    const double *inject_u;  /* optional DEVICE [3][n] U[0,1) for the bundle centres (parity tests) */
+    XrtSightline sightlines[XRT_MAX_SIGHTLINES];
+} XrtPlasmaDesc;
+
 typedef struct XrtSourceDesc {
     int32_t kind;            /* XRT_SRC_*     */
     int32_t spatial;         /* XRT_SPATIAL_* */
@@ -300,6 +333,17 @@ int xrt_source_injected(XrtScene *scene, const XrtSourceInject *draws, uint64_t 
 /* Generate rays [ray_begin, +n) of the Philox stream into history element 0 only. */
 int xrt_source_generate(XrtScene *scene, uint64_t seed, uint64_t stream_id,
                         uint64_t ray_begin, uint64_t n, const XrtHistory *hist, void *stream);
+
+/* Build the bundle table of one iteration on the device (all pointers are device pointers owned
+   by the caller): table[i] for every bundle, intensity[i] = expected number of photons or -1 when
+   the bundle is filtered out, counts[i] = rays the bundle emits.  Random numbers: Philox keyed by
+   (seed, stream_id), counted by bundle index. */
+int xrt_bundles_generate(const XrtPlasmaDesc *desc, uint64_t seed, uint64_t stream_id, uint64_t n_bundles,
+                         XrtBundle *table_dev, double *intensity_dev, int64_t *counts_dev, void *stream);
+
+/* Point a plasma scene (source.kind == XRT_SRC_BUNDLES) at a device-resident bundle table and its
+   inclusive prefix sum of counts; bundles with a zero count are skipped by the lookup. */
+int xrt_scene_set_bundles(XrtScene *scene, const XrtBundle *table_dev, const uint64_t *end_dev, uint64_t n_bundles);
 
 /* FP64 FMA-chain microbenchmark: runs `iters` dependent-chain DFMA steps per thread on a
    full grid and reports the number of FP64 flops issued; the caller times it with CUDA

@@ -121,6 +121,84 @@ def torch():
     return torch
 
 
+class FixedUniforms:
+    """Host-random interface that hands out prepared uniforms (the ones injected into the device kernel)."""
+
+    def __init__(self, u):
+        self.u, self.k = u, 0
+
+    def uniform(self, lo, hi, n):
+        out = lo + (hi - lo) * self.u[self.k]
+        self.k += 1
+        return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['plasma_cubic', 'plasma_cubic_poisson', 'plasma_toroidal', 'plasma_datafile'])
+def test_device_bundle_table_matches_host_restatement(torch, name):
+    """xrt_bundles_generate with injected centre uniforms against the numpy restatement (pinned to the oracle above)."""
+    cfg = scenes.get(name)
+    cfg['sources']['source']['bundle_count'] = 5000
+    _, sname, sparam, sfilters, optics = xscene.prepare(xconfig.get_config(xconfig.to_numpy(cfg)))
+    dev = torch.device('cuda', 0)
+    n = int(sparam['bundle_count'])
+    u = np.random.default_rng(8).random((3, n))
+    ref = plasma.bundle_properties(sparam, sfilters, FixedUniforms(u))
+    inten = plasma.bundle_intensity(sparam, ref)
+
+    db = plasma.DeviceBundles(torch, dev, dict(sparam, use_poisson=True, max_rays=None), sfilters, L.load())
+    total = db.generate(5, 1 << 32, inject_u=torch.from_numpy(u).to(dev))
+    table = db.table.cpu().numpy()
+    got_int = db.intensity.cpu().numpy()
+    counts = db.counts.cpu().numpy()
+    m = ref['mask']
+    assert np.array_equal(got_int >= 0, m)
+    np.testing.assert_allclose(table[:, 0:3], ref['origin'], rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(table[:, 3], np.cos(ref['spread']), rtol=1e-13)
+    np.testing.assert_allclose(got_int[m], inten[m], rtol=1e-12)
+    np.testing.assert_allclose(table[m][:, 5:8], ref['velocity'][m] / voigt.C_LIGHT, rtol=1e-13, atol=1e-30)
+    thermal = ref['temperature'] > 0
+    sigma = np.where(thermal, voigt.doppler_sigma(np.abs(ref['temperature']), sparam['mass_number'], sparam['wavelength']), 0.0)
+    np.testing.assert_allclose(table[m][:, 4], sigma[m], rtol=1e-13)
+    # Poisson counts: zero where filtered, mean and variance of (k - lam) / sqrt(lam) as expected
+    assert not counts[~m].any() and total == counts.sum()
+    lam = inten[m]
+    ok = lam > 0
+    z = (counts[m][ok] - lam[ok]) / np.sqrt(lam[ok])
+    assert abs(z.mean()) < 5 / np.sqrt(len(z)) and abs(z.var() - 1) < 0.15
+    # without Poisson the count is the truncated intensity
+    if np.all(lam >= 1):
+        db2 = plasma.DeviceBundles(torch, dev, dict(sparam, use_poisson=False, max_rays=None), sfilters, L.load())
+        db2.generate(5, 1 << 32, inject_u=torch.from_numpy(u).to(dev))
+        assert np.array_equal(db2.counts.cpu().numpy()[m], lam.astype(np.int64))
+
+
+@pytest.mark.gpu
+def test_device_poisson_sampler_small_and_large_means(torch):
+    """Both branches of the sampler (inversion below 10, transformed rejection above) against scipy's pmf."""
+    from scipy import stats
+    cfg = scenes.get('plasma_cubic_poisson')
+    dev = torch.device('cuda', 0)
+    for emis in (5.3e13, 1.4e14, 5.3e14, 5.3e16):       # means of about 3, 8, 30 and 3000 rays per bundle
+        cfg['sources']['source'].update({'bundle_count': 200000, 'emissivity': emis, 'spread_radius': None,
+                                         'spread': float(np.radians(5.0))})
+        _, sname, sparam, sfilters, optics = xscene.prepare(xconfig.get_config(xconfig.to_numpy(cfg)))
+        db = plasma.DeviceBundles(torch, dev, dict(sparam, max_rays=None), sfilters, L.load())
+        db.generate(11, 1 << 32)
+        lam = float(db.intensity[0].cpu())
+        k = db.counts.cpu().numpy()
+        assert abs(k.mean() - lam) < 5 * np.sqrt(lam / len(k))
+        lo, hi = int(max(0, lam - 6 * np.sqrt(lam))), int(lam + 6 * np.sqrt(lam)) + 2
+        obs = np.bincount(np.clip(k, lo, hi) - lo, minlength=hi - lo + 1).astype(float)
+        exp = stats.poisson.pmf(np.arange(lo, hi + 1), lam) * len(k)
+        exp[0] += stats.poisson.cdf(lo - 1, lam) * len(k)
+        exp[-1] += stats.poisson.sf(hi, lam) * len(k)
+        keep = exp > 20
+        chi2 = np.sum((obs[keep] - exp[keep])**2 / exp[keep])
+        p = stats.chi2.sf(chi2, keep.sum() - 1)
+        assert p > 1e-4, (lam, chi2, keep.sum(), p)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['plasma_cubic_poisson', 'plasma_toroidal', 'plasma_datafile'])
 def test_device_rays_follow_their_bundles(torch, name):
@@ -135,25 +213,30 @@ def test_device_rays_follow_their_bundles(torch, name):
     rays, mask = tracer.history(0, ids)
     r = rays.cpu().numpy()[0]
     org, dirs, lam = r[0:3].T, r[3:6].T, r[6]
-    from xicsrt_b200 import plasma as xp
-    b = xp.build_bundles(tracer.source_param, tracer.source_filters, _driver.HostRandom(17, 1))
-    assert b['n_rays'] == n
-    end = b['end'].astype(np.int64)
+    end = tracer.bundles.end.cpu().numpy()
+    assert end[-1] == n
     which = np.searchsorted(end, np.arange(n), side='right')
-    tab = b['table'][which]
+    tab = tracer.bundles.table.cpu().numpy()[which]
+    t_origin, t_cos, t_sigma, t_vel = tab[:, 0:3], tab[:, 3], tab[:, 4], tab[:, 5:8]
     half = tracer.source_param['voxel_size'] / 2
-    assert np.all(np.abs(org - tab['origin']) <= half * (1 + 1e-12))
+    assert np.all(np.abs(org - t_origin) <= half * (1 + 1e-12))
     assert np.allclose(np.linalg.norm(dirs, axis=1), 1.0, atol=1e-12)
     axis = tracer.source_param['target'] - org
     axis /= np.linalg.norm(axis, axis=1)[:, None]
     cosang = np.einsum('ij,ij->i', axis, dirs)
-    assert np.all(cosang >= tab['cos_spread'] - 1e-12)
+    assert np.all(cosang >= t_cos - 1e-12)
     # wavelength: Doppler-shifted normal about lambda0 with the bundle's sigma
     lam0 = tracer.source_param['wavelength']
-    shift = 1 - np.einsum('ij,ij->i', tab['velocity_c'], dirs)
-    z = (lam / shift - lam0) / np.where(tab['wave_sigma'] > 0, tab['wave_sigma'], 1.0)
-    z = z[tab['wave_sigma'] > 0]
+    shift = 1 - np.einsum('ij,ij->i', t_vel, dirs)
+    z = (lam / shift - lam0) / np.where(t_sigma > 0, t_sigma, 1.0)
+    z = z[t_sigma > 0]
     assert abs(z.mean()) < 5 / np.sqrt(len(z)) and abs(z.std() - 1) < 5 / np.sqrt(2 * len(z))
+    # a new table every iteration, reproducible per (seed, iteration)
+    first = tracer.bundles.table.clone()
+    tracer.begin_iteration(1)
+    assert not torch.equal(first, tracer.bundles.table)
+    tracer._new_bundles(0)
+    assert torch.equal(first, tracer.bundles.table) and tracer.n_rays == n
     tracer.close()
 
 

@@ -117,20 +117,25 @@ class Tracer:
 
     # ------------------------------------------------------------------
     def _upload(self, iteration):
-        """Flatten and upload the scene; plasma sources draw a fresh bundle table per iteration."""
-        bundles = None
-        if self.is_plasma:
-            from . import plasma
-            bundles = plasma.build_bundles(self.source_param, self.source_filters,
-                                           HostRandom(self.seed, 1 + iteration))
+        """Flatten and upload the scene (once per run); plasma sources then get their first bundle table."""
         desc, self.layout, keep = xscene.flatten(self.source_name, self.source_param, self.source_filters,
-                                                 self.optics, bundles=bundles)
-        if self.scene is not None:
-            self.scene.close()
+                                                 self.optics)
         with self.torch.cuda.device(self.device):
             self.scene = xscene.DeviceScene(desc, self.layout)
         del keep
         self.n_rays = self.layout.n_rays
+        self.bundles = None
+        if self.is_plasma:
+            from . import plasma
+            self.bundles = plasma.DeviceBundles(self.torch, self.device, self.source_param, self.source_filters,
+                                                self.scene.lib)
+            self._new_bundles(iteration)
+
+    def _new_bundles(self, iteration):
+        """Bundle centres, plasma parameters and ray counts of one iteration, built on the device."""
+        self.n_rays = self.bundles.generate(self.seed, (1 << 32) + iteration)
+        self.layout.n_rays = self.n_rays
+        self.scene.set_bundles(self.bundles.table, self.bundles.end)
 
     def begin_iteration(self, iteration):
         """
@@ -138,7 +143,7 @@ class Tracer:
         (_XicsrtPlasmaGeneric.py:384-393): new bundle centres and ray counts each iteration.
         """
         if self.is_plasma and iteration > 0:
-            self._upload(iteration)
+            self._new_bundles(iteration)
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)

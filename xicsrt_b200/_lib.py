@@ -80,6 +80,25 @@ class XrtBundle(C.Structure):
                 ('velocity_c', C.c_double * 3)]
 
 
+PLASMA = {'plasma_generic': 0, 'plasma_cubic': 1, 'plasma_toroidal': 2, 'plasma_datafile': 3}
+
+
+class XrtPlasmaDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('use_poisson', C.c_int32), ('use_spread_radius', C.c_int32),
+                ('n_sightlines', C.c_int32), ('n_profile_t', C.c_int32), ('n_profile_e', C.c_int32),
+                ('thermal_line', C.c_int32), ('pad0', C.c_int32),
+                ('origin', C.c_double * 3), ('orient', C.c_double * 9), ('size', C.c_double * 3),
+                ('target', C.c_double * 3), ('spread', C.c_double), ('spread_radius', C.c_double),
+                ('temperature', C.c_double), ('emissivity', C.c_double), ('velocity', C.c_double * 3),
+                ('temperature_scale', C.c_double), ('emissivity_scale', C.c_double), ('velocity_scale', C.c_double),
+                ('major_radius', C.c_double), ('minor_radius', C.c_double), ('torus_origin', C.c_double * 3),
+                ('intensity_factor', C.c_double), ('sigma_factor', C.c_double), ('inv_c', C.c_double),
+                ('profile_t_rho', C.c_void_p), ('profile_t_val', C.c_void_p),
+                ('profile_e_rho', C.c_void_p), ('profile_e_val', C.c_void_p),
+                ('inject_u', C.c_void_p),
+                ('sightlines', XrtSightline * MAX_SIGHTLINES)]
+
+
 class XrtSourceDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('spatial', C.c_int32), ('cone', C.c_int32), ('wave', C.c_int32),
                 ('origin', C.c_double * 3), ('orient', C.c_double * 9), ('extent', C.c_double * 3),
@@ -143,6 +162,8 @@ SYMBOLS = {
                                      C.POINTER(XrtOutputs), C.POINTER(XrtHistory), _vp]),
     'xrt_source_injected': (C.c_int, [_vp, C.POINTER(XrtSourceInject), _u64, C.POINTER(XrtHistory), _vp]),
     'xrt_source_generate': (C.c_int, [_vp, _u64, _u64, _u64, _u64, C.POINTER(XrtHistory), _vp]),
+    'xrt_bundles_generate': (C.c_int, [C.POINTER(XrtPlasmaDesc), _u64, _u64, _u64, _vp, _vp, _vp, _vp]),
+    'xrt_scene_set_bundles': (C.c_int, [_vp, _vp, _vp, _u64]),
     'xrt_fp64_burn': (C.c_int, [_u64, _vp, C.POINTER(C.c_double), _vp]),
     'xrt_launch_info': (C.c_int, [_vp, _pi32, _pi32, _pi32, _pi32]),
 }

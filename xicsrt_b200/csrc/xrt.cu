@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "xrt_trace.cuh"
+#include "xrt_plasma.cuh"
 
 namespace xrt {
 
@@ -600,14 +601,18 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         return fail(XRT_EINVAL, "source.n_sightlines = %d", src.n_sightlines);
     if (src.wave == XRT_WAVE_TABLE && (src.n_table < 2 || !src.table_cdf || !src.table_x))
         return fail(XRT_EINVAL, "source wavelength table missing");
-    if (src.kind == XRT_SRC_BUNDLES && (src.n_bundles == 0 || !src.bundles || !src.bundle_end))
-        return fail(XRT_EINVAL, "plasma source without bundles");
+    const bool host_bundles = src.kind == XRT_SRC_BUNDLES && src.bundles && src.bundle_end && src.n_bundles > 0;
+    if (src.kind == XRT_SRC_BUNDLES && !host_bundles) {   // table supplied later by xrt_scene_set_bundles
+        src.bundles = nullptr;
+        src.bundle_end = nullptr;
+        src.n_bundles = 0;
+    }
     {
         XrtSourceDesc &m = src;
         UP(m.table_cdf, m.wave == XRT_WAVE_TABLE ? m.n_table : 0);
         UP(m.table_x, m.wave == XRT_WAVE_TABLE ? m.n_table : 0);
-        UP(m.bundles, m.kind == XRT_SRC_BUNDLES ? m.n_bundles : 0);
-        UP(m.bundle_end, m.kind == XRT_SRC_BUNDLES ? m.n_bundles : 0);
+        UP(m.bundles, host_bundles ? m.n_bundles : 0);
+        UP(m.bundle_end, host_bundles ? m.n_bundles : 0);
     }
 
     for (int k = 0; k < d.n_optics; ++k) {
@@ -773,6 +778,8 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     if (!s || !out) return fail(XRT_EINVAL, "null argument");
     if (ray_count == 0) return XRT_OK;
     if (s->dev.n_optics < 1) return fail(XRT_EINVAL, "a scene needs at least one optic");
+    if (s->dev.source.kind == XRT_SRC_BUNDLES && !s->dev.source.bundles)
+        return fail(XRT_EINVAL, "plasma scene without a bundle table: call xrt_scene_set_bundles first");
     TraceKernel kern;
     size_t smem;
     int bps = 0;
@@ -792,6 +799,8 @@ template <int MODE>
 static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const uint64_t *ids, uint64_t ray_begin,
                          uint64_t n, const XrtRaysIn &in, const XrtInject &inj, const XrtOutputs &out,
                          const XrtHistory &hist, void *stream) {
+    if (MODE == REC_PHILOX && s->dev.source.kind == XRT_SRC_BUNDLES && !s->dev.source.bundles)
+        return fail(XRT_EINVAL, "plasma scene without a bundle table: call xrt_scene_set_bundles first");
     if (hist.rays || hist.mask) {
         if (hist.capacity < n) return fail(XRT_EINVAL, "history capacity %llu < %llu rays",
                                            (unsigned long long)hist.capacity, (unsigned long long)n);
@@ -854,6 +863,8 @@ static int launch_source(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     if (!s || !hist) return fail(XRT_EINVAL, "null argument");
     if (n == 0) return XRT_OK;
     if (hist->capacity < n) return fail(XRT_EINVAL, "history capacity too small");
+    if (MODE == REC_PHILOX && s->dev.source.kind == XRT_SRC_BUNDLES && !s->dev.source.bundles)
+        return fail(XRT_EINVAL, "plasma scene without a bundle table: call xrt_scene_set_bundles first");
     uint64_t want = (n + kBlock - 1) / kBlock;
     uint64_t cap = (uint64_t)s->sm_count * 8;
     int grid = (int)(want < cap ? want : cap);
@@ -875,6 +886,39 @@ extern "C" int xrt_source_generate(XrtScene *s, uint64_t seed, uint64_t stream_i
                                    const XrtHistory *hist, void *stream) {
     XrtSourceInject none = {};
     return launch_source<REC_PHILOX>(s, seed, stream_id, ray_begin, n, none, hist, stream);
+}
+
+extern "C" int xrt_scene_set_bundles(XrtScene *s, const XrtBundle *table_dev, const uint64_t *end_dev, uint64_t n_bundles) {
+    if (!s) return fail(XRT_EINVAL, "null scene");
+    if (s->dev.source.kind != XRT_SRC_BUNDLES) return fail(XRT_EINVAL, "the scene's source is not a plasma");
+    if (!table_dev || !end_dev || n_bundles == 0) return fail(XRT_EINVAL, "empty bundle table");
+    s->dev.source.bundles = table_dev;
+    s->dev.source.bundle_end = end_dev;
+    s->dev.source.n_bundles = n_bundles;
+    return XRT_OK;
+}
+
+extern "C" int xrt_bundles_generate(const XrtPlasmaDesc *desc, uint64_t seed, uint64_t stream_id, uint64_t n_bundles,
+                                    XrtBundle *table_dev, double *intensity_dev, int64_t *counts_dev, void *stream) {
+    if (!desc || !table_dev || !intensity_dev || !counts_dev) return fail(XRT_EINVAL, "null argument");
+    if (n_bundles == 0) return XRT_OK;
+    if (desc->kind < XRT_PLASMA_GENERIC || desc->kind > XRT_PLASMA_DATAFILE) return fail(XRT_EINVAL, "plasma kind = %d", desc->kind);
+    if (desc->n_sightlines < 0 || desc->n_sightlines > XRT_MAX_SIGHTLINES) return fail(XRT_EINVAL, "n_sightlines = %d", desc->n_sightlines);
+    if (desc->kind == XRT_PLASMA_DATAFILE &&
+        (desc->n_profile_t < 2 || desc->n_profile_e < 2 || !desc->profile_t_rho || !desc->profile_t_val ||
+         !desc->profile_e_rho || !desc->profile_e_val))
+        return fail(XRT_EINVAL, "datafile plasma without profile tables");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(XRT_ECUDA, "no CUDA device: libxrt has no CPU path");
+    }
+    uint64_t want = (n_bundles + 255) / 256;
+    int grid = (int)(want < 65535 ? want : 65535);
+    k_bundles<<<grid, 256, 0, (cudaStream_t)stream>>>(*desc, seed, stream_id, n_bundles, table_dev, intensity_dev,
+                                                     (long long *)counts_dev);
+    CU(cudaGetLastError());
+    return XRT_OK;
 }
 
 extern "C" int xrt_fp64_burn(uint64_t iters, double *out_dev, double *flops, void *stream) {

@@ -156,3 +156,118 @@ def build_bundles(param, filters, rng):
     table = np.ascontiguousarray(rec)
     end = np.cumsum(counts[keep]).astype(np.uint64)
     return {'table': table, 'end': end, 'n_rays': int(end[-1]), 'props': b, 'counts': counts}
+
+
+# ---------------------------------------------------------------------------
+# device path: the same table built by libxrt (xrt_bundles_generate)
+
+def plasma_desc(param, filters, profiles=None, inject_u=None):
+    """
+    ``XrtPlasmaDesc`` of a prepared plasma source.  ``profiles`` = dict of device tensors
+    (t_rho, t_val, e_rho, e_val) for the datafile class; ``inject_u`` = optional device tensor
+    [3, n] of centre uniforms (parity tests).
+    """
+    if str(param['angular_dist']).lower() != 'isotropic':
+        raise NotImplementedError('plasma sources on the device support angular_dist="isotropic" only')
+    thermal = str(param['wavelength_dist']).lower() == 'voigt'
+    if thermal and float(param['linewidth']) != 0.0:
+        raise NotImplementedError('plasma sources with a natural linewidth need per-bundle Voigt tables')
+    if param['target'] is None:
+        raise ValueError('plasma sources need a target')
+    d = L.XrtPlasmaDesc()
+    d.kind = L.PLASMA[param['_kind']]
+    d.use_poisson = 1 if param['use_poisson'] else 0
+    d.use_spread_radius = 1 if param['spread_radius'] is not None else 0
+    d.thermal_line = 1 if thermal else 0
+    for i in range(3):
+        d.origin[i] = float(param['origin'][i])
+        d.target[i] = float(param['target'][i])
+    for i, v in enumerate(np.asarray(param['orientation'], dtype=np.float64).ravel()):
+        d.orient[i] = float(v)
+    d.size[0], d.size[1], d.size[2] = float(param['xsize']), float(param['ysize']), float(param['zsize'])
+    d.spread = 0.0 if param['spread'] is None else float(np.atleast_1d(param['spread'])[0])
+    d.spread_radius = 0.0 if param['spread_radius'] is None else float(param['spread_radius'])
+    kind = param['_kind']
+    if kind in ('plasma_cubic', 'plasma_toroidal'):
+        d.temperature = float(param['temperature'])
+        d.emissivity = float(param['emissivity'])
+    if kind in ('plasma_toroidal', 'plasma_datafile'):
+        vel = np.broadcast_to(np.asarray(param['velocity'], dtype=np.float64), (3,))
+        d.velocity[0], d.velocity[1], d.velocity[2] = (float(v) for v in vel)
+        d.temperature_scale = float(param['temperature_scale'])
+        d.emissivity_scale = float(param['emissivity_scale'])
+        d.velocity_scale = float(param['velocity_scale'])
+        d.major_radius, d.minor_radius = float(param['major_radius']), float(param['minor_radius'])
+        for i in range(3):
+            d.torus_origin[i] = float(np.asarray(param['torus_origin'], dtype=np.float64)[i])
+    if kind == 'plasma_datafile':
+        d.n_profile_t, d.n_profile_e = int(profiles['t_rho'].numel()), int(profiles['e_rho'].numel())
+        d.profile_t_rho, d.profile_t_val = profiles['t_rho'].data_ptr(), profiles['t_val'].data_ptr()
+        d.profile_e_rho, d.profile_e_val = profiles['e_rho'].data_ptr(), profiles['e_val'].data_ptr()
+    d.intensity_factor = float(param['time_resolution'] * param['bundle_volume'] / (4 * np.pi)
+                               * (param['volume'] / (param['bundle_count'] * param['bundle_volume'])))
+    d.sigma_factor = float(voigt.doppler_sigma(1.0, param['mass_number'], float(param['wavelength'])))
+    d.inv_c = 1.0 / voigt.C_LIGHT
+    sight = [f for f in filters if f['_kind'] == 'sightline']
+    if len(sight) > L.MAX_SIGHTLINES:
+        raise NotImplementedError(f'more than {L.MAX_SIGHTLINES} sightline filters on one source')
+    d.n_sightlines = len(sight)
+    for k, f in enumerate(sight):
+        for i in range(3):
+            d.sightlines[k].origin[i] = float(f['origin'][i])
+            d.sightlines[k].axis[i] = float(f['zaxis'][i])
+        d.sightlines[k].radius = float(f['radius'])
+    if inject_u is not None:
+        d.inject_u = inject_u.data_ptr()
+    return d
+
+
+def load_profiles(param, torch, device):
+    """rho -> value tables of the datafile class as device tensors (two-column text files)."""
+    out = {}
+    for tag, key in (('t', 'temperature_file'), ('e', 'emissivity_file')):
+        data = np.loadtxt(param[key], dtype=np.float64)
+        out[f'{tag}_rho'] = torch.from_numpy(np.ascontiguousarray(data[:, 0])).to(device)
+        out[f'{tag}_val'] = torch.from_numpy(np.ascontiguousarray(data[:, 1])).to(device)
+    return out
+
+
+class DeviceBundles:
+    """The bundle table of one iteration, resident on the device (torch tensors)."""
+
+    def __init__(self, torch, device, param, filters, lib):
+        self.torch, self.device, self.param, self.lib = torch, device, param, lib
+        self.n = int(param['bundle_count'])
+        self.profiles = load_profiles(param, torch, device) if param['_kind'] == 'plasma_datafile' else None
+        self.filters = filters
+        self.table = torch.empty((self.n, 8), dtype=torch.float64, device=device)     # XrtBundle = 8 doubles
+        self.intensity = torch.empty(self.n, dtype=torch.float64, device=device)
+        self.counts = torch.empty(self.n, dtype=torch.int64, device=device)
+        self.end = None
+        assert C.sizeof(L.XrtBundle) == 64
+
+    def generate(self, seed, stream_id, inject_u=None):
+        """Build the table for (seed, stream_id); returns the total number of rays."""
+        torch = self.torch
+        desc = plasma_desc(self.param, self.filters, self.profiles, inject_u)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.xrt_bundles_generate(C.byref(desc), int(seed), int(stream_id), self.n,
+                                                  self.table.data_ptr(), self.intensity.data_ptr(),
+                                                  self.counts.data_ptr(), stream))
+        kept = self.intensity >= 0
+        inten = torch.where(kept, self.intensity, torch.zeros_like(self.intensity))
+        # one device->host read for the three numbers the host needs
+        self.end = torch.cumsum(self.counts, 0)
+        lowest = torch.where(kept, self.intensity, torch.full_like(self.intensity, float('inf'))).min()
+        stats = torch.stack([inten.sum(), lowest, self.end[-1].to(torch.float64)]).cpu().numpy()
+        predicted, lowest, total = int(stats[0]), float(stats[1]), int(stats[2])
+        if self.param['max_rays'] and predicted > self.param['max_rays']:
+            raise ValueError(
+                f"Current settings will produce too many rays ({predicted:0.2e}). "
+                f"Please reduce integration time or adjust other parameters.")
+        if not self.param['use_poisson'] and lowest < 1:
+            raise ValueError('intensity of less than one encountered. Turn on poisson statistics.')
+        if total == 0:
+            raise ValueError('No rays generated. Check plasma input parameters')
+        return total

@@ -144,10 +144,11 @@ def fill_source(src, param, filters, keep, bundles=None):
         if model['mode'] == 'table':
             raise NotImplementedError('plasma sources with a natural linewidth (per-bundle Voigt tables)')
         src.voxel_size = float(param['voxel_size'])
-        src.n_bundles = len(bundles['end'])
-        table = keep.obj(np.ascontiguousarray(bundles['table']))
-        src.bundles = C.cast(table.ctypes.data, C.POINTER(L.XrtBundle))
-        src.bundle_end = keep.arr(bundles['end'], np.uint64, C.c_uint64)
+        if bundles is not None:          # host-built table (tests); the driver builds it on the device
+            src.n_bundles = len(bundles['end'])
+            table = keep.obj(np.ascontiguousarray(bundles['table']))
+            src.bundles = C.cast(table.ctypes.data, C.POINTER(L.XrtBundle))
+            src.bundle_end = keep.arr(bundles['end'], np.uint64, C.c_uint64)
         _set(src.extent, [param['voxel_size']] * 3)
     else:
         if spatial == 'uniform':
@@ -339,7 +340,10 @@ def flatten(source_name, source_param, source_filters, optics, bundles=None):
     layout = SceneLayout()
     layout.source_name = source_name
     fill_source(desc.source, source_param, source_filters, keep, bundles=bundles)
-    layout.n_rays = int(bundles['end'][-1]) if bundles is not None else int(source_param['intensity'])
+    if bundles is not None:
+        layout.n_rays = int(bundles['end'][-1])
+    else:
+        layout.n_rays = int(source_param.get('intensity', 0))     # plasma: set per iteration by the driver
     offset = 0
     for k, (name, param) in enumerate(optics.items()):
         npix = fill_optic(desc.optics[k], param, keep, offset)
@@ -370,6 +374,10 @@ class DeviceScene:
             self.close()
         except Exception:
             pass
+
+    def set_bundles(self, table, end):
+        """Point a plasma scene at a device-resident bundle table (torch tensors, kept alive by the caller)."""
+        L.check(self.lib.xrt_scene_set_bundles(self.handle, table.data_ptr(), end.data_ptr(), int(end.numel())))
 
     def launch_info(self):
         g, b, r, p = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
