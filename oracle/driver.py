@@ -13,7 +13,7 @@ import multiprocessing
 import numpy as np
 
 from xicsrt_b200 import config as xconfig
-from xicsrt_b200 import elements, registry
+from xicsrt_b200 import elements
 
 from oracle import optics, sources
 from oracle.stream import LegacyStream

@@ -15,7 +15,6 @@ each pair ordered (-sqrt, +sqrt).  Complex arithmetic is kept exactly as in
 the reference because ``_ShapeTorus.py:164-167`` decides "no intersection" by
 ``imag != 0`` on these complex values.
 """
-import math
 
 import numpy as np
 

@@ -89,3 +89,21 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
             assert getattr(getattr(L, struct), field).offset == value, what
         else:
             assert C.sizeof(getattr(L, what)) == value, what
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without libxrt.so the binding raises instead of computing something else."""
+    monkeypatch.setattr(L, '_lib', None)
+    monkeypatch.setattr(L, 'LIB_PATH', str(tmp_path / 'libxrt.so'))
+    with pytest.raises(ImportError, match='no CPU fallback'):
+        L.load()
+
+
+def test_public_api_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a device is present')
+    import xicsrt_b200
+    from oracle import scenes
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        xicsrt_b200.raytrace(scenes.get('sphere'))

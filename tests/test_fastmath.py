@@ -40,7 +40,7 @@ int main() {
         double x = (i % 2) ? u * 45.0 : u * 700.0;
         long double re = expl(-(long double)x);
         ee = fmax(ee, fabs((double)((exp_neg(x) - re) / re)));
-        double w = (u - 0.5) * 0.02;
+        double w = (u - 0.5) * 0.1;
         if (w != 0) ea = fmax(ea, fabs((double)((asin_small(w) - asinl((long double)w)) / asinl((long double)w))));
     }
     double s0, c0, s1, c1;

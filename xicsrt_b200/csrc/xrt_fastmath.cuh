@@ -186,11 +186,14 @@ XRT_HD double exp_neg(double x) {
     return from_words(hi_word(p) + k * 1048576, lo_word(p));   // p in [0.7, 1.42], result normal for x <= 700
 }
 
-// asin(w) for the difference of two angles: series for the small arguments that matter,
-// the library call otherwise.  |w| < 0.01: next term (35/1152) w^9 is below 4e-18 relative.
+// asin(w) for the difference of two angles: series for the small arguments that matter
+// (|w| < 0.05 covers mosaic spreads of a few degrees), the library call otherwise.
+// Next term (231/13312) w^13 is below 5e-18 relative at the limit.
 XRT_HD double asin_small(double w) {
     const double z = w * w;
-    double p = 15.0 / 336.0;
+    double p = 63.0 / 2816.0;
+    p = fm(p, z, 35.0 / 1152.0);
+    p = fm(p, z, 15.0 / 336.0);
     p = fm(p, z, 3.0 / 40.0);
     p = fm(p, z, 1.0 / 6.0);
     return fm(w * z, p, w);

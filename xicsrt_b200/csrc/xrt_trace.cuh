@@ -138,11 +138,17 @@ struct PhiloxDraws {
     // Reflection probability below 2^-57: the ray passes only when the uniform is exactly 0
     // (p >= u).  With Philox that draw is not made at all (probability 1.1e-16 per ray).
     __device__ __forceinline__ bool bragg_u_is_zero(int, int) const { return false; }
+    // One Philox block per mosaic layer: words x, y -> the two crystallite offsets (Box-Muller from a
+    // 40-bit radius uniform and a 24-bit angle), words z, w -> the rocking-curve uniform of that layer.
     __device__ __forceinline__ void mosaic_xy(int k, int layer, double s, double &x, double &y) const {
-        double a, b, z0, z1;
-        pair(site_optic(k, layer, 1), a, b);
-        box_muller(a, b, z0, z1);
+        uint4 r = raw(site_optic(k, layer, 1));
+        double z0, z1;
+        box_muller(u01_40(r.x, r.y), u01_24(r.y), z0, z1);
         x = s * z0; y = s * z1;
+    }
+    __device__ __forceinline__ double mosaic_u(int k, int layer) const {
+        uint4 r = raw(site_optic(k, layer, 1));
+        return u01(r.z, r.w);
     }
 };
 
@@ -154,6 +160,7 @@ struct InjectedDraws {
         return inj->u[k][(uint64_t)layer * n + i];
     }
     __device__ __forceinline__ bool bragg_u_is_zero(int k, int layer) const { return bragg_u(k, layer) == 0.0; }
+    __device__ __forceinline__ double mosaic_u(int k, int layer) const { return bragg_u(k, layer); }
     __device__ __forceinline__ void mosaic_xy(int k, int layer, double, double &x, double &y) const {
         const double *p = inj->xy[k] + (uint64_t)layer * 2 * n;
         x = p[i]; y = p[n + i];
@@ -519,11 +526,11 @@ __device__ __forceinline__ double bragg_dtheta(const XrtOpticDesc &op, V3 d, dou
     double s = w * op.inv_two_d;
     double c = fabs(dot(d, n)) * rsqrt(dot(d, d));
     double x = c * sqrt(fma(-s, s, 1.0)) - s * sqrt(fma(-c, c, 1.0));
-    return (fabs(x) < 0.01) ? asin_small(x) : asin(x);      // NaN (lambda > 2d) goes to asin -> NaN
+    return (fabs(x) < 0.05) ? asin_small(x) : asin(x);      // NaN (lambda > 2d) goes to asin -> NaN
 }
 
 // true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).
-template <uint32_t FT, class DR, uint32_t KN = 0>
+template <uint32_t FT, class DR, uint32_t KN = 0, bool MOSAIC = false>
 __device__ __forceinline__ bool bragg_pass(const XrtOpticDesc &op, int k, int layer, const DR &dr, double dth) {
     double p;
     const int rocking = rocking_of<KN>(op);
@@ -548,7 +555,8 @@ __device__ __forceinline__ bool bragg_pass(const XrtOpticDesc &op, int k, int la
         if (!(dth == dth)) return false;
     }
     p *= op.reflectivity;
-    return p >= dr.bragg_u(k, layer);
+    if constexpr (MOSAIC) return p >= dr.mosaic_u(k, layer);
+    else return p >= dr.bragg_u(k, layer);
 }
 
 // _InteractMirror.py:29-42
@@ -757,7 +765,7 @@ __device__ __forceinline__ void optic_interact(const XrtOpticDesc &op, int k, co
                     dr.mosaic_xy(k, layer, op.mosaic_sin_sigma, x, y);
                     V3 nm = mosaic_normal(n, x, y);
                     bool pass = true;
-                    if (flags & XRT_F_CHECK_BRAGG) pass = bragg_pass<FT, DR, KN>(op, k, layer, dr, bragg_dtheta(op, r.d, r.w, nm));
+                    if (flags & XRT_F_CHECK_BRAGG) pass = bragg_pass<FT, DR, KN, true>(op, k, layer, dr, bragg_dtheta(op, r.d, r.w, nm));
                     if (pass) { reflect(r, nm); done = true; }
                 }
                 alive = done;
