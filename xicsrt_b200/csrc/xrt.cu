@@ -17,6 +17,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -786,6 +787,10 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     int rc = trace_launch_config(s, &kern, &smem, &bps, nullptr);
     if (rc != XRT_OK) return rc;
     // one resident wave of blocks, each warp strides over the ray ids
+    if (const char *lim = getenv("XRT_BLOCKS_PER_SM")) {      // measurement knob: fewer resident blocks
+        int v = atoi(lim);
+        if (v >= 1 && v < bps) bps = v;
+    }
     uint64_t want = (ray_count + kBlock - 1) / kBlock;
     uint64_t cap = (uint64_t)s->sm_count * (uint64_t)bps;
     int grid = (int)(want < cap ? want : cap);
