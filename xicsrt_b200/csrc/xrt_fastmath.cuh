@@ -96,6 +96,21 @@ XRT_HD double round_even(double x) {
 #endif
 }
 
+// 1 / x for normal-range x: hardware seed plus two Newton steps on the device (no special-case
+// path), a plain division on the host.
+XRT_HD double recip(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, fma(e, e, e), y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+
 // sin(2 pi u), cos(2 pi u) for u in [0, 1].  Reduction: t = 4u, q = rint(t), r = t - q is
 // exact, x = r pi/2 in [-pi/4, pi/4]; quadrant from q mod 4.
 XRT_HD void sincos_2pi(double u, double &s, double &c) {
@@ -149,7 +164,7 @@ XRT_HD double log_pos(double v) {
     const double m = from_words(hx | (i ^ 0x3ff00000), lo_word(v));
     k += (i >> 20);
     const double f = m - 1.0;
-    const double s = f / (2.0 + f);
+    const double s = f * recip(2.0 + f);
     const double dk = (double)k;
     const double z = s * s;
     // two interleaved Horner chains in w = z^2 (odd and even coefficients, as fdlibm's t1 / t2):

@@ -18,7 +18,29 @@ __device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
     return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-__device__ __forceinline__ V3 unit(V3 a) { return a * rsqrt(dot(a, a)); }
+// Square root, reciprocal square root and reciprocal without the library's special-case path.
+// The library versions add a range check, a branch and an out-of-line slow path for subnormal /
+// huge arguments to every call; the ray code only meets normal-range values (lengths of order
+// one, 1 - x^2 with |x| <= 1), for which the hardware seed (MUFU, ~2^-22 relative) plus one
+// third-order step and a residual correction is correctly rounded to within an ulp.
+//   x < 0 or NaN -> NaN (as sqrt), x == 0 -> 0 for the square root.
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    const double y = rsqrt_seed(x);
+    const double e = fma(-x * y, y, 1.0);                       // 1 - x y^2
+    return fma(y * e, fma(e, 0.375, 0.5), y);                   // y (1 + e/2 + 3 e^2 / 8)
+}
+__device__ __forceinline__ double fast_sqrt(double x) {
+    const double y = fast_rsqrt(x);
+    double g = x * y;
+    g = fma(fma(-g, g, x), 0.5 * y, g);                         // residual correction
+    return (x == 0.0) ? 0.0 : g;
+}
+__device__ __forceinline__ V3 unit(V3 a) { return a * fast_rsqrt(dot(a, a)); }
 __device__ __forceinline__ V3 nan3() { return v3(CUDART_NAN, CUDART_NAN, CUDART_NAN); }
 
 // rows of a 3x3 orientation (x, y, z axes of an element)
@@ -69,7 +91,7 @@ __device__ __forceinline__ double u01_24(uint32_t b) {
 
 // two independent standard normals from two uniforms (Box-Muller); 1 - u1 is in (0, 1]
 __device__ __forceinline__ void box_muller(double u1, double u2, double &z1, double &z2) {
-    double r = sqrt(-2.0 * log_pos(1.0 - u1));
+    double r = fast_sqrt(-2.0 * log_pos(1.0 - u1));
     double s, c;
     sincos_2pi(u2, s, c);
     z1 = r * c;

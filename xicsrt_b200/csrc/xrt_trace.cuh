@@ -123,7 +123,7 @@ struct PhiloxDraws {
     __device__ __forceinline__ double wave_u() const { uint4 r = raw(SITE_WAVE); return u01(r.x, r.y); }
     __device__ __forceinline__ double wave_z() const {
         uint4 r = raw(SITE_WAVE);
-        double rad = sqrt(-2.0 * log_pos(1.0 - u01_40(r.x, r.y)));
+        double rad = fast_sqrt(-2.0 * log_pos(1.0 - u01_40(r.x, r.y)));
         return rad * cos_2pi(u01_24(r.y));
     }
     __device__ __forceinline__ uint64_t lost_key() const {
@@ -256,7 +256,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
         double a, b;
         dr.cone(0, a, b);
         double z = L.cos_spread + (1.0 - L.cos_spread) * a;
-        double rho = sqrt(fma(-z, z, 1.0));
+        double rho = fast_sqrt(fma(-z, z, 1.0));
         double sn, cs;
         sincos_2pi(b, sn, cs);
         l = v3(rho * cs, rho * sn, z);
@@ -382,7 +382,7 @@ __device__ __forceinline__ bool hit_sphere(const XrtOpticDesc &op, bool convex, 
     double d2 = fma(-tca, tca, dot(L, L));
     double r2 = op.radius * op.radius;
     if (!(d2 >= 0.0 && d2 <= r2)) return false;
-    double thc = sqrt(r2 - d2);
+    double thc = fast_sqrt(r2 - d2);
     t = convex ? tca - thc : tca + thc;     // min / max of tca -+ thc (thc >= 0)
     return true;
 }
@@ -524,8 +524,8 @@ __device__ __forceinline__ bool aperture_fold(const XrtOpticDesc &op, double x, 
 // fma, i.e. correctly rounded, so the conditioning is that of the reference's own acos.
 __device__ __forceinline__ double bragg_dtheta(const XrtOpticDesc &op, V3 d, double w, V3 n) {
     double s = w * op.inv_two_d;
-    double c = fabs(dot(d, n)) * rsqrt(dot(d, d));
-    double x = c * sqrt(fma(-s, s, 1.0)) - s * sqrt(fma(-c, c, 1.0));
+    double c = fabs(dot(d, n)) * fast_rsqrt(dot(d, d));
+    double x = c * fast_sqrt(fma(-s, s, 1.0)) - s * fast_sqrt(fma(-c, c, 1.0));
     return (fabs(x) < 0.05) ? asin_small(x) : asin(x);      // NaN (lambda > 2d) goes to asin -> NaN
 }
 
@@ -585,7 +585,7 @@ __device__ __forceinline__ V3 normal_torus(const XrtOpticDesc &op, V3 X) {
     V3 C = v3(op.center), ya = v3(op.orient + 3);
     V3 p = X - C;
     p = p - ya * dot(p, ya);
-    V3 Q = C + p * (op.torus_major * rsqrt(dot(p, p)));
+    V3 Q = C + p * (op.torus_major * fast_rsqrt(dot(p, p)));
     return unit(X - Q);
 }
 
@@ -594,7 +594,7 @@ __device__ __forceinline__ V3 normal_torus(const XrtOpticDesc &op, V3 X) {
 // (_InteractMosaicCrystal.py:109-139, xicsrt_spread.py:297-339)
 
 __device__ __forceinline__ V3 mosaic_normal(V3 n, double x, double y) {
-    double inv = rsqrt(x * x + y * y + 1.0);
+    double inv = fast_rsqrt(x * x + y * y + 1.0);
     double lx = x * inv, ly = y * inv, lz = inv;
     // R0 = n x [1,0,0] + n x [0,0,1];  R1 = n x R0
     V3 r0 = v3(0.0 + n.y, n.z - n.x, -n.y + 0.0);
