@@ -171,7 +171,9 @@ typedef struct XrtSightline {    /* xicsrt/filters/_XicsrtBundleFilterSightline.
 /* one plasma bundle = one focused voxel source (_XicsrtPlasmaGeneric.py:286-345) */
 typedef struct XrtBundle {
     double origin[3];
-    double cos_spread;       /* cos(spread) of the isotropic cone                                */
+    double cos_spread;       /* cone parameter of this bundle: cos(spread) for the isotropic cone,
+                                tan(spread) for flat / flat_xy, sin(spread) for isotropic_xy
+                                (a scalar spread s means [-s, s, -s, s], xicsrt_spread.py:352-366) */
     double wave_sigma;       /* Doppler sigma of this bundle [A] (XRT_WAVE_NORMAL)               */
     double velocity_c[3];    /* velocity / c                                                     */
 } XrtBundle;
@@ -189,8 +191,10 @@ typedef struct XrtPlasmaDesc {
     int32_t use_spread_radius; /* spread = atan(spread_radius / |origin - target|)               */
     int32_t n_sightlines;
     int32_t n_profile_t, n_profile_e;   /* DATAFILE: lengths of the rho -> value tables          */
-    int32_t thermal_line;    /* 1: wave_sigma = sqrt(T) * sigma_factor (Doppler-broadened line)  */
-    int32_t pad0;
+    int32_t thermal_line;    /* 1: wave_sigma = sqrt(T) * sigma_factor (Doppler-broadened line);
+                                2: the same with a natural linewidth: a bundle at T == 0 gets 1 eV
+                                (_XicsrtSourceGeneric.py:333-339)                                   */
+    int32_t cone;            /* XRT_CONE_* of the per-bundle sources (angular_dist)              */
     double origin[3];
     double orient[9];
     double size[3];          /* xsize, ysize, zsize of the plasma box                            */
@@ -237,6 +241,10 @@ typedef struct XrtSourceDesc {
     const XrtBundle *bundles;        /* [n_bundles]                                              */
     const uint64_t *bundle_end;      /* [n_bundles] inclusive prefix sum of rays per bundle      */
     double voxel_size;
+    /* plasma with a natural linewidth: one inverse-CDF table per bundle (XRT_WAVE_TABLE), rows of
+       n_table entries; a row is valid where the bundle emits rays (xrt_bundle_voigt_tables)     */
+    const double *bundle_x;          /* [n_bundles][n_table]                                     */
+    const double *bundle_cdf;        /* [n_bundles][n_table]                                     */
 } XrtSourceDesc;
 
 typedef struct XrtSceneDesc {
@@ -344,6 +352,18 @@ int xrt_bundles_generate(const XrtPlasmaDesc *desc, uint64_t seed, uint64_t stre
 /* Point a plasma scene (source.kind == XRT_SRC_BUNDLES) at a device-resident bundle table and its
    inclusive prefix sum of counts; bundles with a zero count are skipped by the lookup. */
 int xrt_scene_set_bundles(XrtScene *scene, const XrtBundle *table_dev, const uint64_t *end_dev, uint64_t n_bundles);
+
+/* Per-bundle Voigt inverse-CDF tables (xicsrt/tools/xicsrt_voigt.py:30-92, built by every
+   per-bundle XicsrtSourceFocused in _XicsrtSourceGeneric.py:319-354): for each bundle b with
+   counts_dev[b] > 0, sigma = table_dev[b].wave_sigma and the given Lorentzian gamma [A], writes
+   the right bin edges x_dev[b][0..n_table) and the cumulative sums cdf_dev[b][0..n_table) of
+   pdf * dx on the reference's stretched grid.  The Voigt profile is evaluated on the device
+   (Faddeeva function by the exponentially convergent trapezoid rule with pole correction). */
+int xrt_bundle_voigt_tables(const XrtBundle *table_dev, const int64_t *counts_dev, uint64_t n_bundles,
+                            double gamma, int32_t n_table, double *x_dev, double *cdf_dev, void *stream);
+
+/* Attach per-bundle wavelength tables to a plasma scene (after xrt_scene_set_bundles). */
+int xrt_scene_set_bundle_tables(XrtScene *scene, const double *x_dev, const double *cdf_dev, int32_t n_table);
 
 /* FP64 FMA-chain microbenchmark: runs `iters` dependent-chain DFMA steps per thread on a
    full grid and reports the number of FP64 flops issued; the caller times it with CUDA

@@ -53,6 +53,23 @@ def plasma_datafile(seed=24):
     return assemble(src, {'crystal': crystal_G(radius=1.0, rocking_fwhm=2000e-6), 'detector': detector_G()}, seed)
 
 
+def plasma_voigt(seed=25):
+    """Natural linewidth > 0 on a plasma whose temperature varies from bundle to bundle: every
+    per-bundle source of the reference builds its own Voigt table."""
+    src = _plasma('XicsrtPlasmaToroidalDatafile', major_radius=0.5, minor_radius=0.05,
+                  torus_origin=[-0.5, 0.0, 0.0], bundle_count=30, time_resolution=4e-5,
+                  temperature_file=os.path.join(PROFILES, 'temperature.txt'),
+                  emissivity_file=os.path.join(PROFILES, 'emissivity.txt'), linewidth=1e14)
+    return assemble(src, {'crystal': crystal_G(radius=1.0, rocking_fwhm=2000e-6), 'detector': detector_G()}, seed)
+
+
+def plasma_cone(angular_dist, seed):
+    """Per-bundle sources with a non-isotropic emission cone (scalar spread per bundle)."""
+    src = _plasma('XicsrtPlasmaCubic', angular_dist=angular_dist, spread_radius=0.09, spread=None, bundle_count=30,
+                  emissivity=2e11)
+    return assemble(src, {'crystal': crystal_G(radius=1.0, rocking_fwhm=2000e-6), 'detector': detector_G()}, seed)
+
+
 def _mesh_optic(class_name, **kw):
     c = crystal_G(class_name, check_bragg=False, rocking_fwhm=2000e-6)
     c.update(kw)
@@ -124,6 +141,10 @@ EXTRA = {
     'plasma_cubic_poisson': plasma_cubic_poisson,
     'plasma_toroidal': plasma_toroidal,
     'plasma_datafile': plasma_datafile,
+    'plasma_voigt': plasma_voigt,
+    'plasma_flat': lambda: plasma_cone('flat', 26),
+    'plasma_flat_xy': lambda: plasma_cone('flat_xy', 27),
+    'plasma_isotropic_xy': lambda: plasma_cone('isotropic_xy', 28),
     'mesh_torus': mesh_torus,
     'mesh_torus_convex': lambda: mesh_torus(seed=37, convex=[True, False], mesh_size=(15, 15)),
     'mesh_sphere': mesh_sphere,

@@ -60,13 +60,14 @@ PROBE = r'''
 #define S(T) printf(#T " %zu\n", sizeof(T))
 #define O(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
 int main(void) {
-    S(XrtAperture); S(XrtMesh); S(XrtOpticDesc); S(XrtSightline); S(XrtBundle); S(XrtSourceDesc);
+    S(XrtAperture); S(XrtMesh); S(XrtOpticDesc); S(XrtSightline); S(XrtBundle); S(XrtSourceDesc); S(XrtPlasmaDesc);
     S(XrtSceneDesc); S(XrtOutputs); S(XrtHistory); S(XrtRaysIn); S(XrtInject); S(XrtSourceInject);
     O(XrtOpticDesc, origin); O(XrtOpticDesc, center); O(XrtOpticDesc, root_idx); O(XrtOpticDesc, two_d);
     O(XrtOpticDesc, n_aperture); O(XrtOpticDesc, apertures); O(XrtOpticDesc, mesh); O(XrtOpticDesc, npix);
     O(XrtOpticDesc, image_offset);
     O(XrtSourceDesc, axis_basis); O(XrtSourceDesc, cone_par); O(XrtSourceDesc, wave_par); O(XrtSourceDesc, n_table);
-    O(XrtSourceDesc, table_cdf); O(XrtSourceDesc, sightlines); O(XrtSourceDesc, n_bundles); O(XrtSourceDesc, voxel_size);
+    O(XrtSourceDesc, table_cdf); O(XrtSourceDesc, sightlines); O(XrtSourceDesc, n_bundles); O(XrtSourceDesc, voxel_size); O(XrtSourceDesc, bundle_x);
+    O(XrtPlasmaDesc, cone); O(XrtPlasmaDesc, origin); O(XrtPlasmaDesc, inject_u); O(XrtPlasmaDesc, sightlines);
     O(XrtSceneDesc, source); O(XrtSceneDesc, optics);
     O(XrtMesh, n_tri); O(XrtMesh, grid_nx); O(XrtMesh, grid_x0); O(XrtMesh, vgrid_items);
     O(XrtOutputs, found_capacity); O(XrtOutputs, lost_threshold);

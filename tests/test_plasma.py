@@ -41,7 +41,8 @@ def prepared(name):
     return xscene.prepare(cfg)
 
 
-@pytest.mark.parametrize('name', ['plasma_cubic', 'plasma_cubic_poisson', 'plasma_toroidal', 'plasma_datafile'])
+@pytest.mark.parametrize('name', ['plasma_cubic', 'plasma_cubic_poisson', 'plasma_toroidal', 'plasma_datafile',
+                                  'plasma_voigt', 'plasma_flat_xy'])
 def test_bundle_properties_match_oracle(name):
     _, sname, sparam, sfilters, optics = prepared(name)
     seed = scenes.get(name)['general']['random_seed']
@@ -260,3 +261,122 @@ def test_plasma_end_to_end_statistics(torch):
         z = (p_got - p_ref) / np.sqrt(p * (1 - p) * (1 / n_ref + 1 / n_got))
         assert abs(z) < 4.5, (elem, p_ref, p_got, z)
     assert got['total']['image']['detector'].sum() == got['total']['meta']['detector']['num_out']
+
+
+# ---------------------------------------------------------------------------
+# per-ray parity of the plasma sources: the oracle's bundle centres, ray counts and per-ray draws injected
+
+class LoggedRandom:
+    """Host-random interface that replays what the oracle's stream recorded for the bundle table."""
+
+    def __init__(self, stream):
+        self.centres = [v for s, _, v, _ in stream.log if s.startswith('plasma.center.')]
+        self.counts = np.array([int(v[0]) for s, _, v, _ in stream.log if s == 'plasma.count'], dtype=np.int64)
+        self.k = 0
+
+    def uniform(self, lo, hi, n):
+        u = self.centres[self.k]
+        self.k += 1
+        return lo + (hi - lo) * u
+
+    def poisson_array(self, lam):
+        assert len(lam) == len(self.counts)
+        return self.counts
+
+
+def _concat(stream, site):
+    parts = [v for s, _, v, _ in stream.log if s == site]
+    return np.concatenate(parts) if parts else None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['plasma_cubic', 'plasma_cubic_poisson', 'plasma_toroidal', 'plasma_datafile',
+                                  'plasma_voigt', 'plasma_flat', 'plasma_flat_xy'])
+def test_injected_plasma_rays_match_oracle_and_reference(torch, golden_dir, name):
+    """
+    Every ray of a plasma source -- voxel origin, focused cone of its bundle (isotropic / flat /
+    flat_xy), thermal or per-bundle Voigt wavelength, Doppler shift -- within 1e-9 of the oracle
+    and of the unmodified reference's stored rays, from the same draws.
+    """
+    import harness
+    from test_gpu_source import run_source
+    cfg = scenes.get(name)
+    single, stream, oscene = oracle.trace_recorded(cfg)
+    ref = single['history']['source']
+    n = len(ref['mask'])
+    _, sname, sparam, sfilters, optics = prepared(name)
+    bundles = plasma.build_bundles(sparam, sfilters, LoggedRandom(stream))
+    assert bundles['n_rays'] == n
+    desc, layout, keep = xscene.flatten(sname, sparam, sfilters, optics, bundles=bundles)
+    scene = xscene.DeviceScene(desc, layout)
+    origin = np.stack([_concat(stream, f'src.origin.{i}') for i in range(3)])
+    cone = np.stack([_concat(stream, 'src.cone.0'), _concat(stream, 'src.cone.1')])
+    wave = _concat(stream, 'src.wave')
+    assert origin.shape == (3, n) and cone.shape == (2, n) and wave.shape == (n,)
+    got = run_source(torch, scene, n, origin, cone, wave)
+    scene.close()
+    harness.assert_rays_close(got, ref, f'{name}/source', 1e-9)
+    gold = np.load(f'{golden_dir}/{name}.npz')
+    gref = {k: gold[f'iter/source/{k}'] for k in ('origin', 'direction', 'wavelength', 'mask')}
+    harness.assert_rays_close(got, gref, f'{name}/source (golden)', 1e-9)
+
+
+@pytest.mark.gpu
+def test_device_voigt_tables_match_scipy(torch):
+    """xrt_bundle_voigt_tables (device Faddeeva function) against the scipy-built tables of the host restatement."""
+    dev = torch.device('cuda', 0)
+    lam0, mass = 3.9492, 39.948
+    temps = np.array([0.3, 1.0, 25.0, 400.0, 1550.0, 9000.0, 1e5, 5.0])
+    counts = np.array([3, 1, 2, 9, 1, 1, 4, 0], dtype=np.int64)
+    for linewidth in (1e11, 1e13, 1e14, 3e15):
+        gamma = float(voigt.natural_gamma(linewidth, lam0))
+        sigma = voigt.doppler_sigma(temps, mass, lam0)
+        table = np.zeros((len(temps), 8))
+        table[:, 4] = sigma
+        t_table = torch.from_numpy(table).to(dev)
+        t_counts = torch.from_numpy(counts).to(dev)
+        x = torch.full((len(temps), plasma.N_TABLE), -1.0, dtype=torch.float64, device=dev)
+        cdf = torch.full((len(temps), plasma.N_TABLE), -1.0, dtype=torch.float64, device=dev)
+        L.check(L.load().xrt_bundle_voigt_tables(t_table.data_ptr(), t_counts.data_ptr(), len(temps), gamma,
+                                                 plasma.N_TABLE, x.data_ptr(), cdf.data_ptr(), None))
+        torch.cuda.synchronize()
+        x, cdf = x.cpu().numpy(), cdf.cpu().numpy()
+        for b in range(len(temps)):
+            if counts[b] == 0:
+                assert np.all(x[b] == -1.0) and np.all(cdf[b] == -1.0)       # rows of empty bundles are not built
+                continue
+            rx, rcdf = voigt.cdf_table(gamma, float(sigma[b]), gridsize=plasma.N_TABLE)
+            np.testing.assert_allclose(x[b], rx, rtol=1e-12, atol=1e-15 * np.max(np.abs(rx)))   # the centre edge is ~0
+            np.testing.assert_allclose(cdf[b], rcdf, rtol=1e-11)
+            np.testing.assert_allclose(np.diff(cdf[b]), np.diff(rcdf), rtol=1e-10, atol=4e-16)    # bin weights (diff of O(1) sums)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['plasma_voigt', 'plasma_isotropic_xy', 'plasma_flat'])
+def test_plasma_linewidth_and_cones_end_to_end(torch, name):
+    """raytrace(config) on the device path (device-built bundle and Voigt tables, Philox draws) vs the oracle."""
+    from scipy import stats
+    import xicsrt_b200
+    cfg = scenes.get(name)
+    # many bundles with a few rays each: the fraction of a bundle's rays that meets the Bragg condition depends
+    # strongly on where the bundle sits relative to the Rowland circle, and the two sides draw different bundles
+    cfg['sources']['source'].update({'bundle_count': 4000, 'use_poisson': True, 'max_rays': int(1e8)})
+    cfg['sources']['source']['time_resolution'] *= 10
+    cfg['general'].update({'keep_history': True, 'number_of_iter': 2, 'max_lost': 0})
+    ref = oracle.raytrace(copy.deepcopy(cfg))
+    cfg['general']['random_seed'] = 1234
+    got = xicsrt_b200.raytrace(cfg)
+    n_ref, n_got = ref['total']['meta']['source']['num_out'], got['total']['meta']['source']['num_out']
+    assert n_ref > 20000 and abs(n_ref - n_got) < 6 * np.sqrt(n_ref + n_got)
+    for elem in ('crystal', 'detector'):
+        p_ref = ref['total']['meta'][elem]['num_out'] / n_ref
+        p_got = got['total']['meta'][elem]['num_out'] / n_got
+        p = 0.5 * (p_ref + p_got)
+        z = (p_got - p_ref) / np.sqrt(p * (1 - p) * (1 / n_ref + 1 / n_got))
+        assert abs(z) < 4.5, (elem, p_ref, p_got, z)
+    # found rays: wavelength and direction distributions at the source
+    a, b = got['found']['history']['source'], ref['found']['history']['source']
+    assert len(a['wavelength']) > 200
+    assert stats.ks_2samp(a['wavelength'], b['wavelength']).pvalue > 1e-4
+    for ax in range(3):
+        assert stats.ks_2samp(a['direction'][:, ax], b['direction'][:, ax]).pvalue > 1e-4

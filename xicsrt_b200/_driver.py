@@ -136,6 +136,8 @@ class Tracer:
         self.n_rays = self.bundles.generate(self.seed, (1 << 32) + iteration)
         self.layout.n_rays = self.n_rays
         self.scene.set_bundles(self.bundles.table, self.bundles.end)
+        if self.bundles.voigt_x is not None:
+            self.scene.set_bundle_tables(self.bundles.voigt_x, self.bundles.voigt_cdf)
 
     def begin_iteration(self, iteration):
         """

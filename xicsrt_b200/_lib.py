@@ -86,7 +86,7 @@ PLASMA = {'plasma_generic': 0, 'plasma_cubic': 1, 'plasma_toroidal': 2, 'plasma_
 class XrtPlasmaDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('use_poisson', C.c_int32), ('use_spread_radius', C.c_int32),
                 ('n_sightlines', C.c_int32), ('n_profile_t', C.c_int32), ('n_profile_e', C.c_int32),
-                ('thermal_line', C.c_int32), ('pad0', C.c_int32),
+                ('thermal_line', C.c_int32), ('cone', C.c_int32),
                 ('origin', C.c_double * 3), ('orient', C.c_double * 9), ('size', C.c_double * 3),
                 ('target', C.c_double * 3), ('spread', C.c_double), ('spread_radius', C.c_double),
                 ('temperature', C.c_double), ('emissivity', C.c_double), ('velocity', C.c_double * 3),
@@ -109,7 +109,7 @@ class XrtSourceDesc(C.Structure):
                 ('table_cdf', _pd), ('table_x', _pd),
                 ('sightlines', XrtSightline * MAX_SIGHTLINES),
                 ('n_bundles', C.c_uint64), ('bundles', C.POINTER(XrtBundle)), ('bundle_end', _pu64),
-                ('voxel_size', C.c_double)]
+                ('voxel_size', C.c_double), ('bundle_x', _pd), ('bundle_cdf', _pd)]
 
 
 class XrtSceneDesc(C.Structure):
@@ -164,6 +164,8 @@ SYMBOLS = {
     'xrt_source_generate': (C.c_int, [_vp, _u64, _u64, _u64, _u64, C.POINTER(XrtHistory), _vp]),
     'xrt_bundles_generate': (C.c_int, [C.POINTER(XrtPlasmaDesc), _u64, _u64, _u64, _vp, _vp, _vp, _vp]),
     'xrt_scene_set_bundles': (C.c_int, [_vp, _vp, _vp, _u64]),
+    'xrt_bundle_voigt_tables': (C.c_int, [_vp, _vp, _u64, C.c_double, C.c_int32, _vp, _vp, _vp]),
+    'xrt_scene_set_bundle_tables': (C.c_int, [_vp, _vp, _vp, C.c_int32]),
     'xrt_fp64_burn': (C.c_int, [_u64, _vp, C.POINTER(C.c_double), _vp]),
     'xrt_launch_info': (C.c_int, [_vp, _pi32, _pi32, _pi32, _pi32]),
 }

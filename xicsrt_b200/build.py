@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libxrt.so')
 SOURCES = ['xrt.cu']
-HEADERS = ['xrt_math.cuh', 'xrt_trace.cuh', 'xrt_mesh.cuh', os.path.join('..', '..', 'include', 'xrt.h')]
+HEADERS = ['xrt_math.cuh', 'xrt_fastmath.cuh', 'xrt_trace.cuh', 'xrt_mesh.cuh', 'xrt_plasma.cuh', os.path.join('..', '..', 'include', 'xrt.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--shared', '-Xcompiler', '-fPIC']

@@ -600,18 +600,30 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
     if (src.wave < XRT_WAVE_CONST || src.wave > XRT_WAVE_TABLE) return fail(XRT_EINVAL, "source.wave = %d", src.wave);
     if (src.n_sightlines < 0 || src.n_sightlines > XRT_MAX_SIGHTLINES)
         return fail(XRT_EINVAL, "source.n_sightlines = %d", src.n_sightlines);
-    if (src.wave == XRT_WAVE_TABLE && (src.n_table < 2 || !src.table_cdf || !src.table_x))
+    if (src.wave == XRT_WAVE_TABLE && src.kind != XRT_SRC_BUNDLES && (src.n_table < 2 || !src.table_cdf || !src.table_x))
         return fail(XRT_EINVAL, "source wavelength table missing");
+    if (src.wave == XRT_WAVE_TABLE && src.kind == XRT_SRC_BUNDLES && src.n_table < 2)
+        return fail(XRT_EINVAL, "plasma source: n_table = %d", src.n_table);
     const bool host_bundles = src.kind == XRT_SRC_BUNDLES && src.bundles && src.bundle_end && src.n_bundles > 0;
     if (src.kind == XRT_SRC_BUNDLES && !host_bundles) {   // table supplied later by xrt_scene_set_bundles
         src.bundles = nullptr;
         src.bundle_end = nullptr;
         src.n_bundles = 0;
     }
+    const bool host_tables = host_bundles && src.wave == XRT_WAVE_TABLE && src.bundle_x && src.bundle_cdf;
+    if (src.kind != XRT_SRC_BUNDLES) { src.bundle_x = nullptr; src.bundle_cdf = nullptr; }
+    if (src.kind == XRT_SRC_BUNDLES && !host_tables) {    // supplied later by xrt_scene_set_bundle_tables
+        src.bundle_x = nullptr;
+        src.bundle_cdf = nullptr;
+    }
     {
         XrtSourceDesc &m = src;
-        UP(m.table_cdf, m.wave == XRT_WAVE_TABLE ? m.n_table : 0);
-        UP(m.table_x, m.wave == XRT_WAVE_TABLE ? m.n_table : 0);
+        const bool one_table = m.wave == XRT_WAVE_TABLE && m.kind != XRT_SRC_BUNDLES;
+        if (!one_table) { m.table_cdf = nullptr; m.table_x = nullptr; }
+        UP(m.table_cdf, one_table ? m.n_table : 0);
+        UP(m.table_x, one_table ? m.n_table : 0);
+        UP(m.bundle_x, host_tables ? m.n_bundles * (uint64_t)m.n_table : 0);
+        UP(m.bundle_cdf, host_tables ? m.n_bundles * (uint64_t)m.n_table : 0);
         UP(m.bundles, host_bundles ? m.n_bundles : 0);
         UP(m.bundle_end, host_bundles ? m.n_bundles : 0);
     }
@@ -781,6 +793,8 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     if (s->dev.n_optics < 1) return fail(XRT_EINVAL, "a scene needs at least one optic");
     if (s->dev.source.kind == XRT_SRC_BUNDLES && !s->dev.source.bundles)
         return fail(XRT_EINVAL, "plasma scene without a bundle table: call xrt_scene_set_bundles first");
+    if (s->dev.source.kind == XRT_SRC_BUNDLES && s->dev.source.wave == XRT_WAVE_TABLE && !s->dev.source.bundle_cdf)
+        return fail(XRT_EINVAL, "plasma scene with a natural linewidth: call xrt_scene_set_bundle_tables first");
     TraceKernel kern;
     size_t smem;
     int bps = 0;
@@ -806,6 +820,8 @@ static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const u
                          const XrtHistory &hist, void *stream) {
     if (MODE == REC_PHILOX && s->dev.source.kind == XRT_SRC_BUNDLES && !s->dev.source.bundles)
         return fail(XRT_EINVAL, "plasma scene without a bundle table: call xrt_scene_set_bundles first");
+    if (MODE == REC_PHILOX && s->dev.source.kind == XRT_SRC_BUNDLES && s->dev.source.wave == XRT_WAVE_TABLE && !s->dev.source.bundle_cdf)
+        return fail(XRT_EINVAL, "plasma scene with a natural linewidth: call xrt_scene_set_bundle_tables first");
     if (hist.rays || hist.mask) {
         if (hist.capacity < n) return fail(XRT_EINVAL, "history capacity %llu < %llu rays",
                                            (unsigned long long)hist.capacity, (unsigned long long)n);
@@ -870,6 +886,8 @@ static int launch_source(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     if (hist->capacity < n) return fail(XRT_EINVAL, "history capacity too small");
     if (MODE == REC_PHILOX && s->dev.source.kind == XRT_SRC_BUNDLES && !s->dev.source.bundles)
         return fail(XRT_EINVAL, "plasma scene without a bundle table: call xrt_scene_set_bundles first");
+    if (MODE == REC_PHILOX && s->dev.source.kind == XRT_SRC_BUNDLES && s->dev.source.wave == XRT_WAVE_TABLE && !s->dev.source.bundle_cdf)
+        return fail(XRT_EINVAL, "plasma scene with a natural linewidth: call xrt_scene_set_bundle_tables first");
     uint64_t want = (n + kBlock - 1) / kBlock;
     uint64_t cap = (uint64_t)s->sm_count * 8;
     int grid = (int)(want < cap ? want : cap);
@@ -881,7 +899,6 @@ static int launch_source(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
 extern "C" int xrt_source_injected(XrtScene *s, const XrtSourceInject *draws, uint64_t n, const XrtHistory *hist,
                                    void *stream) {
     if (!draws) return fail(XRT_EINVAL, "null argument");
-    if (s && s->dev.source.kind == XRT_SRC_BUNDLES) return fail(XRT_EUNSUPPORTED, "injected draws: box sources only");
     if (s && s->dev.source.cone == XRT_CONE_ISOTROPIC_XY)
         return fail(XRT_EUNSUPPORTED, "injected draws: isotropic_xy has a variable draw count");
     return launch_source<REC_INJECT>(s, 0, 0, 0, n, *draws, hist, stream);
@@ -900,6 +917,34 @@ extern "C" int xrt_scene_set_bundles(XrtScene *s, const XrtBundle *table_dev, co
     s->dev.source.bundles = table_dev;
     s->dev.source.bundle_end = end_dev;
     s->dev.source.n_bundles = n_bundles;
+    return XRT_OK;
+}
+
+extern "C" int xrt_scene_set_bundle_tables(XrtScene *s, const double *x_dev, const double *cdf_dev, int32_t n_table) {
+    if (!s) return fail(XRT_EINVAL, "null scene");
+    if (s->dev.source.kind != XRT_SRC_BUNDLES || s->dev.source.wave != XRT_WAVE_TABLE)
+        return fail(XRT_EINVAL, "the scene's source is not a plasma with a tabulated line shape");
+    if (!x_dev || !cdf_dev || n_table != s->dev.source.n_table) return fail(XRT_EINVAL, "bad bundle wavelength tables");
+    s->dev.source.bundle_x = x_dev;
+    s->dev.source.bundle_cdf = cdf_dev;
+    return XRT_OK;
+}
+
+extern "C" int xrt_bundle_voigt_tables(const XrtBundle *table_dev, const int64_t *counts_dev, uint64_t n_bundles,
+                                       double gamma, int32_t n_table, double *x_dev, double *cdf_dev, void *stream) {
+    if (!table_dev || !counts_dev || !x_dev || !cdf_dev) return fail(XRT_EINVAL, "null argument");
+    if (n_table < 2 || n_table > 8 * kVoigtBlock) return fail(XRT_EINVAL, "n_table = %d (2 .. %d)", n_table, 8 * kVoigtBlock);
+    if (!(gamma > 0.0)) return fail(XRT_EINVAL, "gamma must be > 0");
+    if (n_bundles == 0) return XRT_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(XRT_ECUDA, "no CUDA device: libxrt has no CPU path");
+    }
+    int grid = (int)(n_bundles < 148u * 8u ? n_bundles : 148u * 8u);
+    k_voigt_tables<<<grid, kVoigtBlock, 0, (cudaStream_t)stream>>>(table_dev, (const long long *)counts_dev, n_bundles, gamma,
+                                                                  n_table, x_dev, cdf_dev);
+    CU(cudaGetLastError());
     return XRT_OK;
 }
 

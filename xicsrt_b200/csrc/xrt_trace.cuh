@@ -193,6 +193,7 @@ struct SourceInjectedDraws {
 struct SrcLocal {
     V3 org, vel;
     double cos_spread, wave_sigma, ext0, ext1, ext2;
+    uint64_t bundle;      // plasma: index of the ray's bundle (row of the per-bundle wavelength tables)
 };
 
 template <uint32_t FT, uint32_t KN = 0>
@@ -201,6 +202,7 @@ __device__ __forceinline__ void source_local(const XrtSourceDesc &s, uint64_t in
     L.vel = v3(s.velocity_c);
     L.cos_spread = s.cone_par[0];
     L.wave_sigma = s.wave_par[1];
+    L.bundle = 0;
     if constexpr ((KN & KN_POINT_SOURCE) != 0) { L.ext0 = L.ext1 = L.ext2 = 0.0; }
     else { L.ext0 = s.extent[0]; L.ext1 = s.extent[1]; L.ext2 = s.extent[2]; }
     if constexpr ((FT & FT_SRC_EXT) != 0) {
@@ -212,6 +214,7 @@ __device__ __forceinline__ void source_local(const XrtSourceDesc &s, uint64_t in
                 if (__ldg(s.bundle_end + mid) > index) hi = mid; else lo = mid + 1;
             }
             const XrtBundle *b = s.bundles + lo;
+            L.bundle = lo;
             L.org = v3(__ldg(&b->origin[0]), __ldg(&b->origin[1]), __ldg(&b->origin[2]));
             L.cos_spread = __ldg(&b->cos_spread);
             L.wave_sigma = __ldg(&b->wave_sigma);
@@ -261,8 +264,13 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
         sincos_2pi(b, sn, cs);
         l = v3(rho * cs, rho * sn, z);
     } else if (cone == XRT_CONE_ISOTROPIC_XY) {
-        // rejection from the enclosing circular cone (:130-196)
-        const double cm = s.cone_cos_max;
+        // rejection from the enclosing circular cone (:130-196); a plasma bundle carries sin(spread)
+        // of its scalar spread: limits [-v, v, -v, v], enclosing cone asin(sqrt(2 v^2))
+        const bool per_bundle = s.kind == XRT_SRC_BUNDLES;
+        const double v = L.cos_spread;
+        const double cm = per_bundle ? sqrt(fma(-2.0 * v, v, 1.0)) : s.cone_cos_max;
+        const double x_lo = per_bundle ? -v : s.cone_par[0], x_hi = per_bundle ? v : s.cone_par[1];
+        const double y_lo = per_bundle ? -v : s.cone_par[2], y_hi = per_bundle ? v : s.cone_par[3];
         l = v3(0.0, 0.0, 1.0);
         for (int attempt = 0; attempt < 100000; ++attempt) {
             double a, b;
@@ -275,18 +283,23 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
             double sx = x / sqrt(x * x + z * z);
             double sy = y / sqrt(y * y + z * z);
             l = v3(x, y, z);
-            if (sx > s.cone_par[0] && sx <= s.cone_par[1] && sy > s.cone_par[2] && sy <= s.cone_par[3]) break;
+            if (sx > x_lo && sx <= x_hi && sy > y_lo && sy <= y_hi) break;
         }
     } else {
         double a, b, a0, s1, c1;
         dr.cone(0, a, b);
         if (cone == XRT_CONE_FLAT) {
-            double rr = sqrt(0.0 + (s.cone_par[0] - 0.0) * a);
+            // L.cos_spread holds tan(spread): cone_par[0] of the source, or the bundle's own
+            double rr = sqrt(0.0 + (L.cos_spread - 0.0) * a);
             sincos_2pi(b, s1, c1);
             a0 = atan(rr);
         } else {
-            double x = s.cone_par[0] + (s.cone_par[1] - s.cone_par[0]) * a;
-            double y = s.cone_par[2] + (s.cone_par[3] - s.cone_par[2]) * b;
+            const bool per_bundle = s.kind == XRT_SRC_BUNDLES;
+            const double v = L.cos_spread;
+            const double x_lo = per_bundle ? -v : s.cone_par[0], x_hi = per_bundle ? v : s.cone_par[1];
+            const double y_lo = per_bundle ? -v : s.cone_par[2], y_hi = per_bundle ? v : s.cone_par[3];
+            double x = x_lo + (x_hi - x_lo) * a;
+            double y = y_lo + (y_hi - y_lo) * b;
             a0 = atan(sqrt(x * x + y * y));
             sincos(atan2(y, x), &s1, &c1);
         }
@@ -335,6 +348,13 @@ __device__ __forceinline__ double generate_wavelength(const XrtSourceDesc &s, co
         w = s.wave_par[0];
     } else if (s.wave == XRT_WAVE_UNIFORM) {
         w = s.wave_par[0] + (s.wave_par[1] - s.wave_par[0]) * dr.wave_u();
+    } else if (s.kind == XRT_SRC_BUNDLES) {
+        // the bundle's own table (every per-bundle source of the reference builds one)
+        const double *cdf = s.bundle_cdf + L.bundle * (uint64_t)s.n_table;
+        const double *x = s.bundle_x + L.bundle * (uint64_t)s.n_table;
+        const double lo = __ldg(cdf), hi = __ldg(cdf + s.n_table - 1);
+        double y = lo + (hi - lo) * dr.wave_u();
+        w = interp_inside(y, cdf, x, s.n_table) + s.wave_par[0];
     } else {
         double y = s.wave_par[1] + (s.wave_par[2] - s.wave_par[1]) * dr.wave_u();
         w = interp_inside(y, s.table_cdf, s.table_x, s.n_table) + s.wave_par[0];

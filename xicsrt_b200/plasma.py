@@ -104,6 +104,52 @@ def bundle_intensity(param, b):
     return inten * (param['volume'] / (param['bundle_count'] * param['bundle_volume']))
 
 
+N_TABLE = 1000          # bins of the reference's Voigt table (xicsrt_voigt.py:47)
+
+
+def cone_kind(param):
+    """angular_dist of the per-bundle sources -> XRT_CONE_* (gaussian is a NameError in the reference)."""
+    name = 'isotropic' if param['angular_dist'] is None else str(param['angular_dist']).lower()
+    if name == 'gaussian':
+        raise NotImplementedError('angular_dist "gaussian" is not implemented in the reference.')
+    if name not in L.CONE:
+        raise Exception(f'Distribution "{name}" is not known.')
+    return name
+
+
+def cone_parameter(name, spread):
+    """What XrtBundle.cos_spread holds for a bundle's scalar spread (see include/xrt.h)."""
+    spread = np.asarray(spread, dtype=np.float64)
+    return {'isotropic': np.cos, 'isotropic_xy': np.sin, 'flat': np.tan, 'flat_xy': np.tan}[name](spread)
+
+
+def line_model(param):
+    """
+    'const' | 'uniform' | 'normal' | 'table' for the per-bundle sources: the branch order of
+    _XicsrtSourceGeneric.py:295-354 with a per-bundle temperature.  With a natural linewidth
+    every bundle samples its own tabulated Voigt profile.
+    """
+    wtype = str(param['wavelength_dist']).lower()
+    if wtype == 'monochrome':
+        return 'const'
+    if wtype == 'uniform':
+        return 'uniform'
+    if wtype != 'voigt':
+        raise Exception(f'Wavelength distribution {wtype} unknown')
+    return 'table' if float(param['linewidth']) != 0.0 else 'normal'
+
+
+def bundle_sigma(param, temperature):
+    """Doppler sigma per bundle; with a natural linewidth T == 0 becomes 1 eV (:333-339)."""
+    model = line_model(param)
+    temp = np.asarray(temperature, dtype=np.float64)
+    if model not in ('normal', 'table'):
+        return np.zeros(len(temp))
+    if model == 'table':
+        temp = np.where(temp == 0.0, 1.0, temp)
+    return np.where(temp > 0, voigt.doppler_sigma(np.abs(temp), param['mass_number'], float(param['wavelength'])), 0.0)
+
+
 def bundle_counts(param, b, rng):
     """Rays per bundle: Poisson draw or truncation, as each per-bundle source does at initialize."""
     m = b['mask']
@@ -128,10 +174,8 @@ def build_bundles(param, filters, rng):
     The device bundle table of one iteration.  Returns {'table', 'end', 'n_rays', 'props', 'counts'}.
     Bundles that emit no ray are left out of the table.
     """
-    if str(param['angular_dist']).lower() != 'isotropic':
-        raise NotImplementedError('plasma sources on the device support angular_dist="isotropic" only')
-    if float(param['linewidth']) != 0.0 and str(param['wavelength_dist']).lower() == 'voigt':
-        raise NotImplementedError('plasma sources with a natural linewidth need per-bundle Voigt tables')
+    cone = cone_kind(param)
+    model = line_model(param)
     if param['target'] is None:
         raise ValueError('plasma sources need a target')
     b = bundle_properties(param, filters, rng)
@@ -141,21 +185,24 @@ def build_bundles(param, filters, rng):
     if n == 0:
         raise ValueError('No rays generated. Check plasma input parameters')
 
-    lam0 = float(param['wavelength'])
-    temp = b['temperature'][keep]
-    sigma = np.where(temp > 0, voigt.doppler_sigma(np.abs(temp), param['mass_number'], lam0), 0.0)
-    if str(param['wavelength_dist']).lower() != 'voigt':
-        sigma = np.zeros(n)
+    sigma = bundle_sigma(param, b['temperature'][keep])
 
     rec = np.zeros(n, dtype=[('origin', 'f8', 3), ('cos_spread', 'f8'), ('wave_sigma', 'f8'), ('velocity_c', 'f8', 3)])
     rec['origin'] = b['origin'][keep]
-    rec['cos_spread'] = np.cos(b['spread'][keep])
+    rec['cos_spread'] = cone_parameter(cone, b['spread'][keep])
     rec['wave_sigma'] = sigma
     rec['velocity_c'] = b['velocity'][keep] / voigt.C_LIGHT
     assert rec.dtype.itemsize == C.sizeof(L.XrtBundle)
     table = np.ascontiguousarray(rec)
     end = np.cumsum(counts[keep]).astype(np.uint64)
-    return {'table': table, 'end': end, 'n_rays': int(end[-1]), 'props': b, 'counts': counts}
+    out = {'table': table, 'end': end, 'n_rays': int(end[-1]), 'props': b, 'counts': counts}
+    if model == 'table':
+        # one table per emitting bundle, as each per-bundle source builds (host restatement with scipy's wofz)
+        gamma = float(voigt.natural_gamma(float(param['linewidth']), float(param['wavelength'])))
+        tabs = [voigt.cdf_table(gamma, float(sg), gridsize=N_TABLE) for sg in sigma]
+        out['voigt_x'] = np.ascontiguousarray([t[0] for t in tabs], dtype=np.float64)
+        out['voigt_cdf'] = np.ascontiguousarray([t[1] for t in tabs], dtype=np.float64)
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -167,18 +214,15 @@ def plasma_desc(param, filters, profiles=None, inject_u=None):
     (t_rho, t_val, e_rho, e_val) for the datafile class; ``inject_u`` = optional device tensor
     [3, n] of centre uniforms (parity tests).
     """
-    if str(param['angular_dist']).lower() != 'isotropic':
-        raise NotImplementedError('plasma sources on the device support angular_dist="isotropic" only')
-    thermal = str(param['wavelength_dist']).lower() == 'voigt'
-    if thermal and float(param['linewidth']) != 0.0:
-        raise NotImplementedError('plasma sources with a natural linewidth need per-bundle Voigt tables')
+    model = line_model(param)
     if param['target'] is None:
         raise ValueError('plasma sources need a target')
     d = L.XrtPlasmaDesc()
     d.kind = L.PLASMA[param['_kind']]
     d.use_poisson = 1 if param['use_poisson'] else 0
     d.use_spread_radius = 1 if param['spread_radius'] is not None else 0
-    d.thermal_line = 1 if thermal else 0
+    d.thermal_line = {'normal': 1, 'table': 2}.get(model, 0)
+    d.cone = L.CONE[cone_kind(param)]
     for i in range(3):
         d.origin[i] = float(param['origin'][i])
         d.target[i] = float(param['target'][i])
@@ -245,6 +289,17 @@ class DeviceBundles:
         self.counts = torch.empty(self.n, dtype=torch.int64, device=device)
         self.end = None
         assert C.sizeof(L.XrtBundle) == 64
+        # natural linewidth: one Voigt inverse-CDF table per bundle, built on the device each iteration
+        self.voigt_x = self.voigt_cdf = None
+        if line_model(param) == 'table':
+            need = 2 * 8 * N_TABLE * self.n
+            free = torch.cuda.mem_get_info(device)[0]
+            if need > 0.8 * free:
+                raise MemoryError(f'per-bundle Voigt tables need {need / 2**30:.1f} GiB for {self.n} bundles '
+                                  f'({free / 2**30:.1f} GiB free): reduce bundle_count')
+            self.gamma = float(voigt.natural_gamma(float(param['linewidth']), float(param['wavelength'])))
+            self.voigt_x = torch.empty((self.n, N_TABLE), dtype=torch.float64, device=device)
+            self.voigt_cdf = torch.empty((self.n, N_TABLE), dtype=torch.float64, device=device)
 
     def generate(self, seed, stream_id, inject_u=None):
         """Build the table for (seed, stream_id); returns the total number of rays."""
@@ -255,6 +310,10 @@ class DeviceBundles:
             L.check(self.lib.xrt_bundles_generate(C.byref(desc), int(seed), int(stream_id), self.n,
                                                   self.table.data_ptr(), self.intensity.data_ptr(),
                                                   self.counts.data_ptr(), stream))
+            if self.voigt_x is not None:
+                L.check(self.lib.xrt_bundle_voigt_tables(self.table.data_ptr(), self.counts.data_ptr(), self.n,
+                                                         self.gamma, N_TABLE, self.voigt_x.data_ptr(),
+                                                         self.voigt_cdf.data_ptr(), stream))
         kept = self.intensity >= 0
         inten = torch.where(kept, self.intensity, torch.zeros_like(self.intensity))
         # one device->host read for the three numbers the host needs

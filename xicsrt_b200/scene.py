@@ -135,20 +135,28 @@ def fill_source(src, param, filters, keep, bundles=None):
     if kind.startswith('plasma'):
         src.kind = L.SRC_BUNDLES
         _set(src.target, param['target'])
-        _fill_cone(src, param['angular_dist'], 0.0)
-        if src.cone != L.CONE['isotropic']:
-            raise NotImplementedError('plasma sources on the device support angular_dist="isotropic" only')
-        wparam = dict(param)
-        wparam['temperature'] = 1.0   # per-bundle sigma comes from the bundle table
-        model = _fill_wavelength(src, wparam, keep)
-        if model['mode'] == 'table':
-            raise NotImplementedError('plasma sources with a natural linewidth (per-bundle Voigt tables)')
+        from . import plasma as xplasma
+        # per-bundle cone parameter (XrtBundle.cos_spread) and Doppler sigma come from the bundle table
+        src.cone = L.CONE[xplasma.cone_kind(param)]
+        line = xplasma.line_model(param)
+        if line == 'table':
+            # natural linewidth: every bundle samples its own table (xrt_bundle_voigt_tables)
+            src.wave = L.WAVE['table']
+            _set(src.wave_par, [float(param['wavelength'])])
+            src.n_table = xplasma.N_TABLE
+        else:
+            wparam = dict(param)
+            wparam['temperature'] = 1.0
+            _fill_wavelength(src, wparam, keep)
         src.voxel_size = float(param['voxel_size'])
         if bundles is not None:          # host-built table (tests); the driver builds it on the device
             src.n_bundles = len(bundles['end'])
             table = keep.obj(np.ascontiguousarray(bundles['table']))
             src.bundles = C.cast(table.ctypes.data, C.POINTER(L.XrtBundle))
             src.bundle_end = keep.arr(bundles['end'], np.uint64, C.c_uint64)
+            if line == 'table':
+                src.bundle_x = keep.f64(bundles['voigt_x'].ravel())
+                src.bundle_cdf = keep.f64(bundles['voigt_cdf'].ravel())
         _set(src.extent, [param['voxel_size']] * 3)
     else:
         if spatial == 'uniform':
@@ -378,6 +386,10 @@ class DeviceScene:
     def set_bundles(self, table, end):
         """Point a plasma scene at a device-resident bundle table (torch tensors, kept alive by the caller)."""
         L.check(self.lib.xrt_scene_set_bundles(self.handle, table.data_ptr(), end.data_ptr(), int(end.numel())))
+
+    def set_bundle_tables(self, x, cdf):
+        """Per-bundle wavelength tables [n_bundles, n_table] of a plasma with a natural linewidth."""
+        L.check(self.lib.xrt_scene_set_bundle_tables(self.handle, x.data_ptr(), cdf.data_ptr(), int(x.shape[1])))
 
     def launch_info(self):
         g, b, r, p = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
