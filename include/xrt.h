@@ -160,6 +160,12 @@ typedef struct XrtOpticDesc {
     int32_t npix[2];         /* pixel_xsize, pixel_ysize (when XRT_F_IMAGE)                      */
     double pixel_size;
     uint64_t image_offset;   /* element offset of this optic's image in XrtOutputs.images        */
+    /* Bragg pre-test of the fused kernel; filled in by xrt_scene_create (input values are ignored).
+       cull_t2 > 0 enables it: a ray with (sin theta_B - sin theta_i)^2 > cull_t2 (1 - min(sin)^2)
+       cannot pass the rocking curve (see bragg_cull in csrc/xrt_trace.cuh)                      */
+    double cull_t2;          /* (1.05 angle beyond which the rocking curve is 0 or < 2^-57 + 2e-6)^2 */
+    double cull_err;         /* bound on the error of the approximate sin theta_B                 */
+    double cull_inv_r;       /* 1 / radius (sphere: n = (center - X) / radius)                    */
 } XrtOpticDesc;
 
 typedef struct XrtSightline {    /* xicsrt/filters/_XicsrtBundleFilterSightline.py:31-56 */

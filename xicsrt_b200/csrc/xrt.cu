@@ -15,6 +15,7 @@
 //   k_burn          dependent DFMA chains: the FP64 roofline denominator.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -136,7 +137,7 @@ __device__ __forceinline__ void emit_lost(const XrtOutputs &out, const WarpCtx &
 // ---- stage C: the optics after the split optic, for the `cnt` rays in queue 2
 template <uint32_t FT>
 __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs &out, const WarpCtx &c, int split,
-                                        uint64_t seed, uint64_t stream_id, const double *q2, int first, int cnt) {
+                                        const PhiloxKeys &pk, uint64_t stream_id, const double *q2, int first, int cnt) {
     const bool active = (int)c.lane < cnt;
     Ray r;
     r.alive = false;
@@ -151,7 +152,7 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
         r.alive = true;
     }
     __syncwarp();
-    dr.init(seed, stream_id, id, split);
+    dr.init(pk, stream_id, id, split);
     const int nopt = sc.n_optics;
     for (int k = split + 1; k < nopt; ++k) {
         const XrtOpticDesc &op = sc.optics[k];
@@ -168,7 +169,7 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
 // ---- stage B: interaction of the split optic for `cnt` rays popped from queue 1
 template <uint32_t FT, uint32_t KN>
 __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
-                                        const WarpCtx &c, int split, bool lazy, uint64_t seed, uint64_t stream_id,
+                                        const WarpCtx &c, int split, bool lazy, const PhiloxKeys &pk, uint64_t stream_id,
                                         const double *q1, int first, int cnt, double *q2, int &n2, unsigned &n_split) {
     constexpr int P = kQ1Cap;
     const bool active = (int)c.lane < cnt;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     }
     __syncwarp();
     PhiloxDraws dr;
-    dr.init(seed, stream_id, id, split);
+    dr.init(pk, stream_id, id, split);
     if (active) {
         if (lazy) {
             SrcLocal L;
@@ -223,7 +224,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
 // mesh variants keep many more values live (face loops, Clough-Tocher cubics): 2 blocks / SM
 template <uint32_t FT, int SPLIT, uint32_t KN>
 __global__ void __launch_bounds__(kBlock, ((FT & FT_MESH) != 0 && XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS)
-k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
+k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
         const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const int split_rt,
         const int lazy_rt) {
     extern __shared__ double s_queue[];
@@ -272,13 +273,13 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         if (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
             const int cnt = n2 < 32 ? n2 : 32;
             n2 -= cnt;
-            stage_c<FT>(sc, out, c, split, seed, stream_id, q2, n2, cnt);
+            stage_c<FT>(sc, out, c, split, pk, stream_id, q2, n2, cnt);
             continue;
         }
         if (n1 >= 32 || (!more && n1 > 0)) {
             const int cnt = n1 < 32 ? n1 : 32;
             n1 -= cnt;
-            stage_b<FT, KN>(sc, ops, out, c, split, lazy, seed, stream_id, q1, n1, cnt, q2, n2, n_split);
+            stage_b<FT, KN>(sc, ops, out, c, split, lazy, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
             continue;
         }
         if (!more) break;
@@ -290,7 +291,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         const bool valid = c.lane < n_valid;
         base += n_warps * 32;
         PhiloxDraws dr;
-        dr.init(seed, stream_id, id, split);
+        dr.init(pk, stream_id, id, split);
         Ray r;
         r.alive = false;
         r.w = 0.0;
@@ -312,6 +313,11 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint
         V3 n = v3(0.0, 0.0, 1.0);
         bool cand = false;
         if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
+        // Bragg pre-test: most candidates miss the rocking curve by many widths and are lost here, before
+        // the queue, with a bound that needs no exact wavelength (rays that pass take the exact path)
+        if constexpr ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) {
+            if (cand && ops.cull_t2 > 0.0) cand = !bragg_cull(sc.source, ops, dr, r.o, r.d);
+        }
         emit_lost(out, c, dr, valid && !cand, id);
 
         const unsigned m = __ballot_sync(kFull, cand);
@@ -358,7 +364,7 @@ enum { REC_PHILOX = 0, REC_INJECT = 1 };
 // KN != 0: the scene has the known structure (split optic = optic 0), see k_trace
 template <uint32_t FT, int MODE, uint32_t KN = 0>
 __global__ void __launch_bounds__(kBlock)
-k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
+k_record(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
          const uint64_t *__restrict__ ids, const uint64_t ray_begin, const uint64_t n,
          const XrtRaysIn in, const XrtInject inj, const XrtOutputs out, const XrtHistory hist, const int split) {
     const int nopt = sc.n_optics;
@@ -369,7 +375,7 @@ k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uin
         InjectedDraws idr;
         if constexpr (MODE == REC_PHILOX) {
             const uint64_t id = ids ? ids[i] : ray_begin + i;
-            pdr.init(seed, stream_id, id, split);
+            pdr.init(pk, stream_id, id, split);
             generate_ray<FT, PhiloxDraws, KN>(sc.source, pdr, id, r);
         } else {
             r.o = v3(in.origin + 3 * i);
@@ -411,14 +417,14 @@ k_record(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uin
 
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)
-k_source(const __grid_constant__ XrtSceneDesc sc, const uint64_t seed, const uint64_t stream_id,
+k_source(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
          const uint64_t ray_begin, const uint64_t n, const XrtSourceInject sinj, const XrtHistory hist) {
     const uint64_t stride = (uint64_t)gridDim.x * kBlock;
     for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
         Ray r;
         if constexpr (MODE == REC_PHILOX) {
             PhiloxDraws dr;
-            dr.init(seed, stream_id, ray_begin + i, -1);
+            dr.init(pk, stream_id, ray_begin + i, -1);
             generate_ray<FT_FULL>(sc.source, dr, ray_begin + i, r);
         } else {
             SourceInjectedDraws dr;
@@ -665,6 +671,7 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
             m.mesh = nullptr;
         }
     }
+    for (int k = 0; k < d.n_optics; ++k) d.optics[k].cull_t2 = d.optics[k].cull_err = d.optics[k].cull_inv_r = 0.0;
     s->features = scene_features(d);
     s->split = 0;
     for (int k = 0; k < d.n_optics; ++k) {
@@ -689,6 +696,16 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         if (o.interact == XRT_INTERACT_CRYSTAL && (o.flags & XRT_F_CHECK_BRAGG) && o.rocking_type == XRT_ROCK_GAUSS)
             s->known |= KN_CRYSTAL_GAUSS;
         if (o.flags & XRT_F_IMAGE) s->known |= KN_IMAGE;
+        // parameters of the Bragg pre-test (bragg_cull) for the spectrometer variant
+        if ((s->known & KN_SPECTROMETER) == KN_SPECTROMETER && s->split == 0 && s->lazy_wavelength && s->features == 0 &&
+            o.rock_inv_two_sigma2 > 0.0 && std::isfinite(o.rock_inv_two_sigma2) && o.radius > 0.0 &&
+            std::isfinite(o.inv_two_d) && std::getenv("XRT_NO_CULL") == nullptr) {
+            XrtOpticDesc &w = d.optics[s->split];
+            const double t = 1.05 * std::sqrt(40.0 / o.rock_inv_two_sigma2) + 2e-6;
+            w.cull_t2 = t * t;
+            w.cull_err = 2e-3 * std::fabs(src.wave_par[1]) * std::fabs(o.inv_two_d) + 1e-9;
+            w.cull_inv_r = 1.0 / o.radius;
+        }
     }
     return XRT_OK;
 }
@@ -726,7 +743,7 @@ extern "C" int xrt_scene_create(const XrtSceneDesc *desc, XrtScene **scene) {
 
 // ---- launch helpers -------------------------------------------------------
 
-typedef void (*TraceKernel)(const XrtSceneDesc, const uint64_t, const uint64_t, const uint64_t, const uint64_t,
+typedef void (*TraceKernel)(const XrtSceneDesc, const PhiloxKeys, const uint64_t, const uint64_t, const uint64_t,
                             const XrtOutputs, const int, const int);
 
 template <uint32_t FT>
@@ -808,7 +825,9 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     uint64_t want = (ray_count + kBlock - 1) / kBlock;
     uint64_t cap = (uint64_t)s->sm_count * (uint64_t)bps;
     int grid = (int)(want < cap ? want : cap);
-    kern<<<grid, kBlock, smem, (cudaStream_t)stream>>>(s->dev, seed, stream_id, ray_begin, ray_count, *out, s->split,
+    PhiloxKeys pk;
+    philox_round_keys(seed, stream_id, pk);
+    kern<<<grid, kBlock, smem, (cudaStream_t)stream>>>(s->dev, pk, stream_id, ray_begin, ray_count, *out, s->split,
                                                       s->lazy_wavelength);
     CU(cudaGetLastError());
     return XRT_OK;
@@ -830,17 +849,19 @@ static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const u
     uint64_t cap = (uint64_t)s->sm_count * 8;
     int grid = (int)(want < cap ? want : cap);
     cudaStream_t st = (cudaStream_t)stream;
+    PhiloxKeys pk;
+    philox_round_keys(seed, stream_id, pk);
     if (s->features == 0 && MODE == REC_PHILOX && s->split == 0 && (s->known & KN_SPECTROMETER) == KN_SPECTROMETER)
         k_record<0, MODE, (MODE == REC_PHILOX ? (uint32_t)KN_SPECTROMETER : 0u)><<<grid, kBlock, 0, st>>>(
-            s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+            s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == 0)
-        k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+        k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == FT_MID)
-        k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+        k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == FT_MESHLEAN)
-        k_record<FT_MESHLEAN, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+        k_record<FT_MESHLEAN, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else
-        k_record<FT_FULL, MODE><<<grid, kBlock, 0, st>>>(s->dev, seed, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+        k_record<FT_FULL, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     CU(cudaGetLastError());
     return XRT_OK;
 }
@@ -891,7 +912,9 @@ static int launch_source(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     uint64_t want = (n + kBlock - 1) / kBlock;
     uint64_t cap = (uint64_t)s->sm_count * 8;
     int grid = (int)(want < cap ? want : cap);
-    k_source<MODE><<<grid, kBlock, 0, (cudaStream_t)stream>>>(s->dev, seed, stream_id, ray_begin, n, sinj, *hist);
+    PhiloxKeys pk;
+    philox_round_keys(seed, stream_id, pk);
+    k_source<MODE><<<grid, kBlock, 0, (cudaStream_t)stream>>>(s->dev, pk, stream_id, ray_begin, n, sinj, *hist);
     CU(cudaGetLastError());
     return XRT_OK;
 }

@@ -75,6 +75,32 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// The same generator with the ten round keys (k + r W) precomputed on the host: the key is the
+// same for every ray of a launch, so the kernels take the schedule as a __grid_constant__
+// parameter and the XORs read it straight from the constant bank (18 integer adds per block less).
+struct PhiloxKeys { uint32_t rk[20]; };
+
+__host__ __device__ inline void philox_round_keys(uint64_t seed, uint64_t stream_id, PhiloxKeys &K) {
+    uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.rk[2 * r] = kx;
+        K.rk[2 * r + 1] = ky;
+        kx += 0x9E3779B9u;
+        ky += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &K) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ K.rk[2 * r], lo1, hi0 ^ c.w ^ K.rk[2 * r + 1], lo0);
+    }
+    return c;
+}
+
 // Uniform in [0, 1) from two 32-bit words: the 52 mantissa bits of a double in [1, 2) are
 // filled with random bits and 1 is subtracted (two integer ops and one DADD; the
 // int -> double conversions of the textbook construction run on the quarter-rate XU pipe).

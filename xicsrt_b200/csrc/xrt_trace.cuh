@@ -79,19 +79,19 @@ enum : uint32_t { SITE_ORIGIN_XY = 0, SITE_ORIGIN_Z = 1, SITE_CONE = 2, SITE_WAV
                   SITE_LOSTKEY = 4, SITE_CONE_RETRY = 0x100 };
 
 struct PhiloxDraws {
-    uint2 key;
+    const PhiloxKeys *keys;   // round keys of (seed, stream_id): a __grid_constant__ kernel parameter
     uint32_t ray_lo, ray_hi, stream;
     int k_shared;     // the crystal whose first rocking-curve uniform shares the wavelength's Philox block
 
-    __device__ __forceinline__ void init(uint64_t seed, uint64_t stream_id, uint64_t ray, int shared_optic) {
-        key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
+    __device__ __forceinline__ void init(const PhiloxKeys &K, uint64_t stream_id, uint64_t ray, int shared_optic) {
+        keys = &K;
         stream = (uint32_t)stream_id;
         ray_lo = (uint32_t)ray;
         ray_hi = (uint32_t)(ray >> 32);
         k_shared = shared_optic;
     }
     __device__ __forceinline__ uint4 raw(uint32_t site) const {
-        return philox4x32_10(make_uint4(ray_lo, ray_hi, site, stream), key);
+        return philox4x32_10(make_uint4(ray_lo, ray_hi, site, stream), *keys);
     }
     __device__ __forceinline__ void pair(uint32_t site, double &a, double &b) const {
         uint4 r = raw(site);
@@ -547,6 +547,41 @@ __device__ __forceinline__ double bragg_dtheta(const XrtOpticDesc &op, V3 d, dou
     double c = fabs(dot(d, n)) * fast_rsqrt(dot(d, d));
     double x = c * fast_sqrt(fma(-s, s, 1.0)) - s * fast_sqrt(fma(-c, c, 1.0));
     return (fabs(x) < 0.05) ? asin_small(x) : asin(x);      // NaN (lambda > 2d) goes to asin -> NaN
+}
+
+// Conservative pre-test of the Bragg condition for the fused kernel (history-off path).
+//
+// In a spectrometer ~98 % of the rays that reach the crystal fail the rocking-curve test, most
+// of them by many widths.  theta_B - theta_i is bounded from below without any inverse
+// trigonometry: with sB = lambda / 2d = sin(theta_B) and sI = |D.n| = sin(theta_i), both
+// angles in [0, pi/2],  |sB - sI| <= |theta_B - theta_i| cos(min(theta_B, theta_i)).  So
+//     (sB - sI)^2 > T^2 (1 - min(sB, sI)^2)   ==>   |theta_B - theta_i| > T,
+// and with T a little beyond the angle where the rocking curve is zero (step) or below 2^-57
+// (Gaussian, x >= 40: bragg_pass returns false there) the ray is lost whatever its uniform is.
+// The wavelength of the test is approximate -- the same Philox words as the exact one, but the
+// normal deviate in FP32 with the MUFU units (|z32 - z| < 1e-3: truncated 24-bit radius
+// uniform guarded at 1 - u >= 2^-10, lg2.approx / sqrt.approx / cos.approx errors ~1e-6) --
+// and op.cull_err = 2e-3 sigma_lambda / 2d + 1e-9 covers that and the rounding of the exact
+// path many times over; T carries a 5 % + 2e-6 rad margin.  Rays that pass the pre-test take
+// the exact FP64 path; rays that fail it would have failed there too (checked ray for ray against
+// the replay kernel in tests/test_gpu_statistics.py).  Sphere crystals, |D| = 1.
+__device__ __forceinline__ float normal_approx(uint4 r, bool &usable) {
+    const float v = 1.0f - (float)(r.x >> 8) * 5.9604644775390625e-8f;      // 1 - u1 to 2^-24, exact in FP32
+    usable = v >= 9.765625e-4f;                                             // 2^-10: |z| < 3.73
+    const float rad = __fsqrt_rn(-1.3862943611198906f * __log2f(v));        // sqrt(-2 ln v)
+    const float t = (float)(r.y & 0xffffffu) * 5.9604644775390625e-8f - 0.5f;   // angle uniform - 1/2, exact
+    return -rad * __cosf(6.283185307179586f * t);                           // cos(2 pi u) = -cos(2 pi (u - 1/2))
+}
+
+__device__ __forceinline__ bool bragg_cull(const XrtSourceDesc &s, const XrtOpticDesc &op, const PhiloxDraws &dr,
+                                           V3 X, V3 d) {
+    bool usable;
+    const float z = normal_approx(dr.raw(SITE_WAVE), usable);
+    const double sB = fma((double)z, s.wave_par[1], s.wave_par[0]) * op.inv_two_d;
+    const double sI = fabs(dot(d, v3(op.center) - X)) * op.cull_inv_r;
+    const double diff = fabs(sB - sI) - op.cull_err;
+    const double m = fmax(fmin(sB, sI) - op.cull_err, 0.0);
+    return usable && diff > 0.0 && diff * diff > op.cull_t2 * fma(-m, m, 1.0);
 }
 
 // true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).
