@@ -68,3 +68,35 @@ def test_device_math_against_long_double(tmp_path):
     assert es < 4e-16 and ec < 4e-16 and ec2 < 4e-16, (es, ec, ec2)     # absolute, |value| <= 1
     assert el < 4e-16 and ee < 4e-16 and ea < 4e-16, (el, ee, ea)       # relative
     assert [float(v) for v in out[6:]] == [0.0, 1.0, 0.0, 1.0, 0.0, 1.0]
+
+
+def test_pretest_normal_deviate_coefficients_against_scipy():
+    """
+    normal_approx (csrc/xrt_trace.cuh): the FP32 inverse-normal-CDF of the Bragg pre-test.  The
+    constants are read from the source and the same arithmetic is done in numpy float32; its
+    error against scipy must stay far inside the 2e-3 the pre-test's margin (cull_err) allows.
+    """
+    import re
+    import numpy as np
+    from scipy.stats import norm
+    text = open(os.path.join(ROOT, 'xicsrt_b200', 'csrc', 'xrt_trace.cuh')).read()
+    body = text[text.index('float normal_approx('):]
+    body = body[:body.index('\n}\n')]
+    lead = float(re.search(r'float p = ([-0-9.e+]+)f;', body).group(1))
+    coef = [float(c) for c in re.findall(r'p = fmaf\(p, w, ([-0-9.e+]+)f\);', body)]
+    assert len(coef) == 8 and 'w < 5.0f' in body
+    f32 = np.float32
+    hi = np.random.default_rng(3).integers(0, 2**32, 2000000, dtype=np.uint64)
+    k = (hi >> np.uint64(8)).astype(f32)
+    x = (k * f32(2.0**-23) + f32(2.0**-24 - 1.0)).astype(f32)
+    w = (f32(-0.6931471805599453) * np.log2((f32(1) - x * x).astype(f32)).astype(f32)).astype(f32)
+    usable = w < f32(5)
+    w = (w - f32(2.5)).astype(f32)
+    p = np.full_like(w, f32(lead))
+    for c in coef:
+        p = (p * w + f32(c)).astype(f32)
+    z = (f32(1.4142135623730951) * p * x).astype(f32)
+    u = (hi.astype(np.float64) + 0.5) * 2.0**-32          # any uniform whose top 32 bits are `hi`
+    err = np.abs(z.astype(np.float64) - norm.ppf(u))[usable]
+    assert usable.mean() > 0.99 and np.abs(z[usable]).max() < 2.95
+    assert err.max() < 2e-5, err.max()

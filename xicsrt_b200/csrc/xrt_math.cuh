@@ -107,6 +107,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &K) {
 __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
     return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)((a << 20) | (b >> 12))) - 1.0;
 }
+// 44 random bits: the low 12 bits of a and all of b
+__device__ __forceinline__ double u01_44(uint32_t a, uint32_t b) {
+    return __hiloint2double((int)(0x3ff00000u | ((a & 0xfffu) << 8) | (b >> 24)), (int)(b << 8)) - 1.0;
+}
 // the same with 40 random bits (a: 32, top 8 of b) and with the low 24 bits of b
 __device__ __forceinline__ double u01_40(uint32_t a, uint32_t b) {
     return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)((a << 20) | ((b >> 24) << 12))) - 1.0;

@@ -82,9 +82,11 @@ struct PhiloxDraws {
     const PhiloxKeys *keys;   // round keys of (seed, stream_id): a __grid_constant__ kernel parameter
     uint32_t ray_lo, ray_hi, stream;
     int k_shared;     // the crystal whose first rocking-curve uniform shares the wavelength's Philox block
+    mutable uint32_t spare;   // word w of the cone block (valid after cone(0, ..)): top 32 bits of the wavelength uniform
 
     __device__ __forceinline__ void init(const PhiloxKeys &K, uint64_t stream_id, uint64_t ray, int shared_optic) {
         keys = &K;
+        spare = 0;
         stream = (uint32_t)stream_id;
         ray_lo = (uint32_t)ray;
         ray_hi = (uint32_t)(ray >> 32);
@@ -112,20 +114,29 @@ struct PhiloxDraws {
         box_muller(c, d, z2, z3);
         off[0] = sig[0] * z0; off[1] = sig[1] * z1; off[2] = sig[2] * z2;
     }
+    // Cone block: words x, y(top 20 bits) -> first uniform (52 bits); y(low 12 bits), z -> second uniform
+    // (44 bits: 3.6e-13 rad of azimuth).  Word w of the attempt-0 block is left for the wavelength.
     __device__ __forceinline__ void cone(int attempt, double &a, double &b) const {
-        pair(attempt == 0 ? SITE_CONE : SITE_CONE_RETRY + (uint32_t)attempt, a, b);
+        uint4 r = raw(attempt == 0 ? SITE_CONE : SITE_CONE_RETRY + (uint32_t)attempt);
+        a = u01(r.x, r.y);
+        b = u01_44(r.y, r.z);
+        if (attempt == 0) spare = r.w;
     }
-    // One Philox block per ray serves the wavelength and the rocking-curve test of the first
-    // crystal: words x, y -> wavelength (a 53-bit uniform, or a normal from a 40-bit radius
-    // uniform -- tail cut at 7.4 sigma, probability 1.4e-13 -- and a 24-bit angle), words
-    // z, w -> the 53-bit uniform of (optic k_shared, layer 0).  The block is a pure function of
-    // (key, ray, site), so the two users below share one evaluation after inlining.
+    // Wavelength.  A normal deviate is the inverse normal CDF of ONE 53-bit uniform whose top 32
+    // bits are word w of the cone block and whose low 21 bits are word x of the SITE_WAVE block,
+    // taken at the centre of its 2^-53 bin (never 0 or 1; |z| < 8.3).  The fused kernel's Bragg
+    // pre-test needs the deviate only roughly and gets it from the cone block alone -- no second
+    // Philox block for the rays it rejects.  Words z, w of the SITE_WAVE block -> the 52-bit
+    // rocking-curve uniform of (optic k_shared, layer 0); the block is a pure function of
+    // (key, ray, site), so its users share one evaluation after inlining.
     __device__ __forceinline__ double wave_u() const { uint4 r = raw(SITE_WAVE); return u01(r.x, r.y); }
     __device__ __forceinline__ double wave_z() const {
-        uint4 r = raw(SITE_WAVE);
-        double rad = fast_sqrt(-2.0 * log_pos(1.0 - u01_40(r.x, r.y)));
-        return rad * cos_2pi(u01_24(r.y));
+        const uint32_t hi = raw(SITE_CONE).w;
+        const uint32_t lo = raw(SITE_WAVE).x;
+        return normcdfinv(u01(hi, lo) + 1.1102230246251565e-16);
     }
+    // top 32 bits of that uniform, for approximate deviates (valid after cone(0, ..) on this object)
+    __device__ __forceinline__ uint32_t wave_hi() const { return spare; }
     __device__ __forceinline__ uint64_t lost_key() const {
         uint4 r = raw(SITE_LOSTKEY);
         return ((uint64_t)r.x << 32) | r.y;
@@ -558,30 +569,52 @@ __device__ __forceinline__ double bragg_dtheta(const XrtOpticDesc &op, V3 d, dou
 //     (sB - sI)^2 > T^2 (1 - min(sB, sI)^2)   ==>   |theta_B - theta_i| > T,
 // and with T a little beyond the angle where the rocking curve is zero (step) or below 2^-57
 // (Gaussian, x >= 40: bragg_pass returns false there) the ray is lost whatever its uniform is.
-// The wavelength of the test is approximate -- the same Philox words as the exact one, but the
-// normal deviate in FP32 with the MUFU units (|z32 - z| < 1e-3: truncated 24-bit radius
-// uniform guarded at 1 - u >= 2^-10, lg2.approx / sqrt.approx / cos.approx errors ~1e-6) --
+// The wavelength of the test is approximate -- the normal deviate of the exact path evaluated
+// in FP32 from the top bits of the same uniform (|z32 - z| < 1e-5, normal_approx below) --
 // and op.cull_err = 2e-3 sigma_lambda / 2d + 1e-9 covers that and the rounding of the exact
 // path many times over; T carries a 5 % + 2e-6 rad margin.  Rays that pass the pre-test take
 // the exact FP64 path; rays that fail it would have failed there too (checked ray for ray against
 // the replay kernel in tests/test_gpu_statistics.py).  Sphere crystals, |D| = 1.
-__device__ __forceinline__ float normal_approx(uint4 r, bool &usable) {
-    const float v = 1.0f - (float)(r.x >> 8) * 5.9604644775390625e-8f;      // 1 - u1 to 2^-24, exact in FP32
-    usable = v >= 9.765625e-4f;                                             // 2^-10: |z| < 3.73
-    const float rad = __fsqrt_rn(-1.3862943611198906f * __log2f(v));        // sqrt(-2 ln v)
-    const float t = (float)(r.y & 0xffffffu) * 5.9604644775390625e-8f - 0.5f;   // angle uniform - 1/2, exact
-    return -rad * __cosf(6.283185307179586f * t);                           // cos(2 pi u) = -cos(2 pi (u - 1/2))
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
+// Standard normal deviate of wave_z() from the top 32 bits of its uniform, in FP32:
+// z = sqrt(2) erfinv(2u - 1) with the central branch of Giles' single-precision erfinv
+// (w = -ln(1 - x^2) < 5, i.e. |z| < 2.93; relative error 2.5e-7, checked against scipy in
+// tests/test_fastmath.py).  u is known to 2^-25 here, so |z32 - z| < 2^-25 / pdf(2.93) + 1e-6 = 7e-6.
+__device__ __forceinline__ float normal_approx(uint32_t hi, bool &usable) {
+    // x = 2 ((hi >> 8) 2^-24 + 2^-25) - 1, exact in FP32
+    const float x = fmaf((float)(hi >> 8), 1.1920928955078125e-7f, 5.9604644775390625e-8f - 1.0f);
+    float w = -0.6931471805599453f * lg2_approx(fmaf(-x, x, 1.0f));
+    usable = w < 5.0f;
+    w -= 2.5f;
+    float p = 2.81022636e-08f;
+    p = fmaf(p, w, 3.43273939e-07f);
+    p = fmaf(p, w, -3.5233877e-06f);
+    p = fmaf(p, w, -4.39150654e-06f);
+    p = fmaf(p, w, 0.00021858087f);
+    p = fmaf(p, w, -0.00125372503f);
+    p = fmaf(p, w, -0.00417768164f);
+    p = fmaf(p, w, 0.246640727f);
+    p = fmaf(p, w, 1.50140941f);
+    return 1.4142135623730951f * p * x;
+}
+
+// cos^2(min(theta_B, theta_i)) <= (1 - sI^2) + 2 |sB - sI|  (equality to first order when sB < sI), which
+// avoids the FP64 min / max selects.
 __device__ __forceinline__ bool bragg_cull(const XrtSourceDesc &s, const XrtOpticDesc &op, const PhiloxDraws &dr,
                                            V3 X, V3 d) {
     bool usable;
-    const float z = normal_approx(dr.raw(SITE_WAVE), usable);
+    const float z = normal_approx(dr.wave_hi(), usable);
     const double sB = fma((double)z, s.wave_par[1], s.wave_par[0]) * op.inv_two_d;
     const double sI = fabs(dot(d, v3(op.center) - X)) * op.cull_inv_r;
-    const double diff = fabs(sB - sI) - op.cull_err;
-    const double m = fmax(fmin(sB, sI) - op.cull_err, 0.0);
-    return usable && diff > 0.0 && diff * diff > op.cull_t2 * fma(-m, m, 1.0);
+    const double gap = fabs(sB - sI);
+    const double diff = gap - op.cull_err;
+    const double c2 = fma(2.0, gap, fma(-sI, sI, 1.0));
+    return usable & (diff > 0.0) & (diff * diff > op.cull_t2 * c2);
 }
 
 // true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).
