@@ -178,18 +178,34 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     r.w = 0.0;
     V3 n = v3(0.0, 0.0, 1.0);
     uint64_t id = 0;
+    constexpr bool SPECTRO = (KN & KN_SPECTROMETER) == KN_SPECTROMETER;
+    bool inside = active;
     if (active) {
         const double *p = q1 + first + c.lane;
         id = (uint64_t)__double_as_longlong(p[0]);
-        r.o = v3(p[1 * P], p[2 * P], p[3 * P]);
-        r.d = v3(p[4 * P], p[5 * P], p[6 * P]);
-        if constexpr (FT != 0) r.w = p[7 * P];
-        if constexpr ((FT & FT_MESH) != 0) n = v3(p[8 * P], p[9 * P], p[10 * P]);
+        if constexpr (SPECTRO) {
+            // queue 1 of the spectrometer variant holds (id, direction, distance): the intersection point
+            // and the bounds test (_TraceObject.py:180-232) are done here, on the ~18 % of the rays that
+            // passed the Bragg pre-test, with the arithmetic of optic_geometry
+            const V3 d = v3(p[1 * P], p[2 * P], p[3 * P]);
+            const double t = p[4 * P];
+            const V3 o = v3(sc.source.origin);
+            const V3 X = v3(fma(d.x, t, o.x), fma(d.y, t, o.y), fma(d.z, t, o.z));
+            const V3 Xl = to_local(ops.orient, X - v3(ops.origin));
+            inside = (fabs(Xl.x) < ops.half_size[0]) && (fabs(Xl.y) < ops.half_size[1]);
+            r.o = X;
+            r.d = d;
+        } else {
+            r.o = v3(p[1 * P], p[2 * P], p[3 * P]);
+            r.d = v3(p[4 * P], p[5 * P], p[6 * P]);
+            if constexpr (FT != 0) r.w = p[7 * P];
+            if constexpr ((FT & FT_MESH) != 0) n = v3(p[8 * P], p[9 * P], p[10 * P]);
+        }
     }
     __syncwarp();
     PhiloxDraws dr;
     dr.init(pk, stream_id, id, split);
-    if (active) {
+    if (inside) {
         if (lazy) {
             SrcLocal L;
             source_local<0, KN>(sc.source, id, L);
@@ -262,14 +278,23 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
     unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
 
-    const uint64_t n_warps = (uint64_t)gridDim.x * (kBlock / 32);
-    const uint64_t warp_global = (uint64_t)blockIdx.x * (kBlock / 32) + warp;
+    // Ray ids in groups of 32: group g = warp_global + it * n_warps belongs to this warp at iteration it.
+    // The loop carries 32-bit counters only; the 64-bit id is one multiply-add per iteration.
+    const uint32_t n_warps = gridDim.x * (kBlock / 32);
+    const uint32_t warp_global = blockIdx.x * (kBlock / 32) + warp;
+    const uint64_t n_groups = (ray_count + 31) >> 5;
+    const uint32_t n_it = warp_global < n_groups ? (uint32_t)((n_groups - warp_global + n_warps - 1) / n_warps) : 0u;
+    const uint32_t tail = (uint32_t)ray_count & 31u;         // valid lanes of the last group (0 = all)
+    const uint32_t tail_it = (tail != 0u && (n_groups - 1) % n_warps == warp_global) ? n_it - 1u : 0xffffffffu;
+    const uint64_t id0 = ray_begin + (uint64_t)warp_global * 32u + c.lane;
+    const uint32_t stride = n_warps * 32u;
+    constexpr bool SPECTRO = (KN & KN_SPECTROMETER) == KN_SPECTROMETER;
 
     // One loop, one copy of each stage: the deepest stage that has a full warp of work runs
     // first; when the ids are exhausted the queues are drained with partial warps.
-    uint64_t base = warp_global * 32;
+    uint32_t it = 0;
     for (;;) {
-        const bool more = base < ray_count;
+        const bool more = it < n_it;
         if (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
             const int cnt = n2 < 32 ? n2 : 32;
             n2 -= cnt;
@@ -284,53 +309,86 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
         }
         if (!more) break;
 
-        // ---- stage A (64-bit id arithmetic kept warp-uniform: one add per lane)
-        const uint64_t left = ray_count - base;
-        const unsigned n_valid = left < 32 ? (unsigned)left : 32u;
-        const uint64_t id = ray_begin + base + c.lane;
-        const bool valid = c.lane < n_valid;
-        base += n_warps * 32;
+        // ---- stage A
+        const uint64_t id = id0 + (uint64_t)it * stride;
+        const bool valid = (it != tail_it) || (c.lane < tail);
+        ++it;
         PhiloxDraws dr;
         dr.init(pk, stream_id, id, split);
-        Ray r;
-        r.alive = false;
-        r.w = 0.0;
-        if (valid) {
-            SrcLocal L;
-            source_local<FT, KN>(sc.source, id, L);
-            generate_geometry<FT, PhiloxDraws, KN>(sc.source, L, dr, r);
-            if (!lazy) r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
-        }
-        n_src += __popc(__ballot_sync(kFull, r.alive));
-        for (int k = 0; k < split; ++k) {
-            const XrtOpticDesc &op = sc.optics[k];
-            if (r.alive) {
-                trace_optic<FT>(op, k, dr, r);
-                if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
-            }
-            count_alive(c, k + 1, r.alive);
-        }
-        V3 n = v3(0.0, 0.0, 1.0);
-        bool cand = false;
-        if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
-        // Bragg pre-test: most candidates miss the rocking curve by many widths and are lost here, before
-        // the queue, with a bound that needs no exact wavelength (rays that pass take the exact path)
-        if constexpr ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) {
-            if (cand && ops.cull_t2 > 0.0) cand = !bragg_cull(sc.source, ops, dr, r.o, r.d);
-        }
-        emit_lost(out, c, dr, valid && !cand, id);
 
-        const unsigned m = __ballot_sync(kFull, cand);
-        if (cand) {
-            double *p = q1 + n1 + __popc(m & c.lt_mask);
-            p[0] = __longlong_as_double((long long)id);
-            p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
-            p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
-            if constexpr (FT != 0) p[7 * P] = r.w;
-            if constexpr ((FT & FT_MESH) != 0) { p[8 * P] = n.x; p[9 * P] = n.y; p[10 * P] = n.z; }
+        if constexpr (SPECTRO) {
+            // Straight-line code for the spectrometer (point source, concave sphere): direction, the two
+            // lengths of the sphere intersection and the Bragg pre-test; no branch, no intersection point.
+            // sin(theta_i) = |D.n| is thc / R for a ray of unit direction (D.(C - X) = tca - t = -thc), so the
+            // pre-test needs nothing else.  A ray it rejects is lost at the crystal whether or not it is inside
+            // the bounds, so the bounds test moves to stage B, behind the queue (18 % of the rays).
+            const XrtSourceDesc &src = sc.source;
+            double a, b;
+            dr.cone(0, a, b);
+            const double cs0 = src.cone_par[0];
+            const double z = cs0 + (1.0 - cs0) * a;
+            const double rho = fast_sqrt(fma(-z, z, 1.0));
+            double sn, cs;
+            sincos_2pi(b, sn, cs);
+            const double lx = rho * cs, ly = rho * sn;
+            const double *B = src.axis_basis;
+            const V3 d = v3(lx * B[0] + ly * B[3] + z * B[6], lx * B[1] + ly * B[4] + z * B[7], lx * B[2] + ly * B[5] + z * B[8]);
+            // hit_sphere, concave
+            const V3 Lc = v3(ops.center) - v3(src.origin);
+            const double tca = dot(Lc, d);
+            const double d2 = fma(-tca, tca, dot(Lc, Lc));
+            const double r2 = ops.radius * ops.radius;
+            const double thc = fast_sqrt(r2 - d2);          // NaN when d2 > r2
+            const double t = tca + thc;
+            bool cand = valid & (d2 >= 0.0) & (d2 <= r2);
+            if (ops.cull_t2 > 0.0) cand &= !bragg_cull_sphere(src, ops, dr.wave_hi(), thc);
+            n_src += __popc(__ballot_sync(kFull, valid));
+            emit_lost(out, c, dr, valid && !cand, id);
+            const unsigned m = __ballot_sync(kFull, cand);
+            if (cand) {
+                double *p = q1 + n1 + __popc(m & c.lt_mask);
+                p[0] = __longlong_as_double((long long)id);
+                p[1 * P] = d.x; p[2 * P] = d.y; p[3 * P] = d.z;
+                p[4 * P] = t;
+            }
+            n1 += __popc(m);
+            __syncwarp();
+        } else {
+            Ray r;
+            r.alive = false;
+            r.w = 0.0;
+            if (valid) {
+                SrcLocal L;
+                source_local<FT, KN>(sc.source, id, L);
+                generate_geometry<FT, PhiloxDraws, KN>(sc.source, L, dr, r);
+                if (!lazy) r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
+            }
+            n_src += __popc(__ballot_sync(kFull, r.alive));
+            for (int k = 0; k < split; ++k) {
+                const XrtOpticDesc &op = sc.optics[k];
+                if (r.alive) {
+                    trace_optic<FT>(op, k, dr, r);
+                    if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
+                }
+                count_alive(c, k + 1, r.alive);
+            }
+            V3 n = v3(0.0, 0.0, 1.0);
+            bool cand = false;
+            if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
+            emit_lost(out, c, dr, valid && !cand, id);
+
+            const unsigned m = __ballot_sync(kFull, cand);
+            if (cand) {
+                double *p = q1 + n1 + __popc(m & c.lt_mask);
+                p[0] = __longlong_as_double((long long)id);
+                p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
+                p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
+                if constexpr (FT != 0) p[7 * P] = r.w;
+                if constexpr ((FT & FT_MESH) != 0) { p[8 * P] = n.x; p[9 * P] = n.y; p[10 * P] = n.z; }
+            }
+            n1 += __popc(m);
+            __syncwarp();
         }
-        n1 += __popc(m);
-        __syncwarp();
     }
 
     if (c.lane == 0) {

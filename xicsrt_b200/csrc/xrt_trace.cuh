@@ -574,7 +574,8 @@ __device__ __forceinline__ double bragg_dtheta(const XrtOpticDesc &op, V3 d, dou
 // and op.cull_err = 2e-3 sigma_lambda / 2d + 1e-9 covers that and the rounding of the exact
 // path many times over; T carries a 5 % + 2e-6 rad margin.  Rays that pass the pre-test take
 // the exact FP64 path; rays that fail it would have failed there too (checked ray for ray against
-// the replay kernel in tests/test_gpu_statistics.py).  Sphere crystals, |D| = 1.
+// the replay kernel in tests/test_gpu_statistics.py).  Sphere crystals, |D| = 1.  The pre-test runs
+// before the bounds test: a ray it rejects is lost at this optic either way.
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -605,12 +606,12 @@ __device__ __forceinline__ float normal_approx(uint32_t hi, bool &usable) {
 
 // cos^2(min(theta_B, theta_i)) <= (1 - sI^2) + 2 |sB - sI|  (equality to first order when sB < sI), which
 // avoids the FP64 min / max selects.
-__device__ __forceinline__ bool bragg_cull(const XrtSourceDesc &s, const XrtOpticDesc &op, const PhiloxDraws &dr,
-                                           V3 X, V3 d) {
+// sphere: sI = |D.n| = thc / R, the half chord of hit_sphere over the radius (|D| = 1)
+__device__ __forceinline__ bool bragg_cull_sphere(const XrtSourceDesc &s, const XrtOpticDesc &op, uint32_t wave_hi, double thc) {
     bool usable;
-    const float z = normal_approx(dr.wave_hi(), usable);
+    const float z = normal_approx(wave_hi, usable);
     const double sB = fma((double)z, s.wave_par[1], s.wave_par[0]) * op.inv_two_d;
-    const double sI = fabs(dot(d, v3(op.center) - X)) * op.cull_inv_r;
+    const double sI = thc * op.cull_inv_r;
     const double gap = fabs(sB - sI);
     const double diff = gap - op.cull_err;
     const double c2 = fma(2.0, gap, fma(-sI, sI, 1.0));
