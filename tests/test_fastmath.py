@@ -22,7 +22,9 @@ int main() {
     std::mt19937_64 g(12345);
     std::uniform_real_distribution<double> U(0.0, 1.0);
     const long double PI = 3.141592653589793238462643383279502884L;
-    double es = 0, ec = 0, ec2 = 0, el = 0, ee = 0, ea = 0;
+    double es = 0, ec = 0, ec2 = 0, el = 0, ee = 0, ea = 0, et = 0;
+    static double tab[2 * kSincosTable];
+    for (int i = 0; i < kSincosTable; ++i) sincos_2pi((double)i / kSincosTable, tab[2 * i + 1], tab[2 * i]);
     for (int i = 0; i < 2000000; ++i) {
         double u = U(g);
         if (i < 9) u = i * 0.125;                       // quadrant boundaries
@@ -32,6 +34,9 @@ int main() {
         es = fmax(es, fabs((double)(s - rs)));
         ec = fmax(ec, fabs((double)(c - rc)));
         ec2 = fmax(ec2, fabs((double)(cos_2pi(u) - rc)));
+        double st, ct;
+        sincos_2pi_tab(u, tab, st, ct);
+        et = fmax(et, fmax(fabs((double)(st - rs)), fabs((double)(ct - rc))));
         double v = 1.0 - u;
         if (v <= 0) v = 1.1e-16;
         if (i % 3 == 0) v = ldexp(v, -(i % 53));        // down to 2^-53
@@ -46,8 +51,8 @@ int main() {
     double s0, c0, s1, c1;
     sincos_2pi(0.0, s0, c0);
     sincos_2pi(1.0, s1, c1);
-    printf("%.3e %.3e %.3e %.3e %.3e %.3e %g %g %g %g %g %g\n", es, ec, ec2, el, ee, ea,
-           s0, c0, s1, c1, log_pos(1.0), exp_neg(0.0));
+    printf("%.3e %.3e %.3e %.3e %.3e %.3e %g %g %g %g %g %g %.3e\n", es, ec, ec2, el, ee, ea,
+           s0, c0, s1, c1, log_pos(1.0), exp_neg(0.0), et);
     return 0;
 }
 '''
@@ -67,7 +72,8 @@ def test_device_math_against_long_double(tmp_path):
     es, ec, ec2, el, ee, ea = (float(v) for v in out[:6])
     assert es < 4e-16 and ec < 4e-16 and ec2 < 4e-16, (es, ec, ec2)     # absolute, |value| <= 1
     assert el < 4e-16 and ee < 4e-16 and ea < 4e-16, (el, ee, ea)       # relative
-    assert [float(v) for v in out[6:]] == [0.0, 1.0, 0.0, 1.0, 0.0, 1.0]
+    assert [float(v) for v in out[6:12]] == [0.0, 1.0, 0.0, 1.0, 0.0, 1.0]
+    assert float(out[12]) < 6e-16, out[12]                               # table version: absolute
 
 
 def test_pretest_normal_deviate_coefficients_against_scipy():

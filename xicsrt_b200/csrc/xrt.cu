@@ -58,6 +58,12 @@ constexpr unsigned kFull = 0xffffffffu;
 // another: only __syncwarp and warp-uniform queue counters.
 
 constexpr int kQ1Cap = 64;     // stage A pushes <= 32 per pass, stage B pops 32 when >= 32 are queued
+#ifndef XRT_UNROLL
+#define XRT_UNROLL 2
+#endif
+constexpr int kUnroll = XRT_UNROLL;   // spectrometer variant: groups of 32 rays per stage-A pass (independent chains)
+constexpr int kQ1CapSpectro = 32 * (kUnroll + 1);
+constexpr int kQ1PlanesSpectro = 5;   // id, direction, distance
 constexpr int kQ2Cap = 64;     // stage B pushes <= 32 per pass, stage C pops 32 when >= 32 are queued
 constexpr int kQ2Planes = 8;   // id, origin, direction, wavelength
 
@@ -65,14 +71,17 @@ template <uint32_t FT> __host__ __device__ constexpr int q1_planes() {
     // id, intersection point, direction [, wavelength when it can be eager] [, normal for mesh shapes]
     return 7 + (FT != 0 ? 1 : 0) + ((FT & FT_MESH) != 0 ? 3 : 0);
 }
-template <uint32_t FT> __host__ __device__ constexpr int warp_queue_doubles() {
-    return q1_planes<FT>() * kQ1Cap + kQ2Planes * kQ2Cap;
+template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int q1_doubles() {
+    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1PlanesSpectro * kQ1CapSpectro : q1_planes<FT>() * kQ1Cap;
+}
+template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int warp_queue_doubles() {
+    return q1_doubles<FT, KN>() + kQ2Planes * kQ2Cap;
 }
 
 // shared-memory copy of the step-1 face operands of a mesh split optic (<= kStageFaces faces)
 constexpr int kStageFaces = 256;
-template <uint32_t FT> __host__ __device__ constexpr size_t block_smem_bytes() {
-    return ((size_t)(XRT_BLOCK / 32) * warp_queue_doubles<FT>() + ((FT & FT_MESH) != 0 ? 9 * kStageFaces : 0)) * sizeof(double);
+template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr size_t block_smem_bytes() {
+    return ((size_t)(XRT_BLOCK / 32) * warp_queue_doubles<FT, KN>() + ((FT & FT_MESH) != 0 ? 9 * kStageFaces : 0)) * sizeof(double);
 }
 
 struct WarpCtx {
@@ -171,7 +180,7 @@ template <uint32_t FT, uint32_t KN>
 __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
                                         const WarpCtx &c, int split, bool lazy, const PhiloxKeys &pk, uint64_t stream_id,
                                         const double *q1, int first, int cnt, double *q2, int &n2, unsigned &n_split) {
-    constexpr int P = kQ1Cap;
+    constexpr int P = ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1CapSpectro : kQ1Cap;
     const bool active = (int)c.lane < cnt;
     Ray r;
     r.alive = false;
@@ -239,23 +248,33 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
 
 // mesh variants keep many more values live (face loops, Clough-Tocher cubics): 2 blocks / SM
 template <uint32_t FT, int SPLIT, uint32_t KN>
-__global__ void __launch_bounds__(kBlock, ((FT & FT_MESH) != 0 && XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS)
+// the spectrometer variant runs two ray groups per pass (independent chains): 119 registers, 2 blocks / SM
+__global__ void __launch_bounds__(kBlock, (((FT & FT_MESH) != 0 || ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
+                                           XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS)
 k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
         const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const int split_rt,
         const int lazy_rt) {
     extern __shared__ double s_queue[];
     __shared__ unsigned long long s_cnt[XRT_MAX_OPTICS + 1];
     if (threadIdx.x <= XRT_MAX_OPTICS) s_cnt[threadIdx.x] = 0ull;
+    // (cos, sin)(2 pi k / 256) for sincos_2pi_tab
+    __shared__ double s_sincos[2 * kSincosTable];
+    for (int i = threadIdx.x; i < kSincosTable; i += kBlock) {
+        double sn, cs;
+        sincos_2pi((double)i / (double)kSincosTable, sn, cs);
+        s_sincos[2 * i] = cs;
+        s_sincos[2 * i + 1] = sn;
+    }
     __syncthreads();
 
-    constexpr int P = kQ1Cap;
+    constexpr int P = ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1CapSpectro : kQ1Cap;
     WarpCtx c;
     c.lane = threadIdx.x & 31u;
     c.lt_mask = (1u << c.lane) - 1u;
     c.s_cnt = s_cnt;
     const int warp = threadIdx.x >> 5;
-    double *q1 = s_queue + (size_t)warp * warp_queue_doubles<FT>();
-    double *q2 = q1 + q1_planes<FT>() * kQ1Cap;
+    double *q1 = s_queue + (size_t)warp * warp_queue_doubles<FT, KN>();
+    double *q2 = q1 + q1_doubles<FT, KN>();
 
     const int split = (SPLIT >= 0) ? SPLIT : split_rt;
     const XrtOpticDesc &ops = sc.optics[split];
@@ -268,7 +287,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             const double *geom;
             const int nf = mesh_stage1_faces(ops, geom);
             if (nf <= kStageFaces) {
-                double *dst = s_queue + (size_t)(kBlock / 32) * warp_queue_doubles<FT>();
+                double *dst = s_queue + (size_t)(kBlock / 32) * warp_queue_doubles<FT, KN>();
                 for (int i = threadIdx.x; i < 9 * nf; i += kBlock) dst[i] = __ldg(geom + i);
                 staged = dst;
             }
@@ -310,57 +329,80 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
         if (!more) break;
 
         // ---- stage A
-        const uint64_t id = id0 + (uint64_t)it * stride;
-        const bool valid = (it != tail_it) || (c.lane < tail);
-        ++it;
-        PhiloxDraws dr;
-        dr.init(pk, stream_id, id, split);
-
         if constexpr (SPECTRO) {
             // Straight-line code for the spectrometer (point source, concave sphere): direction, the two
             // lengths of the sphere intersection and the Bragg pre-test; no branch, no intersection point.
             // sin(theta_i) = |D.n| is thc / R for a ray of unit direction (D.(C - X) = tca - t = -thc), so the
             // pre-test needs nothing else.  A ray it rejects is lost at the crystal whether or not it is inside
             // the bounds, so the bounds test moves to stage B, behind the queue (18 % of the rays).
+            // kUnroll groups of 32 rays per pass: independent dependency chains for the scheduler.
             const XrtSourceDesc &src = sc.source;
-            double a, b;
-            dr.cone(0, a, b);
-            const double cs0 = src.cone_par[0];
-            const double z = cs0 + (1.0 - cs0) * a;
-            const double rho = fast_sqrt(fma(-z, z, 1.0));
-            double sn, cs;
-            sincos_2pi(b, sn, cs);
-            const double lx = rho * cs, ly = rho * sn;
-            const double *B = src.axis_basis;
-            const V3 d = v3(lx * B[0] + ly * B[3] + z * B[6], lx * B[1] + ly * B[4] + z * B[7], lx * B[2] + ly * B[5] + z * B[8]);
-            // hit_sphere, concave
-            const V3 Lc = v3(ops.center) - v3(src.origin);
-            const double tca = dot(Lc, d);
-            const double d2 = fma(-tca, tca, dot(Lc, Lc));
-            const double r2 = ops.radius * ops.radius;
-            const double thc = fast_sqrt(r2 - d2);          // NaN when d2 > r2
-            const double t = tca + thc;
-            bool cand = valid & (d2 >= 0.0) & (d2 <= r2);
-            if (ops.cull_t2 > 0.0) cand &= !bragg_cull_sphere(src, ops, dr.wave_hi(), thc);
-            n_src += __popc(__ballot_sync(kFull, valid));
-            emit_lost(out, c, dr, valid && !cand, id);
-            const unsigned m = __ballot_sync(kFull, cand);
-            if (cand) {
-                double *p = q1 + n1 + __popc(m & c.lt_mask);
-                p[0] = __longlong_as_double((long long)id);
-                p[1 * P] = d.x; p[2 * P] = d.y; p[3 * P] = d.z;
-                p[4 * P] = t;
+            uint64_t idv[kUnroll];
+            V3 dv[kUnroll];
+            double tv[kUnroll];
+            bool validv[kUnroll], candv[kUnroll];
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const uint32_t itj = it + (uint32_t)j;
+                idv[j] = id0 + (uint64_t)itj * stride;
+                validv[j] = (itj < n_it) && ((itj != tail_it) || (c.lane < tail));
+                PhiloxDraws dr;
+                dr.init(pk, stream_id, idv[j], split);
+                double a, b;
+                dr.cone(0, a, b);
+                const double cs0 = src.cone_par[0];
+                const double z = cs0 + (1.0 - cs0) * a;
+                const double rho = fast_sqrt(fma(-z, z, 1.0));
+                double sn, cs;
+                sincos_2pi_tab(b, s_sincos, sn, cs);
+                const double lx = rho * cs, ly = rho * sn;
+                const double *B = src.axis_basis;
+                const V3 d = v3(lx * B[0] + ly * B[3] + z * B[6], lx * B[1] + ly * B[4] + z * B[7],
+                                lx * B[2] + ly * B[5] + z * B[8]);
+                // hit_sphere, concave
+                const V3 Lc = v3(ops.center) - v3(src.origin);
+                const double tca = dot(Lc, d);
+                const double d2 = fma(-tca, tca, dot(Lc, Lc));
+                const double r2 = ops.radius * ops.radius;
+                const double thc = fast_sqrt(r2 - d2);          // NaN when d2 > r2
+                dv[j] = d;
+                tv[j] = tca + thc;
+                bool cand = validv[j] & (d2 >= 0.0) & (d2 <= r2);
+                if (ops.cull_t2 > 0.0) cand &= !bragg_cull_sphere(src, ops, dr.wave_hi(), thc);
+                candv[j] = cand;
             }
-            n1 += __popc(m);
+            it += kUnroll;
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                n_src += __popc(__ballot_sync(kFull, validv[j]));
+                if (out.lost_count) {
+                    PhiloxDraws dr;
+                    dr.init(pk, stream_id, idv[j], split);
+                    emit_lost(out, c, dr, validv[j] && !candv[j], idv[j]);
+                }
+                const unsigned m = __ballot_sync(kFull, candv[j]);
+                if (candv[j]) {
+                    double *p = q1 + n1 + __popc(m & c.lt_mask);
+                    p[0] = __longlong_as_double((long long)idv[j]);
+                    p[1 * P] = dv[j].x; p[2 * P] = dv[j].y; p[3 * P] = dv[j].z;
+                    p[4 * P] = tv[j];
+                }
+                n1 += __popc(m);
+            }
             __syncwarp();
         } else {
+            const uint64_t id = id0 + (uint64_t)it * stride;
+            const bool valid = (it != tail_it) || (c.lane < tail);
+            ++it;
+            PhiloxDraws dr;
+            dr.init(pk, stream_id, id, split);
             Ray r;
             r.alive = false;
             r.w = 0.0;
             if (valid) {
                 SrcLocal L;
                 source_local<FT, KN>(sc.source, id, L);
-                generate_geometry<FT, PhiloxDraws, KN>(sc.source, L, dr, r);
+                generate_geometry<FT, PhiloxDraws, KN>(sc.source, L, dr, r, s_sincos);
                 if (!lazy) r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
             }
             n_src += __popc(__ballot_sync(kFull, r.alive));
@@ -819,7 +861,10 @@ static TraceKernel trace_kernel(const XrtScene *s, size_t *smem) {
         *smem = block_smem_bytes<0>();
         // pre-instantiated structure: point source with a Gaussian line on a concave spherical
         // Bragg crystal as first optic -- the spherical-crystal spectrometer
-        if (s->split == 0 && (s->known & KN_SPECTROMETER) == KN_SPECTROMETER) return k_trace<0, 0, KN_SPECTROMETER>;
+        if (s->split == 0 && (s->known & KN_SPECTROMETER) == KN_SPECTROMETER) {
+            *smem = block_smem_bytes<0, KN_SPECTROMETER>();
+            return k_trace<0, 0, KN_SPECTROMETER>;
+        }
         return trace_kernel_ft<0>(s->split);
     }
     if (s->features == FT_MID) {
