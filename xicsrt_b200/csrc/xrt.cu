@@ -417,6 +417,14 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             V3 n = v3(0.0, 0.0, 1.0);
             bool cand = false;
             if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
+            // Bragg pre-test (bragg_cull_general): enabled by xrt_scene_create for a spherical Bragg crystal
+            // traced in global coordinates; the survivors take the exact path in stage B
+            if (ops.cull_t2 > 0.0) {
+                if (cand && bragg_cull_general(sc.source, ops, !lazy, r.w, dr.wave_hi(), r.o, r.d)) {
+                    cand = false;
+                    r.alive = false;
+                }
+            }
             emit_lost(out, c, dr, valid && !cand, id);
 
             const unsigned m = __ballot_sync(kFull, cand);
@@ -796,14 +804,21 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         if (o.interact == XRT_INTERACT_CRYSTAL && (o.flags & XRT_F_CHECK_BRAGG) && o.rocking_type == XRT_ROCK_GAUSS)
             s->known |= KN_CRYSTAL_GAUSS;
         if (o.flags & XRT_F_IMAGE) s->known |= KN_IMAGE;
-        // parameters of the Bragg pre-test (bragg_cull) for the spectrometer variant
-        if ((s->known & KN_SPECTROMETER) == KN_SPECTROMETER && s->split == 0 && s->lazy_wavelength && s->features == 0 &&
-            o.rock_inv_two_sigma2 > 0.0 && std::isfinite(o.rock_inv_two_sigma2) && o.radius > 0.0 &&
-            std::isfinite(o.inv_two_d) && std::getenv("XRT_NO_CULL") == nullptr) {
+        // parameters of the Bragg pre-test (bragg_cull_* in xrt_trace.cuh): a spherical Bragg crystal with a
+        // Gaussian or step rocking curve, traced in global coordinates, as split optic; the wavelength is either
+        // drawn before the crystal (sources with a Doppler shift, plasma bundles) or it is a constant / normal line
+        const bool rock_ok = (o.rocking_type == XRT_ROCK_GAUSS && o.rock_inv_two_sigma2 > 0.0 && std::isfinite(o.rock_inv_two_sigma2)) ||
+                             (o.rocking_type == XRT_ROCK_STEP && o.rocking_fwhm >= 0.0 && std::isfinite(o.rocking_fwhm));
+        const bool wave_ok = !s->lazy_wavelength || src.wave == XRT_WAVE_NORMAL || src.wave == XRT_WAVE_CONST;
+        if (o.shape == XRT_SHAPE_SPHERE && o.interact == XRT_INTERACT_CRYSTAL && (o.flags & XRT_F_CHECK_BRAGG) &&
+            !(o.flags & XRT_F_TRACE_LOCAL) && rock_ok && wave_ok && o.radius > 0.0 && std::isfinite(o.inv_two_d) &&
+            !(s->features & FT_MESH) && std::getenv("XRT_NO_CULL") == nullptr) {
             XrtOpticDesc &w = d.optics[s->split];
-            const double t = 1.05 * std::sqrt(40.0 / o.rock_inv_two_sigma2) + 2e-6;
+            const double edge = o.rocking_type == XRT_ROCK_GAUSS ? std::sqrt(40.0 / o.rock_inv_two_sigma2) : 0.5 * o.rocking_fwhm;
+            const double t = 1.05 * edge + 2e-6;
             w.cull_t2 = t * t;
-            w.cull_err = 2e-3 * std::fabs(src.wave_par[1]) * std::fabs(o.inv_two_d) + 1e-9;
+            const bool approx = s->lazy_wavelength && src.wave == XRT_WAVE_NORMAL;
+            w.cull_err = (approx ? 2e-3 * std::fabs(src.wave_par[1]) * std::fabs(o.inv_two_d) : 0.0) + 1e-9;
             w.cull_inv_r = 1.0 / o.radius;
         }
     }

@@ -608,16 +608,32 @@ __device__ __forceinline__ float normal_approx(uint32_t hi, bool &usable) {
 
 // cos^2(min(theta_B, theta_i)) <= (1 - sI^2) + 2 |sB - sI|  (equality to first order when sB < sI), which
 // avoids the FP64 min / max selects.
-// sphere: sI = |D.n| = thc / R, the half chord of hit_sphere over the radius (|D| = 1)
-__device__ __forceinline__ bool bragg_cull_sphere(const XrtSourceDesc &s, const XrtOpticDesc &op, uint32_t wave_hi, double thc) {
-    bool usable;
-    const float z = normal_approx(wave_hi, usable);
-    const double sB = fma((double)z, s.wave_par[1], s.wave_par[0]) * op.inv_two_d;
-    const double sI = thc * op.cull_inv_r;
+__device__ __forceinline__ bool bragg_cull_test(const XrtOpticDesc &op, double sB, double sI, bool usable) {
     const double gap = fabs(sB - sI);
     const double diff = gap - op.cull_err;
     const double c2 = fma(2.0, gap, fma(-sI, sI, 1.0));
     return usable & (diff > 0.0) & (diff * diff > op.cull_t2 * c2);
+}
+
+// sphere hit from a point source: sI = |D.n| = thc / R, the half chord of hit_sphere over the radius (|D| = 1)
+__device__ __forceinline__ bool bragg_cull_sphere(const XrtSourceDesc &s, const XrtOpticDesc &op, uint32_t wave_hi, double thc) {
+    bool usable;
+    const float z = normal_approx(wave_hi, usable);
+    const double sB = fma((double)z, s.wave_par[1], s.wave_par[0]) * op.inv_two_d;
+    return bragg_cull_test(op, sB, thc * op.cull_inv_r, usable);
+}
+
+// general form for a sphere traced in global coordinates: X = intersection point, d = unit direction;
+// `lambda` is the ray's wavelength when it is already drawn (eager), else the approximation is used
+__device__ __forceinline__ bool bragg_cull_general(const XrtSourceDesc &s, const XrtOpticDesc &op, bool have_lambda,
+                                                   double lambda, uint32_t wave_hi, V3 X, V3 d) {
+    bool usable = true;
+    if (!have_lambda) {
+        lambda = s.wave_par[0];
+        if (s.wave == XRT_WAVE_NORMAL) lambda = fma((double)normal_approx(wave_hi, usable), s.wave_par[1], lambda);
+    }
+    const double sI = fabs(dot(d, v3(op.center) - X)) * op.cull_inv_r;
+    return bragg_cull_test(op, lambda * op.inv_two_d, sI, usable);
 }
 
 // true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).
