@@ -251,6 +251,12 @@ typedef struct XrtSourceDesc {
        n_table entries; a row is valid where the bundle emits rays (xrt_bundle_voigt_tables)     */
     const double *bundle_x;          /* [n_bundles][n_table]                                     */
     const double *bundle_cdf;        /* [n_bundles][n_table]                                     */
+    /* ray id -> bundle lookup hint, built by the library (input values are ignored): entry i is the
+       bundle of ray id (i << bundle_hint_shift), so a ray's bundle lies in [hint[j], hint[j + 1]]
+       with j = id >> shift and the binary search over bundle_end starts from that bracket         */
+    const uint32_t *bundle_hint;
+    int32_t bundle_hint_shift;
+    int32_t pad1;
 } XrtSourceDesc;
 
 typedef struct XrtSceneDesc {
@@ -356,8 +362,11 @@ int xrt_bundles_generate(const XrtPlasmaDesc *desc, uint64_t seed, uint64_t stre
                          XrtBundle *table_dev, double *intensity_dev, int64_t *counts_dev, void *stream);
 
 /* Point a plasma scene (source.kind == XRT_SRC_BUNDLES) at a device-resident bundle table and its
-   inclusive prefix sum of counts; bundles with a zero count are skipped by the lookup. */
-int xrt_scene_set_bundles(XrtScene *scene, const XrtBundle *table_dev, const uint64_t *end_dev, uint64_t n_bundles);
+   inclusive prefix sum of counts; bundles with a zero count are skipped by the lookup.  n_rays =
+   end_dev[n_bundles - 1] as known to the host (0 = unknown: no lookup hint is built).  The hint
+   table is built on the legacy default stream, which orders it after work on blocking streams. */
+int xrt_scene_set_bundles(XrtScene *scene, const XrtBundle *table_dev, const uint64_t *end_dev, uint64_t n_bundles,
+                          uint64_t n_rays);
 
 /* Per-bundle Voigt inverse-CDF tables (xicsrt/tools/xicsrt_voigt.py:30-92, built by every
    per-bundle XicsrtSourceFocused in _XicsrtSourceGeneric.py:319-354): for each bundle b with

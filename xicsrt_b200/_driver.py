@@ -135,7 +135,7 @@ class Tracer:
         """Bundle centres, plasma parameters and ray counts of one iteration, built on the device."""
         self.n_rays = self.bundles.generate(self.seed, (1 << 32) + iteration)
         self.layout.n_rays = self.n_rays
-        self.scene.set_bundles(self.bundles.table, self.bundles.end)
+        self.scene.set_bundles(self.bundles.table, self.bundles.end, self.n_rays)
         if self.bundles.voigt_x is not None:
             self.scene.set_bundle_tables(self.bundles.voigt_x, self.bundles.voigt_cdf)
 

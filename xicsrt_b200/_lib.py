@@ -110,7 +110,8 @@ class XrtSourceDesc(C.Structure):
                 ('table_cdf', _pd), ('table_x', _pd),
                 ('sightlines', XrtSightline * MAX_SIGHTLINES),
                 ('n_bundles', C.c_uint64), ('bundles', C.POINTER(XrtBundle)), ('bundle_end', _pu64),
-                ('voxel_size', C.c_double), ('bundle_x', _pd), ('bundle_cdf', _pd)]
+                ('voxel_size', C.c_double), ('bundle_x', _pd), ('bundle_cdf', _pd),
+                ('bundle_hint', C.c_void_p), ('bundle_hint_shift', C.c_int32), ('pad1', C.c_int32)]
 
 
 class XrtSceneDesc(C.Structure):
@@ -164,7 +165,7 @@ SYMBOLS = {
     'xrt_source_injected': (C.c_int, [_vp, C.POINTER(XrtSourceInject), _u64, C.POINTER(XrtHistory), _vp]),
     'xrt_source_generate': (C.c_int, [_vp, _u64, _u64, _u64, _u64, C.POINTER(XrtHistory), _vp]),
     'xrt_bundles_generate': (C.c_int, [C.POINTER(XrtPlasmaDesc), _u64, _u64, _u64, _vp, _vp, _vp, _vp]),
-    'xrt_scene_set_bundles': (C.c_int, [_vp, _vp, _vp, _u64]),
+    'xrt_scene_set_bundles': (C.c_int, [_vp, _vp, _vp, _u64, _u64]),
     'xrt_bundle_voigt_tables': (C.c_int, [_vp, _vp, _u64, C.c_double, C.c_int32, _vp, _vp, _vp]),
     'xrt_scene_set_bundle_tables': (C.c_int, [_vp, _vp, _vp, C.c_int32]),
     'xrt_fp64_burn': (C.c_int, [_u64, _vp, C.POINTER(C.c_double), _vp]),

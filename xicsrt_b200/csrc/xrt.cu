@@ -575,6 +575,7 @@ using namespace xrt;
 struct XrtScene {
     XrtSceneDesc dev;               // descriptor whose pointers are device pointers
     std::vector<void *> allocs;
+    void *bundle_hint = nullptr;    // ray id -> bundle bracket table of the current bundle table
     uint32_t features;
     int split;                      // first crystal of the train (0 if none): the kernel's re-pack point
     int lazy_wavelength;            // wavelength independent of the source direction: drawn at the crystal
@@ -700,9 +701,12 @@ extern "C" int xrt_scene_destroy(XrtScene *s) {
     if (!s) return XRT_OK;
     // stream-ordered on the legacy stream: waits for kernels of every blocking stream that still read the tables
     for (void *p : s->allocs) cudaFreeAsync(p, (cudaStream_t)0);
+    if (s->bundle_hint) cudaFreeAsync(s->bundle_hint, (cudaStream_t)0);
     delete s;
     return XRT_OK;
 }
+
+static int build_bundle_hint(XrtScene *s, uint64_t n_rays);
 
 static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
     s->dev = *desc;
@@ -738,8 +742,15 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         UP(m.table_x, one_table ? m.n_table : 0);
         UP(m.bundle_x, host_tables ? m.n_bundles * (uint64_t)m.n_table : 0);
         UP(m.bundle_cdf, host_tables ? m.n_bundles * (uint64_t)m.n_table : 0);
+        const uint64_t host_rays = host_bundles ? m.bundle_end[m.n_bundles - 1] : 0;
         UP(m.bundles, host_bundles ? m.n_bundles : 0);
         UP(m.bundle_end, host_bundles ? m.n_bundles : 0);
+        m.bundle_hint = nullptr;
+        m.bundle_hint_shift = 0;
+        if (host_bundles) {
+            int rc_ = build_bundle_hint(s, host_rays);
+            if (rc_ != XRT_OK) return rc_;
+        }
     }
 
     for (int k = 0; k < d.n_optics; ++k) {
@@ -1051,14 +1062,45 @@ extern "C" int xrt_source_generate(XrtScene *s, uint64_t seed, uint64_t stream_i
     return launch_source<REC_PHILOX>(s, seed, stream_id, ray_begin, n, none, hist, stream);
 }
 
-extern "C" int xrt_scene_set_bundles(XrtScene *s, const XrtBundle *table_dev, const uint64_t *end_dev, uint64_t n_bundles) {
+// Bracket table for the ray id -> bundle search (XrtSourceDesc.bundle_hint), on the legacy default stream.
+static int build_bundle_hint(XrtScene *s, uint64_t n_rays) {
+    XrtSourceDesc &src = s->dev.source;
+    if (s->bundle_hint) {
+        cudaFreeAsync(s->bundle_hint, (cudaStream_t)0);
+        s->bundle_hint = nullptr;
+    }
+    src.bundle_hint = nullptr;
+    src.bundle_hint_shift = 0;
+    if (n_rays == 0 || src.n_bundles < 64 || src.n_bundles > 0xffffffffull) return XRT_OK;
+    int shift = 10;
+    while ((n_rays >> shift) > (1ull << 22)) ++shift;        // at most 4 Mi entries (16 MB)
+    const uint64_t n_buckets = ((n_rays - 1) >> shift) + 1;
+    void *p = nullptr;
+    CU(cudaMallocAsync(&p, (n_buckets + 1) * sizeof(uint32_t), (cudaStream_t)0));
+    s->bundle_hint = p;
+    uint64_t want = (n_buckets + 256) / 256;
+    int grid = (int)(want < 4096 ? want : 4096);
+    k_bundle_hint<<<grid, 256, 0, (cudaStream_t)0>>>(src.bundle_end, src.n_bundles, shift, n_buckets, (uint32_t *)p);
+    CU(cudaGetLastError());
+    src.bundle_hint = (const uint32_t *)p;
+    src.bundle_hint_shift = shift;
+    return XRT_OK;
+}
+
+extern "C" int xrt_scene_set_bundles(XrtScene *s, const XrtBundle *table_dev, const uint64_t *end_dev, uint64_t n_bundles,
+                                     uint64_t n_rays) {
     if (!s) return fail(XRT_EINVAL, "null scene");
     if (s->dev.source.kind != XRT_SRC_BUNDLES) return fail(XRT_EINVAL, "the scene's source is not a plasma");
     if (!table_dev || !end_dev || n_bundles == 0) return fail(XRT_EINVAL, "empty bundle table");
     s->dev.source.bundles = table_dev;
     s->dev.source.bundle_end = end_dev;
     s->dev.source.n_bundles = n_bundles;
-    return XRT_OK;
+    int prev = 0;
+    CU(cudaGetDevice(&prev));
+    if (prev != s->device) CU(cudaSetDevice(s->device));
+    const int rc = build_bundle_hint(s, n_rays);
+    if (prev != s->device) cudaSetDevice(prev);
+    return rc;
 }
 
 extern "C" int xrt_scene_set_bundle_tables(XrtScene *s, const double *x_dev, const double *cdf_dev, int32_t n_table) {

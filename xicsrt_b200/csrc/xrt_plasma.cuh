@@ -153,6 +153,28 @@ k_bundles(const XrtPlasmaDesc p, const uint64_t seed, const uint64_t stream_id, 
 }
 
 // ---------------------------------------------------------------------------
+// ray id -> bundle hint: hint[i] = first bundle whose inclusive prefix sum exceeds i << shift
+// (i.e. the bundle of that ray id); hint[n_buckets] = n_bundles - 1.
+__global__ void __launch_bounds__(256)
+k_bundle_hint(const uint64_t *__restrict__ end, const uint64_t n_bundles, const int shift, const uint64_t n_buckets,
+              uint32_t *__restrict__ hint) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_buckets; i += stride) {
+        uint64_t lo = 0, hi = n_bundles - 1;
+        if (i < n_buckets) {
+            const uint64_t index = i << shift;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (__ldg(end + mid) > index) hi = mid; else lo = mid + 1;
+            }
+        } else {
+            lo = hi;
+        }
+        hint[i] = (uint32_t)lo;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Per-bundle Voigt inverse-CDF tables (xicsrt/tools/xicsrt_voigt.py:30-92).
 //
 // The reference builds one 1000-bin table per bundle source with scipy's Faddeeva function.

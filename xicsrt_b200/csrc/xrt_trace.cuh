@@ -220,6 +220,11 @@ __device__ __forceinline__ void source_local(const XrtSourceDesc &s, uint64_t in
         if (s.kind == XRT_SRC_BUNDLES) {
             // bundle of this ray: first b with bundle_end[b] > index
             uint64_t lo = 0, hi = s.n_bundles - 1;
+            if (s.bundle_hint) {     // bracket from the per-2^shift-ids hint table: usually 0..2 steps left
+                const uint64_t j = index >> s.bundle_hint_shift;
+                lo = __ldg(s.bundle_hint + j);
+                hi = __ldg(s.bundle_hint + j + 1);
+            }
             while (lo < hi) {
                 uint64_t mid = (lo + hi) >> 1;
                 if (__ldg(s.bundle_end + mid) > index) hi = mid; else lo = mid + 1;

@@ -383,9 +383,10 @@ class DeviceScene:
         except Exception:
             pass
 
-    def set_bundles(self, table, end):
+    def set_bundles(self, table, end, n_rays=0):
         """Point a plasma scene at a device-resident bundle table (torch tensors, kept alive by the caller)."""
-        L.check(self.lib.xrt_scene_set_bundles(self.handle, table.data_ptr(), end.data_ptr(), int(end.numel())))
+        L.check(self.lib.xrt_scene_set_bundles(self.handle, table.data_ptr(), end.data_ptr(), int(end.numel()),
+                                               int(n_rays)))
 
     def set_bundle_tables(self, x, cdf):
         """Per-bundle wavelength tables [n_bundles, n_table] of a plasma with a natural linewidth."""
