@@ -279,8 +279,8 @@ def run_gpu_arm(args):
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the events)
-        tracer.begin_iteration(k)           # plasma sources: new bundle table (host work, outside the events)
         starts[k].record()
+        tracer.begin_iteration(k)           # plasma sources: new bundle table, built on the device (inside the events)
         tracer.trace(k, keep_images=True)
         kstops[k].record()
         tracer.allreduce()

@@ -64,6 +64,7 @@ constexpr int kQ1Cap = 64;     // stage A pushes <= 32 per pass, stage B pops 32
 constexpr int kUnroll = XRT_UNROLL;   // spectrometer variant: groups of 32 rays per stage-A pass (independent chains)
 constexpr int kQ1CapSpectro = 32 * (kUnroll + 1);
 constexpr int kQ1PlanesSpectro = 5;   // id, direction, distance
+constexpr int kQbCap = 64;            // spectrometer variant: rays inside the bounds, between the two halves of stage B
 constexpr int kQ2Cap = 64;     // stage B pushes <= 32 per pass, stage C pops 32 when >= 32 are queued
 constexpr int kQ2Planes = 8;   // id, origin, direction, wavelength
 
@@ -72,7 +73,7 @@ template <uint32_t FT> __host__ __device__ constexpr int q1_planes() {
     return 7 + (FT != 0 ? 1 : 0) + ((FT & FT_MESH) != 0 ? 3 : 0);
 }
 template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int q1_doubles() {
-    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1PlanesSpectro * kQ1CapSpectro : q1_planes<FT>() * kQ1Cap;
+    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1PlanesSpectro * (kQ1CapSpectro + kQbCap) : q1_planes<FT>() * kQ1Cap;
 }
 template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int warp_queue_doubles() {
     return q1_doubles<FT, KN>() + kQ2Planes * kQ2Cap;
@@ -178,9 +179,9 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
 // ---- stage B: interaction of the split optic for `cnt` rays popped from queue 1
 template <uint32_t FT, uint32_t KN>
 __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
-                                        const WarpCtx &c, int split, bool lazy, const PhiloxKeys &pk, uint64_t stream_id,
+                                        const WarpCtx &c, int split, bool lazy, bool need_wave, const PhiloxKeys &pk, uint64_t stream_id,
                                         const double *q1, int first, int cnt, double *q2, int &n2, unsigned &n_split) {
-    constexpr int P = ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1CapSpectro : kQ1Cap;
+    constexpr int P = ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQbCap : kQ1Cap;   // spectrometer: q1 = queue b here
     const bool active = (int)c.lane < cnt;
     Ray r;
     r.alive = false;
@@ -193,15 +194,11 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
         const double *p = q1 + first + c.lane;
         id = (uint64_t)__double_as_longlong(p[0]);
         if constexpr (SPECTRO) {
-            // queue 1 of the spectrometer variant holds (id, direction, distance): the intersection point
-            // and the bounds test (_TraceObject.py:180-232) are done here, on the ~18 % of the rays that
-            // passed the Bragg pre-test, with the arithmetic of optic_geometry
+            // queue b of the spectrometer variant: (id, direction, distance) of rays inside the bounds
             const V3 d = v3(p[1 * P], p[2 * P], p[3 * P]);
             const double t = p[4 * P];
             const V3 o = v3(sc.source.origin);
             const V3 X = v3(fma(d.x, t, o.x), fma(d.y, t, o.y), fma(d.z, t, o.z));
-            const V3 Xl = to_local(ops.orient, X - v3(ops.origin));
-            inside = (fabs(Xl.x) < ops.half_size[0]) && (fabs(Xl.y) < ops.half_size[1]);
             r.o = X;
             r.d = d;
         } else {
@@ -215,7 +212,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     PhiloxDraws dr;
     dr.init(pk, stream_id, id, split);
     if (inside) {
-        if (lazy) {
+        if (lazy && need_wave) {      // history is off here: a wavelength nobody tests is not drawn
             SrcLocal L;
             source_local<0, KN>(sc.source, id, L);
             r.w = generate_wavelength<PhiloxDraws, KN, false>(sc.source, L, dr, r.d);   // lazy = no Doppler shift
@@ -243,6 +240,45 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
         p[7 * kQ2Cap] = r.w;
     }
     n2 += __popc(m);
+    __syncwarp();
+}
+
+// ---- spectrometer variant, first half of stage B: intersection point and bounds test
+// (_TraceObject.py:180-232, arithmetic of optic_geometry) for `cnt` rays popped from queue 1 -- the ~18 % that
+// passed the Bragg pre-test; the ~52 % of those inside the bounds are re-packed into queue b
+__device__ __forceinline__ void stage_b1(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
+                                         const WarpCtx &c, int split, const PhiloxKeys &pk, uint64_t stream_id,
+                                         const double *q1, int first, int cnt, double *qb, int &nb) {
+    constexpr int P = kQ1CapSpectro;
+    const bool active = (int)c.lane < cnt;
+    bool inside = false;
+    uint64_t id = 0;
+    V3 d = v3(0.0, 0.0, 1.0);
+    double t = 0.0;
+    if (active) {
+        const double *p = q1 + first + c.lane;
+        id = (uint64_t)__double_as_longlong(p[0]);
+        d = v3(p[1 * P], p[2 * P], p[3 * P]);
+        t = p[4 * P];
+        const V3 o = v3(sc.source.origin);
+        const V3 X = v3(fma(d.x, t, o.x), fma(d.y, t, o.y), fma(d.z, t, o.z));
+        const V3 Xl = to_local(ops.orient, X - v3(ops.origin));
+        inside = (fabs(Xl.x) < ops.half_size[0]) && (fabs(Xl.y) < ops.half_size[1]);
+    }
+    __syncwarp();
+    if (out.lost_count) {
+        PhiloxDraws dr;
+        dr.init(pk, stream_id, id, split);
+        emit_lost(out, c, dr, active && !inside, id);
+    }
+    const unsigned m = __ballot_sync(kFull, inside);
+    if (inside) {
+        double *p = qb + nb + __popc(m & c.lt_mask);
+        p[0] = __longlong_as_double((long long)id);
+        p[1 * kQbCap] = d.x; p[2 * kQbCap] = d.y; p[3 * kQbCap] = d.z;
+        p[4 * kQbCap] = t;
+    }
+    nb += __popc(m);
     __syncwarp();
 }
 
@@ -278,7 +314,8 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
 
     const int split = (SPLIT >= 0) ? SPLIT : split_rt;
     const XrtOpticDesc &ops = sc.optics[split];
-    const bool lazy = (FT == 0) ? true : (lazy_rt != 0);
+    const bool lazy = (FT == 0) ? true : ((lazy_rt & 1) != 0);
+    const bool need_wave = (lazy_rt & 2) != 0;   // some optic from the split optic on reads the wavelength (Bragg test)
 
     // mesh split optic: stage the face operands every ray is tested against in shared memory
     const double *staged = nullptr;
@@ -295,6 +332,8 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
         __syncthreads();
     }
     int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
+    int nb = 0;             // spectrometer variant: queue b (inside the bounds), after the planes of queue 1
+    double *qb = q1 + kQ1PlanesSpectro * kQ1CapSpectro;
     unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
 
     // Ray ids in groups of 32: group g = warp_global + it * n_warps belongs to this warp at iteration it.
@@ -314,17 +353,32 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     uint32_t it = 0;
     for (;;) {
         const bool more = it < n_it;
-        if (n2 >= 32 || (!more && n1 == 0 && n2 > 0)) {
+        if (n2 >= 32 || (!more && n1 == 0 && nb == 0 && n2 > 0)) {
             const int cnt = n2 < 32 ? n2 : 32;
             n2 -= cnt;
             stage_c<FT>(sc, out, c, split, pk, stream_id, q2, n2, cnt);
             continue;
         }
-        if (n1 >= 32 || (!more && n1 > 0)) {
-            const int cnt = n1 < 32 ? n1 : 32;
-            n1 -= cnt;
-            stage_b<FT, KN>(sc, ops, out, c, split, lazy, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
-            continue;
+        if constexpr (SPECTRO) {
+            if (nb >= 32 || (!more && n1 == 0 && nb > 0)) {
+                const int cnt = nb < 32 ? nb : 32;
+                nb -= cnt;
+                stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, pk, stream_id, qb, nb, cnt, q2, n2, n_split);
+                continue;
+            }
+            if (n1 >= 32 || (!more && n1 > 0)) {
+                const int cnt = n1 < 32 ? n1 : 32;
+                n1 -= cnt;
+                stage_b1(sc, ops, out, c, split, pk, stream_id, q1, n1, cnt, qb, nb);
+                continue;
+            }
+        } else {
+            if (n1 >= 32 || (!more && n1 > 0)) {
+                const int cnt = n1 < 32 ? n1 : 32;
+                n1 -= cnt;
+                stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
+                continue;
+            }
         }
         if (!more) break;
 
@@ -402,7 +456,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             if (valid) {
                 SrcLocal L;
                 source_local<FT, KN>(sc.source, id, L);
-                generate_geometry<FT, PhiloxDraws, KN>(sc.source, L, dr, r, s_sincos);
+                generate_geometry<FT, PhiloxDraws, KN, true>(sc.source, L, dr, r, s_sincos);
                 if (!lazy) r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
             }
             n_src += __popc(__ballot_sync(kFull, r.alive));
@@ -579,6 +633,7 @@ struct XrtScene {
     uint32_t features;
     int split;                      // first crystal of the train (0 if none): the kernel's re-pack point
     int lazy_wavelength;            // wavelength independent of the source direction: drawn at the crystal
+    int need_wavelength;            // an optic at or after the split optic reads the wavelength (Bragg test / mosaic cutoff)
     uint32_t known;                 // KN_* facts that hold for this scene (source + split optic)
     int device;
     int sm_count;
@@ -801,6 +856,12 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
     }
     s->lazy_wavelength = (src.kind != XRT_SRC_BUNDLES && src.velocity_c[0] == 0.0 && src.velocity_c[1] == 0.0 &&
                           src.velocity_c[2] == 0.0) ? 1 : 0;
+    s->need_wavelength = 0;
+    for (int k = s->split; k < d.n_optics; ++k) {
+        const XrtOpticDesc &o = d.optics[k];
+        const bool crystal = o.interact == XRT_INTERACT_CRYSTAL || o.interact == XRT_INTERACT_MOSAIC;
+        if (crystal && (o.flags & (XRT_F_CHECK_BRAGG | XRT_F_MOSAIC_CUTOFF))) s->need_wavelength = 1;
+    }
     // the lean variant has no wavelength plane in its queue: a source with a Doppler shift needs the full one
     if (s->features == 0 && !s->lazy_wavelength) s->features = FT_MID;
     s->known = 0;
@@ -957,7 +1018,7 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     PhiloxKeys pk;
     philox_round_keys(seed, stream_id, pk);
     kern<<<grid, kBlock, smem, (cudaStream_t)stream>>>(s->dev, pk, stream_id, ray_begin, ray_count, *out, s->split,
-                                                      s->lazy_wavelength);
+                                                      s->lazy_wavelength | (s->need_wavelength << 1));
     CU(cudaGetLastError());
     return XRT_OK;
 }

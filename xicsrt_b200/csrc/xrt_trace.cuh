@@ -241,7 +241,7 @@ __device__ __forceinline__ void source_local(const XrtSourceDesc &s, uint64_t in
 }
 
 // origin, direction and the source-level mask
-template <uint32_t FT, class DR, uint32_t KN = 0>
+template <uint32_t FT, class DR, uint32_t KN = 0, bool USE_TABLE = false>
 __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const SrcLocal &L, const DR &dr, Ray &r,
                                                   const double *sincos_table = nullptr) {
     // ---- origin (:229-255): three draws of U(-size/2, size/2), or N(0, sigma)
@@ -278,7 +278,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
         double z = L.cos_spread + (1.0 - L.cos_spread) * a;
         double rho = fast_sqrt(fma(-z, z, 1.0));
         double sn, cs;
-        if (sincos_table) sincos_2pi_tab(b, sincos_table, sn, cs);   // fused kernel: shared-memory table
+        if constexpr (USE_TABLE) sincos_2pi_tab(b, sincos_table, sn, cs);   // fused kernel: shared-memory table
         else sincos_2pi(b, sn, cs);
         l = v3(rho * cs, rho * sn, z);
     } else if (cone == XRT_CONE_ISOTROPIC_XY) {
