@@ -36,6 +36,7 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     import bench
     from xicsrt_b200 import _driver, config as xconfig

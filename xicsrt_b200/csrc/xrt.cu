@@ -179,7 +179,7 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
 // ---- stage B: interaction of the split optic for `cnt` rays popped from queue 1
 template <uint32_t FT, uint32_t KN>
 __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
-                                        const WarpCtx &c, int split, bool lazy, bool need_wave, const PhiloxKeys &pk, uint64_t stream_id,
+                                        const WarpCtx &c, int split, bool lazy, bool need_wave, bool defer, const PhiloxKeys &pk, uint64_t stream_id,
                                         const double *q1, int first, int cnt, double *q2, int &n2, unsigned &n_split) {
     constexpr int P = ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQbCap : kQ1Cap;   // spectrometer: q1 = queue b here
     const bool active = (int)c.lane < cnt;
@@ -216,6 +216,14 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
             SrcLocal L;
             source_local<0, KN>(sc.source, id, L);
             r.w = generate_wavelength<PhiloxDraws, KN, false>(sc.source, L, dr, r.d);   // lazy = no Doppler shift
+        }
+        if constexpr (FT != 0) {
+            if (defer) {              // r.w holds the Doppler factor (stage A); the same expressions as generate_wavelength
+                SrcLocal L;
+                source_local<FT, KN>(sc.source, id, L);
+                const double w0 = sc.source.wave_par[0] + L.wave_sigma * dr.wave_z();
+                r.w = (r.w != 1.0) ? w0 * r.w : w0;
+            }
         }
         bool analytic = true;
         if constexpr ((FT & FT_MESH) != 0) analytic = ops.shape != XRT_SHAPE_MESH;
@@ -316,6 +324,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     const XrtOpticDesc &ops = sc.optics[split];
     const bool lazy = (FT == 0) ? true : ((lazy_rt & 1) != 0);
     const bool need_wave = (lazy_rt & 2) != 0;   // some optic from the split optic on reads the wavelength (Bragg test)
+    const bool defer = (FT == 0) ? false : ((lazy_rt & 4) != 0);   // eager normal line: exact deviate left to stage B
 
     // mesh split optic: stage the face operands every ray is tested against in shared memory
     const double *staged = nullptr;
@@ -363,7 +372,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             if (nb >= 32 || (!more && n1 == 0 && nb > 0)) {
                 const int cnt = nb < 32 ? nb : 32;
                 nb -= cnt;
-                stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, pk, stream_id, qb, nb, cnt, q2, n2, n_split);
+                stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, defer, pk, stream_id, qb, nb, cnt, q2, n2, n_split);
                 continue;
             }
             if (n1 >= 32 || (!more && n1 > 0)) {
@@ -376,7 +385,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             if (n1 >= 32 || (!more && n1 > 0)) {
                 const int cnt = n1 < 32 ? n1 : 32;
                 n1 -= cnt;
-                stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
+                stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, defer, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
                 continue;
             }
         }
@@ -453,11 +462,20 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             Ray r;
             r.alive = false;
             r.w = 0.0;
+            double sigma_a = 0.0;
             if (valid) {
                 SrcLocal L;
                 source_local<FT, KN>(sc.source, id, L);
                 generate_geometry<FT, PhiloxDraws, KN, true>(sc.source, L, dr, r, s_sincos);
-                if (!lazy) r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
+                if (defer) {
+                    // normal line with a Doppler shift and / or a per-bundle sigma: the exact deviate (inverse normal
+                    // CDF, a second Philox block) is left to stage B; here the Doppler factor, and sigma for the pre-test
+                    const bool moving = L.vel.x != 0.0 || L.vel.y != 0.0 || L.vel.z != 0.0;
+                    r.w = moving ? 1.0 - dot(L.vel, r.d) : 1.0;
+                    sigma_a = L.wave_sigma;
+                } else if (!lazy) {
+                    r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
+                }
             }
             n_src += __popc(__ballot_sync(kFull, r.alive));
             for (int k = 0; k < split; ++k) {
@@ -474,7 +492,8 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             // Bragg pre-test (bragg_cull_general): enabled by xrt_scene_create for a spherical Bragg crystal
             // traced in global coordinates; the survivors take the exact path in stage B
             if (ops.cull_t2 > 0.0) {
-                if (cand && bragg_cull_general(sc.source, ops, !lazy, r.w, dr.wave_hi(), r.o, r.d)) {
+                const int mode = defer ? WAVE_DEFERRED : (lazy ? WAVE_APPROX : WAVE_EXACT);
+                if (cand && bragg_cull_general(sc.source, ops, mode, r.w, sigma_a, dr.wave_hi(), r.o, r.d)) {
                     cand = false;
                     r.alive = false;
                 }
@@ -634,6 +653,7 @@ struct XrtScene {
     int split;                      // first crystal of the train (0 if none): the kernel's re-pack point
     int lazy_wavelength;            // wavelength independent of the source direction: drawn at the crystal
     int need_wavelength;            // an optic at or after the split optic reads the wavelength (Bragg test / mosaic cutoff)
+    int defer_wavelength;           // eager normal line + Bragg pre-test: exact deviate drawn in stage B
     uint32_t known;                 // KN_* facts that hold for this scene (source + split optic)
     int device;
     int sm_count;
@@ -857,6 +877,7 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
     s->lazy_wavelength = (src.kind != XRT_SRC_BUNDLES && src.velocity_c[0] == 0.0 && src.velocity_c[1] == 0.0 &&
                           src.velocity_c[2] == 0.0) ? 1 : 0;
     s->need_wavelength = 0;
+    s->defer_wavelength = 0;
     for (int k = s->split; k < d.n_optics; ++k) {
         const XrtOpticDesc &o = d.optics[k];
         const bool crystal = o.interact == XRT_INTERACT_CRYSTAL || o.interact == XRT_INTERACT_MOSAIC;
@@ -892,6 +913,8 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
             const bool approx = s->lazy_wavelength && src.wave == XRT_WAVE_NORMAL;
             w.cull_err = (approx ? 2e-3 * std::fabs(src.wave_par[1]) * std::fabs(o.inv_two_d) : 0.0) + 1e-9;
             w.cull_inv_r = 1.0 / o.radius;
+            // eager normal line (plasma bundles, Doppler shift) with no optic before the crystal: defer the exact deviate
+            s->defer_wavelength = (!s->lazy_wavelength && src.wave == XRT_WAVE_NORMAL && s->split == 0) ? 1 : 0;
         }
     }
     return XRT_OK;
@@ -1018,7 +1041,7 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     PhiloxKeys pk;
     philox_round_keys(seed, stream_id, pk);
     kern<<<grid, kBlock, smem, (cudaStream_t)stream>>>(s->dev, pk, stream_id, ray_begin, ray_count, *out, s->split,
-                                                      s->lazy_wavelength | (s->need_wavelength << 1));
+                                                      s->lazy_wavelength | (s->need_wavelength << 1) | (s->defer_wavelength << 2));
     CU(cudaGetLastError());
     return XRT_OK;
 }

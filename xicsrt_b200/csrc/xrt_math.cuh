@@ -107,6 +107,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &K) {
 __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
     return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)((a << 20) | (b >> 12))) - 1.0;
 }
+// three uniforms of 42 bits each from one 128-bit block (a box of 1 m is resolved to 2e-13 m)
+__device__ __forceinline__ void u01_42x3(uint4 r, double &u0, double &u1, double &u2) {
+    u0 = __hiloint2double((int)(0x3ff00000u | (r.x >> 12)), (int)(((r.x & 0xfffu) << 20) | ((r.y >> 22) << 10))) - 1.0;
+    u1 = __hiloint2double((int)(0x3ff00000u | ((r.y >> 2) & 0xfffffu)), (int)(((r.y & 3u) << 30) | ((r.z >> 12) << 10))) - 1.0;
+    u2 = __hiloint2double((int)(0x3ff00000u | ((r.z & 0xfffu) << 8) | (r.w >> 24)), (int)((r.w & 0x00fffffcu) << 8)) - 1.0;
+}
 // 44 random bits: the low 12 bits of a and all of b
 __device__ __forceinline__ double u01_44(uint32_t a, uint32_t b) {
     return __hiloint2double((int)(0x3ff00000u | ((a & 0xfffu) << 8) | (b >> 24)), (int)(b << 8)) - 1.0;

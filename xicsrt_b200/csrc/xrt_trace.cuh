@@ -102,9 +102,7 @@ struct PhiloxDraws {
     }
     // ---- source sites
     __device__ __forceinline__ void origin_uniform(double u[3]) const {
-        double d;
-        pair(SITE_ORIGIN_XY, u[0], u[1]);
-        pair(SITE_ORIGIN_Z, u[2], d);
+        u01_42x3(raw(SITE_ORIGIN_XY), u[0], u[1], u[2]);     // one block: 3 x 42 bits
     }
     __device__ __forceinline__ void origin_gauss(const double sig[3], double off[3]) const {
         double a, b, c, d, z0, z1, z2, z3;
@@ -613,9 +611,9 @@ __device__ __forceinline__ float normal_approx(uint32_t hi, bool &usable) {
 
 // cos^2(min(theta_B, theta_i)) <= (1 - sI^2) + 2 |sB - sI|  (equality to first order when sB < sI), which
 // avoids the FP64 min / max selects.
-__device__ __forceinline__ bool bragg_cull_test(const XrtOpticDesc &op, double sB, double sI, bool usable) {
+__device__ __forceinline__ bool bragg_cull_test(const XrtOpticDesc &op, double sB, double sI, bool usable, double err) {
     const double gap = fabs(sB - sI);
-    const double diff = gap - op.cull_err;
+    const double diff = gap - err;
     const double c2 = fma(2.0, gap, fma(-sI, sI, 1.0));
     return usable & (diff > 0.0) & (diff * diff > op.cull_t2 * c2);
 }
@@ -625,20 +623,29 @@ __device__ __forceinline__ bool bragg_cull_sphere(const XrtSourceDesc &s, const 
     bool usable;
     const float z = normal_approx(wave_hi, usable);
     const double sB = fma((double)z, s.wave_par[1], s.wave_par[0]) * op.inv_two_d;
-    return bragg_cull_test(op, sB, thc * op.cull_inv_r, usable);
+    return bragg_cull_test(op, sB, thc * op.cull_inv_r, usable, op.cull_err);
 }
 
-// general form for a sphere traced in global coordinates: X = intersection point, d = unit direction;
-// `lambda` is the ray's wavelength when it is already drawn (eager), else the approximation is used
-__device__ __forceinline__ bool bragg_cull_general(const XrtSourceDesc &s, const XrtOpticDesc &op, bool have_lambda,
-                                                   double lambda, uint32_t wave_hi, V3 X, V3 d) {
+// general form for a sphere traced in global coordinates: X = intersection point, d = unit direction.
+//   WAVE_EXACT    `lambda` is the ray's wavelength, already drawn
+//   WAVE_APPROX   constant or normal line of the source, deviate from normal_approx (lazy wavelength)
+//   WAVE_DEFERRED plasma bundle / Doppler-shifted normal line whose exact deviate is left to stage B:
+//                 `lambda` holds the Doppler factor 1 - v.D / c and `sigma` the line's sigma for this ray
+enum { WAVE_EXACT = 0, WAVE_APPROX = 1, WAVE_DEFERRED = 2 };
+__device__ __forceinline__ bool bragg_cull_general(const XrtSourceDesc &s, const XrtOpticDesc &op, int mode,
+                                                   double lambda, double sigma, uint32_t wave_hi, V3 X, V3 d) {
     bool usable = true;
-    if (!have_lambda) {
+    double err = op.cull_err;
+    if (mode == WAVE_APPROX) {
         lambda = s.wave_par[0];
         if (s.wave == XRT_WAVE_NORMAL) lambda = fma((double)normal_approx(wave_hi, usable), s.wave_par[1], lambda);
+    } else if (mode == WAVE_DEFERRED) {
+        lambda *= fma((double)normal_approx(wave_hi, usable), sigma, s.wave_par[0]);
+        err = fma(2e-3 * fabs(sigma), fabs(op.inv_two_d), err);       // |z32 - z| < 2e-3, Doppler factor <= 2
+        err += err;
     }
     const double sI = fabs(dot(d, v3(op.center) - X)) * op.cull_inv_r;
-    return bragg_cull_test(op, lambda * op.inv_two_d, sI, usable);
+    return bragg_cull_test(op, lambda * op.inv_two_d, sI, usable, err);
 }
 
 // true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).
