@@ -222,6 +222,8 @@ def run_gpu_arm(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     import ctypes as C

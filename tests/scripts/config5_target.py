@@ -3,7 +3,7 @@
 BASELINE.json configs[4] / SURVEY.md section 8d config 5 at full size, under torchrun on N GPUs:
 XicsrtPlasmaCubic (1e5 bundles, Poisson counts) -> spherical Bragg crystal -> detector, 1e10 rays
 in one iteration sharded by ray id over the ranks, history off, images + counters reduced over
-NCCL; then the history of ray ids < 1e6 (every element) replayed on rank 0.
+NCCL; then the history of a 1e6-ray strided subsample of the ids (every element) replayed on rank 0.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         tests/scripts/config5_target.py [--rays 1e10] [--steps 3]
@@ -37,6 +37,8 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     import bench
     from xicsrt_b200 import _driver, config as xconfig
@@ -72,8 +74,9 @@ def main():
 
     out = None
     if rank == 0:
+        # a strided subsample of the whole id range (consecutive ids would all come from the first few bundles)
         n_hist = int(min(args.history, tracer.n_rays))
-        ids = torch.arange(n_hist, dtype=torch.int64, device=dev)
+        ids = torch.arange(n_hist, dtype=torch.int64, device=dev) * (tracer.n_rays // n_hist)
         rays, mask = tracer.history(args.steps, ids)          # warm-up
         torch.cuda.synchronize()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

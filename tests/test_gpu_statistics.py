@@ -179,7 +179,8 @@ def test_runs_use_cumulative_seeds_and_combine(torch):
 
 @pytest.mark.parametrize('name', ['sphere', 'sphere_step_box', 'apertures', 'mosaic_sphere', 'torus_bragg',
                                   'local_frames', 'plane_mirror', 'sphere_voigt', 'mesh_torus', 'mesh_user_flat',
-                                  'mesh_mosaic', 'plasma_toroidal'])
+                                  'mesh_mosaic', 'plasma_toroidal', 'plasma_cubic_poisson', 'plasma_voigt',
+                                  'sphere_mirror_convex'])
 def test_fused_kernel_equals_replay_kernel(torch, name):
     """
     The staged fused kernel (queues, lazy wavelength) and the straight per-ray replay kernel
@@ -311,3 +312,34 @@ def test_fused_iterations_equal_separate_iterations(torch):
     for elem in ('crystal', 'detector'):
         assert np.array_equal(res['total']['image'][elem], one['total']['image'][elem])
     assert res['found']['history'] == {} and res['lost']['history'] == {}
+
+
+@pytest.mark.parametrize('name', ['sphere', 'sphere_step_box', 'plasma_cubic_poisson', 'plasma_toroidal', 'plasma_voigt'])
+def test_bragg_pretest_changes_no_result(torch, name, monkeypatch):
+    """
+    The conservative Bragg pre-test of the fused kernel (bragg_cull_* in csrc/xrt_trace.cuh: approximate,
+    exact and deferred wavelength modes; Gaussian and step rocking curves) only skips work: counters,
+    images and the found set are identical with the test switched off (XRT_NO_CULL, read at scene creation).
+    """
+    from xicsrt_b200 import _driver, config as xconfig
+    cfg = scenes.get(name)
+    if name.startswith('plasma'):
+        cfg['sources']['source']['time_resolution'] *= 3000
+    else:
+        cfg['sources']['source']['intensity'] = 3000000
+    results = []
+    for no_cull in (False, True):
+        if no_cull:
+            monkeypatch.setenv('XRT_NO_CULL', '1')
+        else:
+            monkeypatch.delenv('XRT_NO_CULL', raising=False)
+        tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), seed=2025)
+        found, lost = tracer.select_ids(3, 100)
+        meta, image = tracer.counts_and_images(True)
+        results.append((tracer.n_rays, meta, image, np.sort(found.cpu().numpy())))
+        tracer.close()
+    (n0, meta0, image0, found0), (n1, meta1, image1, found1) = results
+    assert n0 == n1 > 1000000 and meta0 == meta1
+    assert meta0['detector'] > 500 and np.array_equal(found0, found1)
+    for elem, img in image0.items():
+        assert (img is None and image1[elem] is None) or np.array_equal(img, image1[elem])
