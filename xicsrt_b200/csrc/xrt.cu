@@ -763,6 +763,7 @@ static uint32_t scene_features(const XrtSceneDesc &d) {
     }
     // compiled variants: lean spectrometer, all analytic features, lean mesh, everything
     if (ft == 0) return 0;
+    if (ft == FT_MOSAICLEAN || ft == FT_SRCLEAN) return ft;     // one extra feature: far less code than FT_MID
     if ((ft & ~FT_MID) == 0) return FT_MID;
     if ((ft & ~FT_MESHLEAN) == 0) return FT_MESHLEAN;
     return FT_FULL;
@@ -981,6 +982,14 @@ static TraceKernel trace_kernel(const XrtScene *s, size_t *smem) {
         *smem = block_smem_bytes<FT_MID>();
         return trace_kernel_ft<FT_MID>(s->split);
     }
+    if (s->features == FT_MOSAICLEAN) {
+        *smem = block_smem_bytes<FT_MOSAICLEAN>();
+        return s->split == 0 ? k_trace<FT_MOSAICLEAN, 0, 0> : k_trace<FT_MOSAICLEAN, -1, 0>;
+    }
+    if (s->features == FT_SRCLEAN) {
+        *smem = block_smem_bytes<FT_SRCLEAN>();
+        return s->split == 0 ? k_trace<FT_SRCLEAN, 0, 0> : k_trace<FT_SRCLEAN, -1, 0>;
+    }
     if (s->features == FT_MESHLEAN) {
         *smem = block_smem_bytes<FT_MESHLEAN>();
         return trace_kernel_ft<FT_MESHLEAN>(s->split);
@@ -1071,6 +1080,10 @@ static int launch_record(XrtScene *s, uint64_t seed, uint64_t stream_id, const u
         k_record<0, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == FT_MID)
         k_record<FT_MID, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+    else if (s->features == FT_MOSAICLEAN)
+        k_record<FT_MOSAICLEAN, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
+    else if (s->features == FT_SRCLEAN)
+        k_record<FT_SRCLEAN, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else if (s->features == FT_MESHLEAN)
         k_record<FT_MESHLEAN, MODE><<<grid, kBlock, 0, st>>>(s->dev, pk, stream_id, ids, ray_begin, n, in, inj, out, hist, s->split);
     else

@@ -27,6 +27,8 @@ enum : uint32_t {
     FT_MID = FT_LOCAL | FT_CYL | FT_TORUS | FT_APERTURE | FT_MOSAIC | FT_ROCKTAB | FT_SRC_EXT,
     FT_FULL = FT_MID | FT_MESH,
     FT_MESHLEAN = FT_MESH | FT_LOCAL,   // mesh optics (traced in local coordinates) + plane / sphere, box source
+    FT_MOSAICLEAN = FT_MOSAIC,          // mosaic crystal + plane / sphere, box source (config 3)
+    FT_SRCLEAN = FT_SRC_EXT,            // plasma bundles / extended sources + plane / sphere (config 5)
 };
 
 // Known-structure mask KN: facts about the source and the split optic that a pre-instantiated
