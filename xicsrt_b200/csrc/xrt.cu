@@ -293,7 +293,9 @@ __device__ __forceinline__ void stage_b1(const XrtSceneDesc &sc, const XrtOpticD
 // mesh variants keep many more values live (face loops, Clough-Tocher cubics): 2 blocks / SM
 template <uint32_t FT, int SPLIT, uint32_t KN>
 // the spectrometer variant runs two ray groups per pass (independent chains): 119 registers, 2 blocks / SM
-__global__ void __launch_bounds__(kBlock, (((FT & FT_MESH) != 0 || ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
+// ... as does the lean extended-source variant (bundle lookup + focused cone basis: 116 registers, no spills)
+__global__ void __launch_bounds__(kBlock, (((FT & FT_MESH) != 0 || FT == FT_SRCLEAN ||
+                                            ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
                                            XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS)
 k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
         const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const int split_rt,

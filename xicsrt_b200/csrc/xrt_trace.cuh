@@ -676,6 +676,9 @@ __device__ __forceinline__ bool bragg_pass(const XrtOpticDesc &op, int k, int la
         if (!(dth == dth)) return false;
     }
     p *= op.reflectivity;
+    // p == 0 (outside a step curve or a table): only a uniform that is exactly 0 passes `p >= u`; as for the
+    // Gaussian tail above, Philox draws never do (the Bragg pre-test relies on it), injected draws are compared
+    if (!MOSAIC && p == 0.0) return dr.bragg_u_is_zero(k, layer);
     if constexpr (MOSAIC) return p >= dr.mosaic_u(k, layer);
     else return p >= dr.bragg_u(k, layer);
 }
