@@ -34,6 +34,9 @@ namespace xrt {
 #ifndef XRT_MIN_BLOCKS
 #define XRT_MIN_BLOCKS 3
 #endif
+#ifndef XRT_RECORD_BLOCKS
+#define XRT_RECORD_BLOCKS 3
+#endif
 constexpr int kBlock = XRT_BLOCK;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -546,7 +549,7 @@ enum { REC_PHILOX = 0, REC_INJECT = 1 };
 
 // KN != 0: the scene has the known structure (split optic = optic 0), see k_trace
 template <uint32_t FT, int MODE, uint32_t KN = 0>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, (FT & FT_MESH) != 0 ? 2 : XRT_RECORD_BLOCKS)   // 3 x 256 at 78 registers: the replay is latency bound
 k_record(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
          const uint64_t *__restrict__ ids, const uint64_t ray_begin, const uint64_t n,
          const XrtRaysIn in, const XrtInject inj, const XrtOutputs out, const XrtHistory hist, const int split) {
