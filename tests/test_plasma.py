@@ -76,6 +76,39 @@ def test_bundle_table_matches_reference_ray_counts(golden_dir, name):
     assert C.sizeof(L.XrtBundle) == b['table'].dtype.itemsize
 
 
+def test_linewidth_and_cone_models_of_the_bundle_sources():
+    """Host side of the per-bundle Voigt tables and cone parameters (xicsrt_b200/plasma.py)."""
+    _, sname, sparam, sfilters, optics = prepared('plasma_voigt')
+    assert plasma.line_model(sparam) == 'table'
+    seed = scenes.get('plasma_voigt')['general']['random_seed']
+    b = plasma.build_bundles(sparam, sfilters, StreamAdapter(LegacyStream(seed)))
+    n = len(b['end'])
+    assert b['voigt_x'].shape == (n, plasma.N_TABLE) and b['voigt_cdf'].shape == (n, plasma.N_TABLE)
+    gamma = voigt.natural_gamma(sparam['linewidth'], sparam['wavelength'])
+    temp = b['props']['temperature'][b['counts'] > 0]
+    assert len(np.unique(temp)) > 5                                   # a different table per bundle
+    for row in (0, n // 2, n - 1):
+        sigma = voigt.doppler_sigma(temp[row], sparam['mass_number'], sparam['wavelength'])
+        assert np.isclose(b['table']['wave_sigma'][row], sigma, rtol=1e-14)
+        x, cdf = voigt.cdf_table(gamma, float(sigma))
+        assert np.array_equal(b['voigt_x'][row], x) and np.array_equal(b['voigt_cdf'][row], cdf)
+    # T == 0 with a natural linewidth is given 1 eV (_XicsrtSourceGeneric.py:333-339); without one sigma = 0
+    assert np.isclose(plasma.bundle_sigma(sparam, [0.0])[0], voigt.doppler_sigma(1.0, sparam['mass_number'], sparam['wavelength']))
+    assert plasma.bundle_sigma(dict(sparam, linewidth=0.0), [0.0])[0] == 0.0
+    assert plasma.line_model(dict(sparam, wavelength_dist='monochrome')) == 'const'
+    # cone parameter per distribution (include/xrt.h: XrtBundle.cos_spread)
+    s = np.array([0.05, 0.1])
+    for name, fn in (('isotropic', np.cos), ('flat', np.tan), ('flat_xy', np.tan), ('isotropic_xy', np.sin)):
+        assert np.array_equal(plasma.cone_parameter(name, s), fn(s))
+    with pytest.raises(NotImplementedError):
+        plasma.cone_kind(dict(sparam, angular_dist='gaussian'))
+    for name in ('plasma_flat', 'plasma_flat_xy', 'plasma_isotropic_xy'):
+        _, _, sp, sf, _ = prepared(name)
+        bb = plasma.build_bundles(sp, sf, StreamAdapter(LegacyStream(1)))
+        kind = plasma.cone_kind(sp)
+        assert np.array_equal(bb['table']['cos_spread'], plasma.cone_parameter(kind, bb['props']['spread'][bb['counts'] > 0]))
+
+
 def test_poisson_counts_and_limits():
     _, sname, sparam, sfilters, optics = prepared('plasma_cubic_poisson')
     from xicsrt_b200._driver import HostRandom
