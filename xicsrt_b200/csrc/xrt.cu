@@ -61,6 +61,8 @@ constexpr unsigned kFull = 0xffffffffu;
 // another: only __syncwarp and warp-uniform queue counters.
 
 constexpr int kQ1Cap = 64;     // stage A pushes <= 32 per pass, stage B pops 32 when >= 32 are queued
+constexpr int kQaCap = 64;     // mesh variants: rays that hit the coarse mesh (id, coarse hit point), between the halves of stage A
+constexpr int kQaPlanes = 4;
 #ifndef XRT_UNROLL
 #define XRT_UNROLL 2
 #endif
@@ -76,14 +78,15 @@ template <uint32_t FT> __host__ __device__ constexpr int q1_planes() {
     return 7 + (FT != 0 ? 1 : 0) + ((FT & FT_MESH) != 0 ? 3 : 0);
 }
 template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int q1_doubles() {
-    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1PlanesSpectro * (kQ1CapSpectro + kQbCap) : q1_planes<FT>() * kQ1Cap;
+    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1PlanesSpectro * (kQ1CapSpectro + kQbCap)
+                                                        : q1_planes<FT>() * kQ1Cap + ((FT & FT_MESH) != 0 ? kQaPlanes * kQaCap : 0);
 }
 template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int warp_queue_doubles() {
     return q1_doubles<FT, KN>() + kQ2Planes * kQ2Cap;
 }
 
 // shared-memory copy of the step-1 face operands of a mesh split optic (<= kStageFaces faces)
-constexpr int kStageFaces = 256;
+constexpr int kStageFaces = 128;
 template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr size_t block_smem_bytes() {
     return ((size_t)(XRT_BLOCK / 32) * warp_queue_doubles<FT, KN>() + ((FT & FT_MESH) != 0 ? 9 * kStageFaces : 0)) * sizeof(double);
 }
@@ -345,9 +348,19 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
         }
         __syncthreads();
     }
+    constexpr bool SPECTRO_K = (KN & KN_SPECTROMETER) == KN_SPECTROMETER;
     int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
     int nb = 0;             // spectrometer variant: queue b (inside the bounds), after the planes of queue 1
     double *qb = q1 + kQ1PlanesSpectro * kQ1CapSpectro;
+    // mesh variants: queue a (coarse-mesh hits) after the planes of queue 1.  Stage A is split in two when the split
+    // optic is the first optic, a refining mesh, and the wavelength is lazy (a ray is rebuilt from its id in stage A2)
+    int na = 0;
+    double *qa = q1 + q1_planes<FT>() * kQ1Cap;
+    bool mesh_staged = false;
+    if constexpr ((FT & FT_MESH) != 0 && !SPECTRO_K) {
+        mesh_staged = split == 0 && ops.shape == XRT_SHAPE_MESH && (ops.flags & XRT_F_MESH_REFINE) && lazy &&
+                      sc.source.kind != XRT_SRC_BUNDLES && sc.source.cone != XRT_CONE_ISOTROPIC_XY;
+    }
     unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
 
     // Ray ids in groups of 32: group g = warp_global + it * n_warps belongs to this warp at iteration it.
@@ -367,7 +380,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     uint32_t it = 0;
     for (;;) {
         const bool more = it < n_it;
-        if (n2 >= 32 || (!more && n1 == 0 && nb == 0 && n2 > 0)) {
+        if (n2 >= 32 || (!more && n1 == 0 && nb == 0 && na == 0 && n2 > 0)) {
             const int cnt = n2 < 32 ? n2 : 32;
             n2 -= cnt;
             stage_c<FT>(sc, out, c, split, pk, stream_id, q2, n2, cnt);
@@ -387,11 +400,54 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
                 continue;
             }
         } else {
-            if (n1 >= 32 || (!more && n1 > 0)) {
+            if (n1 >= 32 || (!more && na == 0 && n1 > 0)) {
                 const int cnt = n1 < 32 ? n1 : 32;
                 n1 -= cnt;
                 stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, defer, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
                 continue;
+            }
+            if constexpr ((FT & FT_MESH) != 0) {
+                if (na >= 32 || (!more && na > 0)) {
+                    // ---- stage A2: the coarse-mesh hits, re-packed: rebuild the ray from its id, finish the mesh
+                    // intersection from the coarse hit point (nearest vertex, candidate faces, interpolation), bounds
+                    const int cnt = na < 32 ? na : 32;
+                    na -= cnt;
+                    const bool active = (int)c.lane < cnt;
+                    uint64_t id = 0;
+                    V3 Xc = nan3();
+                    if (active) {
+                        const double *p = qa + na + c.lane;
+                        id = (uint64_t)__double_as_longlong(p[0]);
+                        Xc = v3(p[1 * kQaCap], p[2 * kQaCap], p[3 * kQaCap]);
+                    }
+                    __syncwarp();
+                    PhiloxDraws dr;
+                    dr.init(pk, stream_id, id, split);
+                    Ray r;
+                    r.alive = false;
+                    r.w = 0.0;
+                    V3 n = v3(0.0, 0.0, 1.0);
+                    bool cand = false;
+                    if (active) {
+                        SrcLocal L;
+                        source_local<FT, KN>(sc.source, id, L);
+                        generate_geometry<FT, PhiloxDraws, KN, true>(sc.source, L, dr, r, s_sincos);
+                        cand = optic_geometry<FT, true, KN>(ops, r, n, staged, &Xc) == HIT_INSIDE;
+                    }
+                    emit_lost(out, c, dr, active && !cand, id);
+                    const unsigned m = __ballot_sync(kFull, cand);
+                    if (cand) {
+                        double *p = q1 + n1 + __popc(m & c.lt_mask);
+                        p[0] = __longlong_as_double((long long)id);
+                        p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
+                        p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
+                        p[7 * P] = r.w;
+                        p[8 * P] = n.x; p[9 * P] = n.y; p[10 * P] = n.z;
+                    }
+                    n1 += __popc(m);
+                    __syncwarp();
+                    continue;
+                }
             }
         }
         if (!more) break;
@@ -493,6 +549,31 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             }
             V3 n = v3(0.0, 0.0, 1.0);
             bool cand = false;
+            if constexpr ((FT & FT_MESH) != 0) {
+                if (mesh_staged) {
+                    // ---- stage A1: coarse mesh only; the hits go to queue a as (id, coarse hit point)
+                    V3 Xc = nan3();
+                    bool hit = false;
+                    if (r.alive) {
+                        V3 o = r.o, d = r.d;
+                        if (optic_is_local<FT>(ops)) {
+                            o = to_local(ops.orient, o - v3(ops.origin));
+                            d = to_local(ops.orient, d);
+                        }
+                        hit = mesh_coarse_hit(ops, o, d, Xc, staged);
+                    }
+                    emit_lost(out, c, dr, valid && !hit, id);
+                    const unsigned mh = __ballot_sync(kFull, hit);
+                    if (hit) {
+                        double *p = qa + na + __popc(mh & c.lt_mask);
+                        p[0] = __longlong_as_double((long long)id);
+                        p[1 * kQaCap] = Xc.x; p[2 * kQaCap] = Xc.y; p[3 * kQaCap] = Xc.z;
+                    }
+                    na += __popc(mh);
+                    __syncwarp();
+                    continue;
+                }
+            }
             if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
             // Bragg pre-test (bragg_cull_general): enabled by xrt_scene_create for a spherical Bragg crystal
             // traced in global coordinates; the survivors take the exact path in stage B

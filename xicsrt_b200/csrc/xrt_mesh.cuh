@@ -198,8 +198,20 @@ __device__ __forceinline__ int mesh_stage1_faces(const XrtOpticDesc &op, const d
 
 // ShapeMesh.intersect (:135-170).  o, d in the optic's tracing frame.  `staged` (optional) is a
 // shared-memory copy of the step-1 face operands.
-__device__ __forceinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
-                                               const double *staged = nullptr) {
+// The coarse step alone (step 1 of a refining mesh): true = some coarse face is hit, Xc = the hit point.
+// The fused kernel runs it for every ray, re-packs the ~half that hit and resumes mesh_intersect with Xc.
+__device__ __forceinline__ bool mesh_coarse_hit(const XrtOpticDesc &op, V3 o, V3 d, V3 &Xc, const double *staged = nullptr) {
+    const double *geom;
+    const int n1 = mesh_stage1_faces(op, geom);
+    Xc = nan3();
+    const int face = staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
+    return face >= 0;
+}
+
+// Not inlined: the fused kernel reaches it from four places (optics before / at / after the split optic, stage A2)
+// and four inlined copies made the mesh variants 250 kB of code -- instruction-cache stalls of 4.5 cycles per issue.
+__device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
+                                            const double *staged = nullptr, const V3 *resume_Xc = nullptr) {
     const XrtMesh &m = *op.mesh;
     X = nan3();
     n = nan3();
@@ -210,7 +222,12 @@ __device__ __forceinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 
         face = staged ? mesh_all_faces<true>(staged, n1, o, d, X) : mesh_all_faces<false>(geom, n1, o, d, X);
     } else {
         V3 Xc = nan3();
-        face = staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
+        if (resume_Xc) {        // coarse step already done (mesh_coarse_hit): a coarse face was hit at *resume_Xc
+            Xc = *resume_Xc;
+            face = 0;
+        } else {
+            face = staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
+        }
         if (face >= 0) {
             const int vert = mesh_nearest_vertex(m, Xc);
             face = (vert >= 0) ? mesh_candidate_faces(m, vert, o, d, X) : -1;

@@ -801,7 +801,8 @@ __device__ __forceinline__ void frame_to_external(const XrtOpticDesc &op, bool l
 }
 
 template <uint32_t FT, bool WANT_NORMAL, uint32_t KN = 0>
-__device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3 &n, const double *staged_mesh = nullptr) {
+__device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3 &n, const double *staged_mesh = nullptr,
+                                              const V3 *mesh_resume = nullptr) {
     V3 o = r.o, d = r.d;
     const uint32_t flags = flags_of<KN>(op);
     const bool local = optic_is_local<FT>(op);
@@ -819,7 +820,7 @@ __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3
     if constexpr ((FT & FT_MESH) != 0) {
         if (shape_of<KN>(op) == XRT_SHAPE_MESH) {
             analytic = false;
-            ok = mesh_intersect(op, o, d, X, n, staged_mesh);
+            ok = mesh_intersect(op, o, d, X, n, staged_mesh, mesh_resume);
         }
     }
     if (analytic) {
