@@ -296,10 +296,10 @@ __device__ __forceinline__ void stage_b1(const XrtSceneDesc &sc, const XrtOpticD
     __syncwarp();
 }
 
-// mesh variants keep many more values live (face loops, Clough-Tocher cubics): 2 blocks / SM
+// Resident blocks per SM: 2 for the mesh variants (face loops and Clough-Tocher cubics keep many values live), for
+// the spectrometer variant (two ray groups per pass = two independent chains: 118 registers, no spills) and for the
+// lean extended-source variant (bundle lookup + focused cone basis: 116 registers, no spills); 3 otherwise.
 template <uint32_t FT, int SPLIT, uint32_t KN>
-// the spectrometer variant runs two ray groups per pass (independent chains): 119 registers, 2 blocks / SM
-// ... as does the lean extended-source variant (bundle lookup + focused cone basis: 116 registers, no spills)
 __global__ void __launch_bounds__(kBlock, (((FT & FT_MESH) != 0 || FT == FT_SRCLEAN ||
                                             ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
                                            XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS)
