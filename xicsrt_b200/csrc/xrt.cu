@@ -970,8 +970,9 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         const bool crystal = o.interact == XRT_INTERACT_CRYSTAL || o.interact == XRT_INTERACT_MOSAIC;
         if (crystal && (o.flags & (XRT_F_CHECK_BRAGG | XRT_F_MOSAIC_CUTOFF))) s->need_wavelength = 1;
     }
-    // the lean variant has no wavelength plane in its queue: a source with a Doppler shift needs the full one
-    if (s->features == 0 && !s->lazy_wavelength) s->features = FT_MID;
+    // the lean variant has no wavelength plane in its queue: a source with a Doppler shift takes the lean
+    // extended-source variant
+    if (s->features == 0 && !s->lazy_wavelength) s->features = FT_SRCLEAN;
     s->known = 0;
     if (d.n_optics > 0) {
         const XrtOpticDesc &o = d.optics[s->split];
