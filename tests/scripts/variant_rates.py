@@ -19,6 +19,6 @@ run(cfg, 'point source (spectrometer variant)')
 cfg = bench.spectrometer(n); cfg['sources']['source'].update({'xsize': 1e-3, 'ysize': 1e-3, 'zsize': 1e-3})
 run(cfg, 'box source 1 mm (generic lean)')
 cfg = bench.spectrometer(n); cfg['optics']['crystal']['rocking_type'] = 'step'
-run(cfg, 'step rocking curve (generic lean)')
+run(cfg, 'step rocking curve (spectrometer variant)')
 cfg = bench.spectrometer(n); cfg['sources']['source']['velocity'] = [0.0, 0.0, 1e4]
-run(cfg, 'Doppler-shifted line (all-features variant, deferred deviate)')
+run(cfg, 'Doppler-shifted line (lean extended-source variant, deferred deviate)')

@@ -982,7 +982,8 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         if (o.shape == XRT_SHAPE_SPHERE && !(o.flags & XRT_F_CONVEX)) s->known |= KN_SPHERE;
         const uint32_t size_bits = XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE | XRT_F_HAS_ZSIZE;
         if ((o.flags & size_bits) == (XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE)) s->known |= KN_BOUNDS_XY;
-        if (o.interact == XRT_INTERACT_CRYSTAL && (o.flags & XRT_F_CHECK_BRAGG) && o.rocking_type == XRT_ROCK_GAUSS)
+        if (o.interact == XRT_INTERACT_CRYSTAL && (o.flags & XRT_F_CHECK_BRAGG) &&
+            (o.rocking_type == XRT_ROCK_GAUSS || o.rocking_type == XRT_ROCK_STEP))
             s->known |= KN_CRYSTAL_GAUSS;
         if (o.flags & XRT_F_IMAGE) s->known |= KN_IMAGE;
         // parameters of the Bragg pre-test (bragg_cull_* in xrt_trace.cuh): a spherical Bragg crystal with a
