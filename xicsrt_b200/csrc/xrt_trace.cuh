@@ -622,12 +622,33 @@ __device__ __forceinline__ bool bragg_cull_test(const XrtOpticDesc &op, double s
     return usable & (diff > 0.0) & (diff * diff > op.cull_t2 * c2);
 }
 
-// sphere hit from a point source: sI = |D.n| = thc / R, the half chord of hit_sphere over the radius (|D| = 1)
-__device__ __forceinline__ bool bragg_cull_sphere(const XrtSourceDesc &s, const XrtOpticDesc &op, uint32_t wave_hi, double thc) {
+// sphere hit from a point source: sI = |D.n| = thc / R, the half chord of hit_sphere over the radius (|D| = 1).
+// Also hands back the two numbers of the bound, gap = |sB - sI| (-1 when the approximate deviate is not usable) and
+// c2 >= cos^2(min angle), for the second, uniform-dependent test of stage B1 (bragg_cull_uniform).
+__device__ __forceinline__ bool bragg_cull_sphere(const XrtSourceDesc &s, const XrtOpticDesc &op, uint32_t wave_hi, double thc,
+                                                  double &gap_out, double &c2_out) {
     bool usable;
     const float z = normal_approx(wave_hi, usable);
     const double sB = fma((double)z, s.wave_par[1], s.wave_par[0]) * op.inv_two_d;
-    return bragg_cull_test(op, sB, thc * op.cull_inv_r, usable, op.cull_err);
+    const double sI = thc * op.cull_inv_r;
+    const double gap = fabs(sB - sI);
+    const double diff = gap - op.cull_err;
+    const double c2 = fma(2.0, gap, fma(-sI, sI, 1.0));
+    gap_out = usable ? gap : -1.0;
+    c2_out = c2;
+    return usable & (diff > 0.0) & (diff * diff > op.cull_t2 * c2);
+}
+
+// Second level of the pre-test, for a Gaussian rocking curve, once the ray's rocking-curve uniform u is known:
+// the ray is reflected iff exp(-x) reflectivity >= u, x = dtheta^2 / 2 sigma^2, i.e. iff x <= ln(reflectivity / u).
+// With the lower bound on |dtheta| of the first level, x >= (gap - err)^2 / (c2 two_sigma2); if that exceeds
+// ln(reflectivity / u) (taken 1e-3 + 0.1 % too large: FP32 logarithm of a rounded u) the ray is lost.
+// u = 0 gives an infinite bound: never rejected here.
+__device__ __forceinline__ bool bragg_cull_uniform(const XrtOpticDesc &op, double gap, double c2, double u) {
+    const float lim = 0.6931471805599453f * (lg2_approx((float)op.reflectivity) - lg2_approx((float)u));   // ln(refl / u)
+    const double bound = (double)fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * op.rock_two_sigma2;   // on dtheta^2
+    const double diff = gap - op.cull_err;
+    return (diff > 0.0) & (diff * diff > bound * c2) & (lim == lim);
 }
 
 // general form for a sphere traced in global coordinates: X = intersection point, d = unit direction.
