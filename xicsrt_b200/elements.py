@@ -28,9 +28,16 @@ from . import registry
 log = logging.getLogger('xicsrt_b200')
 
 
+def cross3(a, b):
+    """np.cross for two 3-vectors with the same operations in the same order (bit-identical), ten times cheaper."""
+    a0, a1, a2 = float(a[0]), float(a[1]), float(a[2])
+    b0, b1, b2 = float(b[0]), float(b[1]), float(b[2])
+    return np.array([a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0])
+
+
 def default_xaxis(zaxis):
     """cross([0,0,1], zaxis) normalised, or [1,0,0] when that vanishes."""
-    xaxis = np.cross(np.array([0.0, 0.0, 1.0]), zaxis)
+    xaxis = cross3((0.0, 0.0, 1.0), zaxis)
     if not np.all(xaxis == 0.0):
         xaxis = xaxis / np.linalg.norm(xaxis)
     else:
@@ -68,7 +75,7 @@ def _setup_geometry(param):
         param['xaxis'] = np.array(param['xaxis'], dtype=np.float64)
     xaxis, zaxis = param['xaxis'], param['zaxis']
     # rows are x, y = z cross x, z
-    param['orientation'] = np.array([xaxis, np.cross(zaxis, xaxis), zaxis])
+    param['orientation'] = np.array([xaxis, cross3(zaxis, xaxis), zaxis])
     return param
 
 

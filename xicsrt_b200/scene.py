@@ -68,15 +68,21 @@ def _four(spread):
     raise Exception('Spread must have 1, 2 or 3 elements. See docstring.')
 
 
+def _norm3(v):
+    """np.linalg.norm(v[None, :], axis=1)[0] for a 3-vector: the same sum order, bit-identical."""
+    return np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+
+
 def cone_basis(axis, xaxis, zaxis):
-    """Rows (o_2, o_1, axis) of the cone frame, _XicsrtSourceGeneric.py:282-292."""
-    axis = np.asarray(axis, dtype=np.float64)[None, :]
-    axis = axis / np.linalg.norm(axis, axis=1)[:, None]
-    o1 = np.cross(axis, xaxis) + np.cross(axis, zaxis)
-    o1 /= np.linalg.norm(o1, axis=1)[:, None]
-    o2 = np.cross(axis, o1)
-    o2 /= np.linalg.norm(o2, axis=1)[:, None]
-    return np.concatenate([o2, o1, axis], axis=0)
+    """Rows (o_2, o_1, axis) of the cone frame, _XicsrtSourceGeneric.py:282-292 (norms over axis 1 there)."""
+    from .elements import cross3
+    axis = np.asarray(axis, dtype=np.float64)
+    axis = axis / _norm3(axis)
+    o1 = cross3(axis, xaxis) + cross3(axis, zaxis)
+    o1 /= _norm3(o1)
+    o2 = cross3(axis, o1)
+    o2 /= _norm3(o2)
+    return np.stack([o2, o1, axis])
 
 
 def _fill_cone(src, name, spread):
