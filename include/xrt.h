@@ -264,6 +264,9 @@ typedef struct XrtSceneDesc {
     int32_t n_optics;
     XrtSourceDesc source;
     XrtOpticDesc optics[XRT_MAX_OPTICS];
+    /* single-precision constants of the spectrometer variant's FP32 broad phase (k_trace stage A32);
+       filled in by xrt_scene_create, input values are ignored.  kn32[0] > 0 enables it. */
+    float kn32[32];
 } XrtSceneDesc;
 
 typedef struct XrtScene XrtScene;   /* opaque; one per device context */

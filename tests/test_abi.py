@@ -68,7 +68,7 @@ int main(void) {
     O(XrtSourceDesc, axis_basis); O(XrtSourceDesc, cone_par); O(XrtSourceDesc, wave_par); O(XrtSourceDesc, n_table);
     O(XrtSourceDesc, table_cdf); O(XrtSourceDesc, sightlines); O(XrtSourceDesc, n_bundles); O(XrtSourceDesc, voxel_size); O(XrtSourceDesc, bundle_x); O(XrtSourceDesc, bundle_hint_shift);
     O(XrtPlasmaDesc, cone); O(XrtPlasmaDesc, origin); O(XrtPlasmaDesc, inject_u); O(XrtPlasmaDesc, sightlines);
-    O(XrtSceneDesc, source); O(XrtSceneDesc, optics);
+    O(XrtSceneDesc, source); O(XrtSceneDesc, optics); O(XrtSceneDesc, kn32);
     O(XrtMesh, n_tri); O(XrtMesh, grid_nx); O(XrtMesh, grid_x0); O(XrtMesh, vgrid_items);
     O(XrtOutputs, found_capacity); O(XrtOutputs, lost_threshold);
     return 0;

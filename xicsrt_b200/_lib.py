@@ -116,7 +116,7 @@ class XrtSourceDesc(C.Structure):
 
 class XrtSceneDesc(C.Structure):
     _fields_ = [('version', C.c_int32), ('n_optics', C.c_int32), ('source', XrtSourceDesc),
-                ('optics', XrtOpticDesc * MAX_OPTICS)]
+                ('optics', XrtOpticDesc * MAX_OPTICS), ('kn32', C.c_float * 32)]
 
 
 class XrtOutputs(C.Structure):

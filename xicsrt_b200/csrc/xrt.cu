@@ -70,6 +70,7 @@ constexpr int kUnroll = XRT_UNROLL;   // spectrometer variant: groups of 32 rays
 constexpr int kQ1CapSpectro = 32 * (kUnroll + 1);
 constexpr int kQ1PlanesSpectro = 7;   // id, direction, distance, and the two numbers of the pre-test bound (gap, c2)
 constexpr int kQbPlanes = 5;          // id, direction, distance
+constexpr int kQ0Cap = 32 * (kUnroll + 1);   // spectrometer variant: ids that passed the FP32 broad phase
 constexpr int kQbCap = 64;            // spectrometer variant: rays inside the bounds, between the two halves of stage B
 constexpr int kQ2Cap = 64;     // stage B pushes <= 32 per pass, stage C pops 32 when >= 32 are queued
 constexpr int kQ2Planes = 8;   // id, origin, direction, wavelength
@@ -79,7 +80,7 @@ template <uint32_t FT> __host__ __device__ constexpr int q1_planes() {
     return 7 + (FT != 0 ? 1 : 0) + ((FT & FT_MESH) != 0 ? 3 : 0);
 }
 template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int q1_doubles() {
-    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1PlanesSpectro * kQ1CapSpectro + kQbPlanes * kQbCap
+    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQ1PlanesSpectro * kQ1CapSpectro + kQbPlanes * kQbCap + kQ0Cap
                                                         : q1_planes<FT>() * kQ1Cap + ((FT & FT_MESH) != 0 ? kQaPlanes * kQaCap : 0);
 }
 template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int warp_queue_doubles() {
@@ -303,6 +304,71 @@ __device__ __forceinline__ void stage_b1(const XrtSceneDesc &sc, const XrtOpticD
     __syncwarp();
 }
 
+// ---- spectrometer variant, FP64 stage A for one ray: direction from the cone block, the two lengths of the sphere
+// intersection and the first level of the Bragg pre-test.  Returns true for a ray that goes on to stage B1.
+__device__ __forceinline__ bool spectro_stage_a(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const PhiloxKeys &pk,
+                                                uint64_t stream_id, int split, const double *s_sincos, uint64_t id, bool valid,
+                                                V3 &d_out, double &t_out, double &gap_out, double &c2_out) {
+    const XrtSourceDesc &src = sc.source;
+    PhiloxDraws dr;
+    dr.init(pk, stream_id, id, split);
+    double a, b;
+    dr.cone(0, a, b);
+    const double cs0 = src.cone_par[0];
+    const double z = cs0 + (1.0 - cs0) * a;
+    const double rho = fast_sqrt(fma(-z, z, 1.0));
+    double sn, cs;
+    sincos_2pi_tab(b, s_sincos, sn, cs);
+    const double lx = rho * cs, ly = rho * sn;
+    const double *B = src.axis_basis;
+    const V3 d = v3(lx * B[0] + ly * B[3] + z * B[6], lx * B[1] + ly * B[4] + z * B[7], lx * B[2] + ly * B[5] + z * B[8]);
+    // hit_sphere, concave
+    const V3 Lc = v3(ops.center) - v3(src.origin);
+    const double tca = dot(Lc, d);
+    const double d2 = fma(-tca, tca, dot(Lc, Lc));
+    const double r2 = ops.radius * ops.radius;
+    const double thc = fast_sqrt(r2 - d2);          // NaN when d2 > r2
+    d_out = d;
+    t_out = tca + thc;
+    bool cand = valid & (d2 >= 0.0) & (d2 <= r2);
+    gap_out = -1.0;
+    c2_out = 1.0;
+    if (ops.cull_t2 > 0.0) cand &= !bragg_cull_sphere(src, ops, dr.wave_hi(), thc, gap_out, c2_out);
+    return cand;
+}
+
+// ---- spectrometer variant, FP32 broad phase for one ray (stage A32).  The same Philox block, the same geometry and
+// the same first-level test as spectro_stage_a, in single precision with the MUFU units; K = XrtSceneDesc.kn32.
+// 1 - z^2 is formed as w (2 - w) with w = 1 - z = (1 - cos spread)(1 - a), so rho keeps its relative accuracy near the
+// axis; with that every quantity of the test is within 1e-6 of its FP64 value and K[21] adds
+// 2e-5 to the margin of the bound.  true = the ray provably fails the Bragg test (whatever its uniform): lost at the
+// crystal.  Everything else -- including rays that miss the sphere or give a NaN here -- is decided in FP64.
+__device__ __forceinline__ bool spectro_cull32(const float *K, uint4 r) {
+    const float a1 = 1.0f - (float)(r.x >> 8) * 5.9604644775390625e-8f;                 // 1 - a, exact
+    const float w = K[1] * a1;                                                          // 1 - z
+    const float z = 1.0f - w;
+    float rho;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rho) : "f"(w * (2.0f - w)));
+    const uint32_t b24 = ((r.y & 0xfffu) << 12) | (r.z >> 20);                          // top 24 bits of the azimuth uniform
+    const float ang = 6.283185307179586f * ((float)b24 * 5.9604644775390625e-8f - 0.5f);
+    const float lx = -rho * __cosf(ang), ly = -rho * __sinf(ang);                       // cos(2 pi b) = -cos(2 pi (b - 1/2))
+    const float dx = lx * K[2] + ly * K[5] + z * K[8];
+    const float dy = lx * K[3] + ly * K[6] + z * K[9];
+    const float dz = lx * K[4] + ly * K[7] + z * K[10];
+    const float tca = K[11] * dx + K[12] * dy + K[13] * dz;
+    const float d2 = fmaf(-tca, tca, K[14]);
+    float thc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(thc) : "f"(K[15] - d2));
+    const float sI = thc * K[16];
+    bool usable;
+    const float zn = normal_approx(r.w, usable);
+    const float sB = fmaf(zn, K[18], K[17]) * K[19];
+    const float gap = fabsf(sB - sI);
+    const float diff = gap - K[21];
+    const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
+    return usable & (diff > 0.0f) & (diff * diff > K[20] * c2);
+}
+
 // Resident blocks per SM: 2 for the mesh variants (face loops and Clough-Tocher cubics keep many values live), for
 // the spectrometer variant (two ray groups per pass = two independent chains: 118 registers, no spills) and for the
 // lean extended-source variant (bundle lookup + focused cone basis: 116 registers, no spills); 3 otherwise.
@@ -359,6 +425,9 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
     int nb = 0;             // spectrometer variant: queue b (inside the bounds), after the planes of queue 1
     double *qb = q1 + kQ1PlanesSpectro * kQ1CapSpectro;
+    int n0 = 0;             // spectrometer variant: queue 0 (ids that passed the FP32 broad phase), after queue b
+    double *q0 = qb + kQbPlanes * kQbCap;
+    const bool broad32 = SPECTRO_K && sc.kn32[0] > 0.0f;
     // mesh variants: queue a (coarse-mesh hits) after the planes of queue 1.  Stage A is split in two when the split
     // optic is the first optic, a refining mesh, and the wavelength is lazy (a ray is rebuilt from its id in stage A2)
     int na = 0;
@@ -387,23 +456,52 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     uint32_t it = 0;
     for (;;) {
         const bool more = it < n_it;
-        if (n2 >= 32 || (!more && n1 == 0 && nb == 0 && na == 0 && n2 > 0)) {
+        if (n2 >= 32 || (!more && n0 == 0 && n1 == 0 && nb == 0 && na == 0 && n2 > 0)) {
             const int cnt = n2 < 32 ? n2 : 32;
             n2 -= cnt;
             stage_c<FT>(sc, out, c, split, pk, stream_id, q2, n2, cnt);
             continue;
         }
         if constexpr (SPECTRO) {
-            if (nb >= 32 || (!more && n1 == 0 && nb > 0)) {
+            if (nb >= 32 || (!more && n0 == 0 && n1 == 0 && nb > 0)) {
                 const int cnt = nb < 32 ? nb : 32;
                 nb -= cnt;
                 stage_b<FT, KN>(sc, ops, out, c, split, lazy, need_wave, defer, pk, stream_id, qb, nb, cnt, q2, n2, n_split);
                 continue;
             }
-            if (n1 >= 32 || (!more && n1 > 0)) {
+            if (n1 >= 32 || (!more && n0 == 0 && n1 > 0)) {
                 const int cnt = n1 < 32 ? n1 : 32;
                 n1 -= cnt;
                 stage_b1(sc, ops, out, c, split, pk, stream_id, q1, n1, cnt, qb, nb);
+                continue;
+            }
+            if (n0 >= 32 || (!more && n0 > 0)) {
+                // ---- stage A64: the rays the FP32 broad phase could not reject, in FP64 from their ids
+                const int cnt = n0 < 32 ? n0 : 32;
+                n0 -= cnt;
+                const bool active = (int)c.lane < cnt;
+                uint64_t id = 0;
+                if (active) id = (uint64_t)__double_as_longlong(q0[n0 + c.lane]);
+                __syncwarp();
+                V3 d;
+                double t, gap, c2;
+                const bool cand = spectro_stage_a(sc, ops, pk, stream_id, split, s_sincos, id, active, d, t, gap, c2);
+                if (out.lost_count) {
+                    PhiloxDraws dr;
+                    dr.init(pk, stream_id, id, split);
+                    emit_lost(out, c, dr, active && !cand, id);
+                }
+                const unsigned m = __ballot_sync(kFull, cand);
+                if (cand) {
+                    double *p = q1 + n1 + __popc(m & c.lt_mask);
+                    p[0] = __longlong_as_double((long long)id);
+                    p[1 * P] = d.x; p[2 * P] = d.y; p[3 * P] = d.z;
+                    p[4 * P] = t;
+                    p[5 * P] = gap;
+                    p[6 * P] = c2;
+                }
+                n1 += __popc(m);
+                __syncwarp();
                 continue;
             }
         } else {
@@ -467,43 +565,44 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             // pre-test needs nothing else.  A ray it rejects is lost at the crystal whether or not it is inside
             // the bounds, so the bounds test moves to stage B, behind the queue (18 % of the rays).
             // kUnroll groups of 32 rays per pass: independent dependency chains for the scheduler.
-            const XrtSourceDesc &src = sc.source;
             uint64_t idv[kUnroll];
+            bool validv[kUnroll], candv[kUnroll];
+            if (broad32) {
+                // ---- stage A32: FP32 broad phase; the ~20 % it cannot reject go to queue 0 as bare ids
+#pragma unroll
+                for (int j = 0; j < kUnroll; ++j) {
+                    const uint32_t itj = it + (uint32_t)j;
+                    idv[j] = id0 + (uint64_t)itj * stride;
+                    validv[j] = (itj < n_it) && ((itj != tail_it) || (c.lane < tail));
+                    PhiloxDraws dr;
+                    dr.init(pk, stream_id, idv[j], split);
+                    candv[j] = validv[j] & !spectro_cull32(sc.kn32, dr.raw(SITE_CONE));
+                }
+                it += kUnroll;
+#pragma unroll
+                for (int j = 0; j < kUnroll; ++j) {
+                    n_src += __popc(__ballot_sync(kFull, validv[j]));
+                    if (out.lost_count) {
+                        PhiloxDraws dr;
+                        dr.init(pk, stream_id, idv[j], split);
+                        emit_lost(out, c, dr, validv[j] && !candv[j], idv[j]);
+                    }
+                    const unsigned m = __ballot_sync(kFull, candv[j]);
+                    if (candv[j]) q0[n0 + __popc(m & c.lt_mask)] = __longlong_as_double((long long)idv[j]);
+                    n0 += __popc(m);
+                }
+                __syncwarp();
+                continue;
+            }
             V3 dv[kUnroll];
             double tv[kUnroll];
-            bool validv[kUnroll], candv[kUnroll];
             double gapv[kUnroll], c2v[kUnroll];
 #pragma unroll
             for (int j = 0; j < kUnroll; ++j) {
                 const uint32_t itj = it + (uint32_t)j;
                 idv[j] = id0 + (uint64_t)itj * stride;
                 validv[j] = (itj < n_it) && ((itj != tail_it) || (c.lane < tail));
-                PhiloxDraws dr;
-                dr.init(pk, stream_id, idv[j], split);
-                double a, b;
-                dr.cone(0, a, b);
-                const double cs0 = src.cone_par[0];
-                const double z = cs0 + (1.0 - cs0) * a;
-                const double rho = fast_sqrt(fma(-z, z, 1.0));
-                double sn, cs;
-                sincos_2pi_tab(b, s_sincos, sn, cs);
-                const double lx = rho * cs, ly = rho * sn;
-                const double *B = src.axis_basis;
-                const V3 d = v3(lx * B[0] + ly * B[3] + z * B[6], lx * B[1] + ly * B[4] + z * B[7],
-                                lx * B[2] + ly * B[5] + z * B[8]);
-                // hit_sphere, concave
-                const V3 Lc = v3(ops.center) - v3(src.origin);
-                const double tca = dot(Lc, d);
-                const double d2 = fma(-tca, tca, dot(Lc, Lc));
-                const double r2 = ops.radius * ops.radius;
-                const double thc = fast_sqrt(r2 - d2);          // NaN when d2 > r2
-                dv[j] = d;
-                tv[j] = tca + thc;
-                bool cand = validv[j] & (d2 >= 0.0) & (d2 <= r2);
-                gapv[j] = -1.0;
-                c2v[j] = 1.0;
-                if (ops.cull_t2 > 0.0) cand &= !bragg_cull_sphere(src, ops, dr.wave_hi(), thc, gapv[j], c2v[j]);
-                candv[j] = cand;
+                candv[j] = spectro_stage_a(sc, ops, pk, stream_id, split, s_sincos, idv[j], validv[j], dv[j], tv[j], gapv[j], c2v[j]);
             }
             it += kUnroll;
 #pragma unroll
@@ -965,6 +1064,7 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         }
     }
     for (int k = 0; k < d.n_optics; ++k) d.optics[k].cull_t2 = d.optics[k].cull_err = d.optics[k].cull_inv_r = 0.0;
+    for (int i = 0; i < 32; ++i) d.kn32[i] = 0.0f;
     s->features = scene_features(d);
     s->split = 0;
     for (int k = 0; k < d.n_optics; ++k) {
@@ -1014,6 +1114,29 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
             const bool approx = s->lazy_wavelength && src.wave == XRT_WAVE_NORMAL;
             w.cull_err = (approx ? 2e-3 * std::fabs(src.wave_par[1]) * std::fabs(o.inv_two_d) : 0.0) + 1e-9;
             w.cull_inv_r = 1.0 / o.radius;
+            // FP32 broad phase of the spectrometer variant (spectro_cull32): single-precision copies of its constants.
+            // Its arithmetic error on sin(theta_i) is about 1e-6 (|C - O| ~ R); the margin is 2e-5, scaled with
+            // |C - O|^2 / R^2, and the phase is left off for a source farther than 2 R from the centre of curvature.
+            if ((s->known & KN_SPECTROMETER) == KN_SPECTROMETER && s->features == 0 && approx &&
+                std::getenv("XRT_NO_BROAD32") == nullptr) {
+                float *K = d.kn32;
+                const double lx = o.center[0] - src.origin[0], ly = o.center[1] - src.origin[1], lz = o.center[2] - src.origin[2];
+                const double ll = lx * lx + ly * ly + lz * lz, r2 = o.radius * o.radius;
+                if (ll <= 4.0 * r2) {
+                    K[1] = (float)(1.0 - src.cone_par[0]);
+                    for (int i = 0; i < 9; ++i) K[2 + i] = (float)src.axis_basis[i];
+                    K[11] = (float)lx; K[12] = (float)ly; K[13] = (float)lz;
+                    K[14] = (float)ll;
+                    K[15] = (float)r2;
+                    K[16] = (float)(1.0 / o.radius);
+                    K[17] = (float)src.wave_par[0];
+                    K[18] = (float)src.wave_par[1];
+                    K[19] = (float)o.inv_two_d;
+                    K[20] = (float)w.cull_t2;
+                    K[21] = (float)(w.cull_err + 2e-5 * std::fmax(1.0, ll / r2));
+                    K[0] = 1.0f;
+                }
+            }
             // eager normal line (plasma bundles, Doppler shift) with no optic before the crystal: defer the exact deviate
             s->defer_wavelength = (!s->lazy_wavelength && src.wave == XRT_WAVE_NORMAL && s->split == 0) ? 1 : 0;
         }
