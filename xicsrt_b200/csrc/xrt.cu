@@ -70,7 +70,11 @@ constexpr int kUnroll = XRT_UNROLL;   // spectrometer variant: groups of 32 rays
 constexpr int kQ1CapSpectro = 32 * (kUnroll + 1);
 constexpr int kQ1PlanesSpectro = 7;   // id, direction, distance, and the two numbers of the pre-test bound (gap, c2)
 constexpr int kQbPlanes = 5;          // id, direction, distance
-constexpr int kQ0Cap = 32 * (kUnroll + 1);   // spectrometer variant: ids that passed the FP32 broad phase
+#ifndef XRT_UNROLL32
+#define XRT_UNROLL32 3
+#endif
+constexpr int kUnroll32 = XRT_UNROLL32;      // groups of 32 rays per pass of the FP32 broad phase
+constexpr int kQ0Cap = 32 * (kUnroll32 + 1);   // spectrometer variant: ids that passed the FP32 broad phase
 constexpr int kQbCap = 64;            // spectrometer variant: rays inside the bounds, between the two halves of stage B
 constexpr int kQ2Cap = 64;     // stage B pushes <= 32 per pass, stage C pops 32 when >= 32 are queued
 constexpr int kQ2Planes = 8;   // id, origin, direction, wavelength
@@ -565,35 +569,38 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             // pre-test needs nothing else.  A ray it rejects is lost at the crystal whether or not it is inside
             // the bounds, so the bounds test moves to stage B, behind the queue (18 % of the rays).
             // kUnroll groups of 32 rays per pass: independent dependency chains for the scheduler.
-            uint64_t idv[kUnroll];
-            bool validv[kUnroll], candv[kUnroll];
             if (broad32) {
-                // ---- stage A32: FP32 broad phase; the ~20 % it cannot reject go to queue 0 as bare ids
+                // ---- stage A32: FP32 broad phase, kUnroll32 groups per pass; the ~20 % it cannot reject go to
+                // queue 0 as bare ids
+                uint64_t id32[kUnroll32];
+                bool valid32[kUnroll32], pass32[kUnroll32];
 #pragma unroll
-                for (int j = 0; j < kUnroll; ++j) {
+                for (int j = 0; j < kUnroll32; ++j) {
                     const uint32_t itj = it + (uint32_t)j;
-                    idv[j] = id0 + (uint64_t)itj * stride;
-                    validv[j] = (itj < n_it) && ((itj != tail_it) || (c.lane < tail));
+                    id32[j] = id0 + (uint64_t)itj * stride;
+                    valid32[j] = (itj < n_it) && ((itj != tail_it) || (c.lane < tail));
                     PhiloxDraws dr;
-                    dr.init(pk, stream_id, idv[j], split);
-                    candv[j] = validv[j] & !spectro_cull32(sc.kn32, dr.raw(SITE_CONE));
+                    dr.init(pk, stream_id, id32[j], split);
+                    pass32[j] = valid32[j] & !spectro_cull32(sc.kn32, dr.raw(SITE_CONE));
                 }
-                it += kUnroll;
+                it += kUnroll32;
 #pragma unroll
-                for (int j = 0; j < kUnroll; ++j) {
-                    n_src += __popc(__ballot_sync(kFull, validv[j]));
+                for (int j = 0; j < kUnroll32; ++j) {
+                    n_src += __popc(__ballot_sync(kFull, valid32[j]));
                     if (out.lost_count) {
                         PhiloxDraws dr;
-                        dr.init(pk, stream_id, idv[j], split);
-                        emit_lost(out, c, dr, validv[j] && !candv[j], idv[j]);
+                        dr.init(pk, stream_id, id32[j], split);
+                        emit_lost(out, c, dr, valid32[j] && !pass32[j], id32[j]);
                     }
-                    const unsigned m = __ballot_sync(kFull, candv[j]);
-                    if (candv[j]) q0[n0 + __popc(m & c.lt_mask)] = __longlong_as_double((long long)idv[j]);
+                    const unsigned m = __ballot_sync(kFull, pass32[j]);
+                    if (pass32[j]) q0[n0 + __popc(m & c.lt_mask)] = __longlong_as_double((long long)id32[j]);
                     n0 += __popc(m);
                 }
                 __syncwarp();
                 continue;
             }
+            uint64_t idv[kUnroll];
+            bool validv[kUnroll], candv[kUnroll];
             V3 dv[kUnroll];
             double tv[kUnroll];
             double gapv[kUnroll], c2v[kUnroll];
