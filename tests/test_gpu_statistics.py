@@ -344,3 +344,56 @@ def test_bragg_pretest_changes_no_result(torch, name, monkeypatch):
     assert meta0['detector'] > 300 and np.array_equal(found0, found1)
     for elem, img in image0.items():
         assert (img is None and image1[elem] is None) or np.array_equal(img, image1[elem])
+
+
+def _spectrometer_variants():
+    import bench
+    out = {}
+    out['default'] = bench.spectrometer(3000000)
+    c = bench.spectrometer(3000000)                       # the whole geometry three times larger
+    for name, o in c['optics'].items():
+        o['origin'] = [3 * v for v in o['origin']]
+        o['xsize'], o['ysize'] = 3 * o['xsize'], 3 * o['ysize']
+    c['optics']['crystal']['radius'] = 3.0
+    out['scaled_x3'] = c
+    c = bench.spectrometer(3000000)                       # wide cone: most rays miss the crystal, many miss the sphere
+    c['sources']['source']['spread'] = float(np.radians(75.0))
+    out['wide_cone'] = c
+    c = bench.spectrometer(3000000)                       # broad line, narrow rocking curve, lossy crystal
+    c['sources']['source']['temperature'] = 40000.0
+    c['optics']['crystal'].update({'rocking_fwhm': 9e-6, 'reflectivity': 0.37})
+    out['broad_line_narrow_curve'] = c
+    c = bench.spectrometer(3000000)                       # source well off the Rowland circle
+    c['sources']['source']['origin'] = [0.01, -0.02, 0.15]
+    out['off_rowland'] = c
+    return out
+
+
+@pytest.mark.parametrize('name', ['default', 'scaled_x3', 'wide_cone', 'broad_line_narrow_curve', 'off_rowland'])
+def test_fp32_broad_phase_changes_no_result(torch, name, monkeypatch):
+    """
+    Spectrometer variant: the FP32 broad phase (stage A32) and both levels of the FP64 pre-test only skip work.
+    Counters, images and the found set are identical with the broad phase off (XRT_NO_BROAD32) and with every
+    pre-test off (XRT_NO_CULL), on geometries that stress its error bound.
+    """
+    from xicsrt_b200 import _driver, config as xconfig
+    cfg = _spectrometer_variants()[name]
+    results = []
+    for env in ({}, {'XRT_NO_BROAD32': '1'}, {'XRT_NO_CULL': '1'}):
+        for key in ('XRT_NO_BROAD32', 'XRT_NO_CULL'):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), seed=77)
+        info = tracer.scene.launch_info()
+        found, lost = tracer.select_ids(2, 50)
+        meta, image = tracer.counts_and_images(True)
+        results.append((meta, image, np.sort(found.cpu().numpy()), info))
+        tracer.close()
+    meta0, image0, found0, info0 = results[0]
+    assert info0['registers'] > 100                      # the spectrometer variant (2 blocks / SM) is the kernel in use
+    assert meta0['source'] == 3000000
+    for meta, image, found, _ in results[1:]:
+        assert meta == meta0 and np.array_equal(found, found0)
+        for elem, img in image0.items():
+            assert np.array_equal(img, image[elem])
