@@ -55,6 +55,14 @@ constexpr unsigned kFull = 0xffffffffu;
 //                         optic (Bragg / mosaic / mirror), its image          -> queue 2
 //   stage C  queue 2      the remaining optics, images, found list
 //
+// Variants of this scheme:
+//   spectrometer (KN)  A32 FP32 broad phase of the Bragg pre-test, all rays        -> queue 0 (ids)
+//                      A64 FP64 direction, sphere chord, first level of the pre-test -> queue 1
+//                      B1  intersection point, bounds, second level (rocking uniform) -> queue b
+//                      B2  exact wavelength, Bragg angle, rocking curve, reflection   -> queue 2, then C
+//   mesh split optic   A1 coarse mesh for every ray -> queue a; A2 refinement + interpolation -> queue 1
+//   other scenes       stage A ends with the (FP64) Bragg pre-test where it applies (bragg_cull_general)
+//
 // The split optic is the first crystal of the train (0 if there is none).  SPLIT >= 0 makes
 // its index a compile-time constant, so its parameters are fetched from the constant bank at
 // fixed offsets (uniform loads) instead of register-indexed ones.  Warps never wait for one
