@@ -57,8 +57,9 @@ constexpr unsigned kFull = 0xffffffffu;
 //
 // Variants of this scheme:
 //   spectrometer (KN)  A32 FP32 broad phase of the Bragg pre-test, all rays        -> queue 0 (ids)
-//                      A64 FP64 direction, sphere chord, first level of the pre-test -> queue 1
-//                      B1  intersection point, bounds, second level (rocking uniform) -> queue b
+//                      A64+B1 FP64 direction, sphere chord, first level of the pre-test, intersection point,
+//                          bounds, second level (rocking uniform)                     -> queue b
+//                      (broad phase off: FP64 stage A for every ray -> queue 1 -> B1 -> queue b)
 //                      B2  exact wavelength, Bragg angle, rocking curve, reflection   -> queue 2, then C
 //   mesh split optic   A1 coarse mesh for every ray -> queue a; A2 refinement + interpolation -> queue 1
 //   other scenes       stage A ends with the (FP64) Bragg pre-test where it applies (bragg_cull_general)
@@ -488,7 +489,10 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
                 continue;
             }
             if (n0 >= 32 || (!more && n0 > 0)) {
-                // ---- stage A64: the rays the FP32 broad phase could not reject, in FP64 from their ids
+                // ---- stage A64 + B1: the rays the FP32 broad phase could not reject, in FP64 from their ids: first
+                // level of the pre-test, intersection point and bounds (arithmetic of optic_geometry), second level
+                // with the rocking-curve uniform -- 86 % of them are still candidates after the first level, so the
+                // two steps share one pass without a queue in between                               -> queue b
                 const int cnt = n0 < 32 ? n0 : 32;
                 n0 -= cnt;
                 const bool active = (int)c.lane < cnt;
@@ -497,22 +501,28 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
                 __syncwarp();
                 V3 d;
                 double t, gap, c2;
-                const bool cand = spectro_stage_a(sc, ops, pk, stream_id, split, s_sincos, id, active, d, t, gap, c2);
-                if (out.lost_count) {
-                    PhiloxDraws dr;
-                    dr.init(pk, stream_id, id, split);
-                    emit_lost(out, c, dr, active && !cand, id);
+                bool cand = spectro_stage_a(sc, ops, pk, stream_id, split, s_sincos, id, active, d, t, gap, c2);
+                {
+                    const V3 o = v3(sc.source.origin);
+                    const V3 X = v3(fma(d.x, t, o.x), fma(d.y, t, o.y), fma(d.z, t, o.z));
+                    const V3 Xl = to_local(ops.orient, X - v3(ops.origin));
+                    cand &= (fabs(Xl.x) < ops.half_size[0]) & (fabs(Xl.y) < ops.half_size[1]);
                 }
+                PhiloxDraws dr;
+                dr.init(pk, stream_id, id, split);
+                if (ops.cull_t2 > 0.0 && ops.rocking_type != XRT_ROCK_STEP) {
+                    const double u = dr.bragg_u(split, 0);
+                    if (bragg_cull_uniform(ops, gap, c2, u)) cand = false;
+                }
+                if (out.lost_count) emit_lost(out, c, dr, active && !cand, id);
                 const unsigned m = __ballot_sync(kFull, cand);
                 if (cand) {
-                    double *p = q1 + n1 + __popc(m & c.lt_mask);
+                    double *p = qb + nb + __popc(m & c.lt_mask);
                     p[0] = __longlong_as_double((long long)id);
-                    p[1 * P] = d.x; p[2 * P] = d.y; p[3 * P] = d.z;
-                    p[4 * P] = t;
-                    p[5 * P] = gap;
-                    p[6 * P] = c2;
+                    p[1 * kQbCap] = d.x; p[2 * kQbCap] = d.y; p[3 * kQbCap] = d.z;
+                    p[4 * kQbCap] = t;
                 }
-                n1 += __popc(m);
+                nb += __popc(m);
                 __syncwarp();
                 continue;
             }
