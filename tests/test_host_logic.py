@@ -174,3 +174,72 @@ def test_images_are_saved_rotated(tmp_path):
     img = np.array(Image.open(tmp_path / 'xicsrt_detector.tif'))
     assert img.shape == (50, 100)
     assert np.array_equal(img, np.rot90(res['total']['image']['detector']))
+
+
+def test_fp32_broad_phase_error_budget():
+    """
+    The FP32 broad phase of the spectrometer variant (spectro_cull32 in csrc/xrt.cu) is conservative only if its
+    single-precision sin(theta_i) = thc / R stays within the margin kn32[21] - cull_err = 2e-5 max(1, |C-O|^2/R^2) of
+    the FP64 value.  Here the same arithmetic is restated in numpy float32 (correctly rounded sqrt / sin / cos; the MUFU
+    units add at most 2^-21 absolute to sin / cos and one ulp to sqrt) on the benchmark geometry and on the stress
+    geometries of the GPU test, with uniforms that include the cone axis and the cone edge; for chords within 0.05 of
+    sin(theta_B) -- a wrong rejection is only possible within ~2e-4 of it -- the worst error must use less than a
+    fifth of the margin.
+    """
+    import bench
+    from xicsrt_b200 import config as xconfig, scene as xscene
+    f32 = np.float32
+    rng = np.random.default_rng(11)
+    n = 400000
+    a = np.concatenate([rng.random(n), 1.0 - 10.0**rng.uniform(-12, -1, n // 4), 10.0**rng.uniform(-12, -1, n // 4)])
+    b = rng.random(len(a))
+    variants = {'default': {}, 'scaled': {'scale': 3.0}, 'wide': {'spread': np.radians(75.0)},
+                'off_rowland': {'origin': [0.01, -0.02, 0.15]}}
+    for name, mod in variants.items():
+        cfg = bench.spectrometer(1000)
+        if 'scale' in mod:
+            for o in cfg['optics'].values():
+                o['origin'] = [mod['scale'] * v for v in o['origin']]
+            cfg['optics']['crystal']['radius'] = mod['scale']
+        if 'spread' in mod:
+            cfg['sources']['source']['spread'] = float(mod['spread'])
+        if 'origin' in mod:
+            cfg['sources']['source']['origin'] = mod['origin']
+        _, sname, sp, sf, optics = xscene.prepare(xconfig.get_config(xconfig.to_numpy(cfg)))
+        cp = optics['crystal']
+        basis = xscene.cone_basis(sp['direction'] if sp.get('direction') is not None else sp['zaxis'], sp['xaxis'], sp['zaxis'])
+        cs0 = np.cos(np.atleast_1d(sp['spread'])[0])
+        Lc = np.asarray(cp['center'], dtype=np.float64) - np.asarray(sp['origin'], dtype=np.float64)
+        R = float(cp['radius'])
+        # ---- FP64, as spectro_stage_a
+        z = cs0 + (1.0 - cs0) * a
+        rho = np.sqrt(1.0 - z * z)
+        d = (rho * np.cos(2 * np.pi * b))[:, None] * basis[0] + (rho * np.sin(2 * np.pi * b))[:, None] * basis[1] + z[:, None] * basis[2]
+        tca = d @ Lc
+        thc2 = R * R - (Lc @ Lc - tca * tca)
+        hit = thc2 > 0
+        sI64 = np.sqrt(np.where(hit, thc2, 1.0)) / R
+        # ---- FP32, as spectro_cull32 (1 - a to 2^-24 relative, 24-bit azimuth, w (2 - w), constants rounded to float)
+        one_minus_a = (1.0 - a).astype(f32)               # all 52 bits of the uniform: 2^-24 relative
+        b24 = (np.floor(b * 2**24) / 2**24).astype(f32)
+        w = (f32(1.0 - cs0) * one_minus_a).astype(f32)
+        z32 = (f32(1) - w).astype(f32)
+        rho32 = np.sqrt((w * (f32(2) - w)).astype(f32)).astype(f32)
+        ang = (f32(6.283185307179586) * (b24 - f32(0.5))).astype(f32)
+        lx, ly = (-rho32 * np.cos(ang).astype(f32)).astype(f32), (-rho32 * np.sin(ang).astype(f32)).astype(f32)
+        B = basis.astype(f32)
+        d32 = [(lx * B[0, i] + ly * B[1, i] + z32 * B[2, i]).astype(f32) for i in range(3)]
+        L32 = Lc.astype(f32)
+        tca32 = (L32[0] * d32[0] + L32[1] * d32[1] + L32[2] * d32[2]).astype(f32)
+        d2 = (f32(Lc @ Lc) - tca32 * tca32).astype(f32)
+        t2 = (f32(R * R) - d2).astype(f32)
+        sI32 = (np.sqrt(np.where(t2 > 0, t2, f32(1))).astype(f32) * f32(1.0 / R)).astype(f32)
+        # a wrong rejection needs |sI32 - sI| > margin where sI is within ~T of sin(theta_B): only chords near the
+        # Bragg angle matter (elsewhere the gap is hundreds of margins wide)
+        sB0 = float(sp['wavelength']) / (2.0 * float(cp['crystal_spacing']))
+        both = hit & (t2 > 0) & (np.abs(sI64 - sB0) < 0.05)
+        err = np.abs(sI32.astype(np.float64) - sI64)[both].max()
+        mufu = 2.0**-21 * 2.0 * np.abs(Lc).sum() / R + 2.4e-7          # sin / cos through rho <= 1 into tca, thc; sqrt ulps
+        margin = 2e-5 * max(1.0, (Lc @ Lc) / (R * R))
+        assert Lc @ Lc <= 4 * R * R
+        assert err + mufu < margin / 5, (name, err, mufu, margin)

@@ -352,12 +352,16 @@ __device__ __forceinline__ bool spectro_stage_a(const XrtSceneDesc &sc, const Xr
 
 // ---- spectrometer variant, FP32 broad phase for one ray (stage A32).  The same Philox block, the same geometry and
 // the same first-level test as spectro_stage_a, in single precision with the MUFU units; K = XrtSceneDesc.kn32.
-// 1 - z^2 is formed as w (2 - w) with w = 1 - z = (1 - cos spread)(1 - a), so rho keeps its relative accuracy near the
-// axis; with that every quantity of the test is within 1e-6 of its FP64 value and K[21] adds
+// 1 - z^2 is formed as w (2 - w) with w = 1 - z = (1 - cos spread)(1 - a), 1 - a to 2^-24 relative, so rho keeps its
+// relative accuracy near the axis; with that every quantity of the test is within 1e-6 of its FP64 value and K[21] adds
 // 2e-5 to the margin of the bound.  true = the ray provably fails the Bragg test (whatever its uniform): lost at the
 // crystal.  Everything else -- including rays that miss the sphere or give a NaN here -- is decided in FP64.
 __device__ __forceinline__ bool spectro_cull32(const float *K, uint4 r) {
-    const float a1 = 1.0f - (float)(r.x >> 8) * 5.9604644775390625e-8f;                 // 1 - a, exact
+    // 1 - a from all 52 bits of the polar uniform (complement of the mantissa, two exact-or-rounded pieces): its
+    // RELATIVE precision is what rho = sqrt(w (2 - w)) near the cone axis needs -- truncating a to 24 bits would put
+    // rays within 4e-5 rad of the axis off by that much
+    const float a1 = fmaf((float)((~r.y) >> 12), 2.220446049250313e-16f, fmaf((float)(~r.x), 2.3283064365386963e-10f,
+                                                                                2.220446049250313e-16f));
     const float w = K[1] * a1;                                                          // 1 - z
     const float z = 1.0f - w;
     float rho;
