@@ -1151,7 +1151,8 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
                 float *K = d.kn32;
                 const double lx = o.center[0] - src.origin[0], ly = o.center[1] - src.origin[1], lz = o.center[2] - src.origin[2];
                 const double ll = lx * lx + ly * ly + lz * lz, r2 = o.radius * o.radius;
-                if (ll <= 4.0 * r2) {
+                // ... and for Bragg angles below 6 degrees, where thc -> sI amplifies the error of thc^2 by 1 / (2 sI)
+                if (ll <= 4.0 * r2 && std::fabs(src.wave_par[0] * o.inv_two_d) >= 0.1) {
                     K[1] = (float)(1.0 - src.cone_par[0]);
                     for (int i = 0; i < 9; ++i) K[2 + i] = (float)src.axis_basis[i];
                     K[11] = (float)lx; K[12] = (float)ly; K[13] = (float)lz;
