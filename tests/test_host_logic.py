@@ -243,3 +243,41 @@ def test_fp32_broad_phase_error_budget():
         margin = 2e-5 * max(1.0, (Lc @ Lc) / (R * R))
         assert Lc @ Lc <= 4 * R * R
         assert err + mufu < margin / 5, (name, err, mufu, margin)
+
+
+def test_bragg_pretest_inequalities_are_conservative():
+    """
+    The two levels of the Bragg pre-test (bragg_cull_test / bragg_cull_uniform in csrc/xrt_trace.cuh) restated in
+    numpy: whenever the bound rejects a ray, the exact rocking-curve test -- dtheta = asin(sB) - asin(sI),
+    p = exp(-dtheta^2 / 2 sigma^2) * reflectivity, reflected iff p >= u -- rejects it too; and the bound is not
+    vacuous (it rejects most rays that fail by a wide margin).
+    """
+    rng = np.random.default_rng(5)
+    n = 2000000
+    for fwhm, refl, err in ((48.07e-6, 1.0, 2.7e-7), (9e-6, 0.37, 1e-9), (400e-6, 1.0, 5e-6)):
+        sigma = fwhm / (2 * np.sqrt(2 * np.log(2)))
+        two_sigma2 = 2 * sigma * sigma
+        sB = rng.uniform(0.05, 0.999, n)
+        # sI around sB on every scale from far inside to far outside the rocking curve, plus measurement error <= err
+        sI = np.clip(sB + rng.choice([-1.0, 1.0], n) * 10.0**rng.uniform(-8, -1.5, n), 0.0, 1.0)
+        sB_seen = sB + rng.uniform(-err, err, n)            # what the pre-test sees (approximate deviate)
+        dtheta = np.arcsin(sB) - np.arcsin(sI)
+        x = dtheta * dtheta / two_sigma2
+        u = rng.random(n)
+        passes = np.exp(-x) * refl >= u
+        # first level: T = 1.05 * sqrt(40 * two_sigma2) + 2e-6
+        T = 1.05 * np.sqrt(40.0 * two_sigma2) + 2e-6
+        gap = np.abs(sB_seen - sI)
+        diff = gap - err
+        c2 = 2.0 * gap + (1.0 - sI * sI)
+        cull1 = (diff > 0) & (diff * diff > T * T * c2)
+        assert not np.any(cull1 & (x < 40.0)), 'first level rejected a ray with x < 40'
+        assert not np.any(cull1 & passes)
+        # second level: ln(refl / u) in float32, 1e-3 + 0.1 % too large
+        lim = (np.float32(0.6931471805599453) * (np.log2(np.float32(refl)) - np.log2(u.astype(np.float32)))).astype(np.float32)
+        bound = (np.abs(lim) * np.float32(1e-3) + (lim + np.float32(1e-3))).astype(np.float64) * two_sigma2
+        cull2 = (diff > 0) & (diff * diff > bound * c2)
+        assert not np.any(cull2 & passes), 'second level rejected a ray the exact test reflects'
+        fails_wide = x > 60.0
+        assert cull1[fails_wide].mean() > 0.95
+        assert cull2[~passes & (x > 3.0 * np.maximum(np.log(refl / u), 0.5) + 1.0)].mean() > 0.9
