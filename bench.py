@@ -378,9 +378,11 @@ def run_gpu_arm(args):
                          f'(oracle port of the NumPy path; reference scheme xicsrt_multiprocessing)'}
 
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
-    traffic = None
+    traffic, executed = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))['k_trace']['dram_bytes_per_launch']
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))['k_trace']
+        traffic = prof['dram_bytes_per_launch']
+        executed = prof.get('executed')         # instruction counts of the same capture (what the kernel really executes)
     except (OSError, KeyError, ValueError):
         pass
 
@@ -401,7 +403,8 @@ def run_gpu_arm(args):
                          'frac': (achieved / fp64_peak) if achieved else None, 'traffic': traffic,
                          'flop_equiv_per_ray': F, 'f_bounds': f_bounds, 'f_reflect': f_reflect,
                          'peak_source': 'DFMA-chain microbenchmark (xrt_fp64_burn) measured in this run',
-                         'kernel': 'k_trace', 'kernel_ms_per_step': 1e3 * t_kernel / args.steps},
+                         'kernel': 'k_trace', 'kernel_ms_per_step': 1e3 * t_kernel / args.steps,
+                         'executed_ncu': executed if headline else None},
             'roofline_history': hist_line,
             'cpu_baseline': cpu,
             'detected_per_step': n_detected,
