@@ -176,6 +176,16 @@ def local_frames(n=4000, seed=12):
     return assemble(source_G(n), {'crystal': c, 'detector': d}, seed)
 
 
+def sphere_rocking_file(n=20000, seed=19):
+    """rocking_type='file' (_InteractCrystal.py:151-178): XOP diff_pat table, sigma / pi mix, reflectivity < 1."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'profiles',
+                        'diff_pat.dat')
+    return assemble(source_G(n), {'crystal': crystal_G(radius=1.0, rocking_type='file', rocking_file=path,
+                                                       rocking_mix=0.3, reflectivity=0.9),
+                                  'detector': detector_G()}, seed)
+
+
 def two_iter_two_runs(n=3000, seed=13):
     cfg = sphere(n, seed)
     cfg['general']['number_of_iter'] = 2
@@ -198,6 +208,7 @@ ANALYTIC = {
     'mosaic_sphere_cutoff': lambda: mosaic_sphere(seed=18, cutoff=1e-8, depth=5),
     'mosaic_plane': mosaic_plane,
     'apertures': apertures, 'local_frames': local_frames,
+    'sphere_rocking_file': sphere_rocking_file,
     'two_iter_two_runs': two_iter_two_runs,
 }
 

@@ -146,6 +146,8 @@ EXTRA = {
     'plasma_flat_xy': lambda: plasma_cone('flat_xy', 27),
     'plasma_isotropic_xy': lambda: plasma_cone('isotropic_xy', 28),
     'mesh_torus': mesh_torus,
+    # config 4 of BASELINE.json at its stated size: 41 x 41 fine (1681 points / 3200 faces), 5 x 5 coarse
+    'mesh_torus_41': lambda: mesh_torus(n=6000, seed=38, mesh_size=(41, 41)),
     'mesh_torus_convex': lambda: mesh_torus(seed=37, convex=[True, False], mesh_size=(15, 15)),
     'mesh_sphere': mesh_sphere,
     'mesh_cylinder': mesh_cylinder,
