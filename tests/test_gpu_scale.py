@@ -1,0 +1,203 @@
+# -*- coding: utf-8 -*-
+"""
+Parity of the BENCHMARKED kernel at the scale it is benchmarked (``-m gpu``).
+
+The bit-exact oracle tests (test_gpu_parity.py) drive the straight replay kernel through
+``xrt_trace_injected``; the fused kernel that bench.py times adds work-skipping stages in front
+of the same ray code: an FP32 broad phase, a two-level conservative Bragg pre-test, table
+``sincos``, lazy / deferred wavelengths and shared-memory queues.  Each of them is allowed to
+*skip* work only, never to change a result.  This file proves that at 1e9 rays per launch:
+
+  1. for every geometry below and three seeds, the history-off launch (exactly what bench.py
+     times) gives the same counters and images, and the history-on launch the same found-id
+     set, with the broad phase off (XRT_NO_BROAD32) and with every pre-test off (XRT_NO_CULL);
+     the geometries include the enable thresholds of the broad phase (|C - O|^2 ~ 4 R^2,
+     sin(theta_B) ~ 0.1), the planar limit R = 1e5 of the reference's
+     testing/integrated_test_02.ipynb, reflectivity < 1, a step curve, box / focused / moving
+     sources and a plasma (the generic fast path);
+  2. the found rays of a 1e8-ray run have the distributions of the oracle's own 1e8-ray run
+     (``oracle.raytrace_mp``): binomial z on the per-element counts, two-sample chi-square on the
+     detector image, two-sample KS on the found rays' local x, y and wavelength
+     (reference side >= 1e8 rays).
+
+A conservative bound that is violated with probability 1e-7 per ray shows up ~100 times in 1e9
+rays; the 3e6-ray versions of these tests in test_gpu_statistics.py could not see it.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import scenes
+
+pytestmark = pytest.mark.gpu
+
+N_SCALE = int(os.environ.get('XRT_TEST_SCALE_RAYS', 1_000_000_000))
+SEEDS = (11, 2025, 90210)
+ENVS = ({}, {'XRT_NO_BROAD32': '1'}, {'XRT_NO_CULL': '1'})
+LAMBDA = 3.9492
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def rowland(sin_b=0.80374151, radius=1.0, source_distance=None, detector_distance=None, spread_deg=10.0, size=0.2,
+            n=N_SCALE, **crystal_kw):
+    """
+    Point source at the origin looking along +z at a concave spherical crystal whose vertex is met at the Bragg
+    angle asin(sin_b); detector square on the reflected central ray at the same distance.  With the defaults this
+    is geometry G of SURVEY.md section 8d (source on the Rowland circle: distance = R sin(theta_B)).
+    """
+    cos_b = float(np.sqrt(1.0 - sin_b * sin_b))
+    s = radius * sin_b if source_distance is None else source_distance
+    refl = np.array([0.0, 2.0 * sin_b * cos_b, 1.0 - 2.0 * sin_b * sin_b])
+    s_det = radius * sin_b if detector_distance is None else detector_distance
+    crystal = {'class_name': 'XicsrtOpticSphericalCrystal', 'check_size': True, 'origin': [0.0, 0.0, s],
+               'zaxis': [0.0, cos_b, -sin_b], 'xsize': size, 'ysize': size, 'radius': radius,
+               'crystal_spacing': LAMBDA / (2.0 * sin_b), 'rocking_type': 'gaussian', 'rocking_fwhm': 48.070e-6}
+    crystal.update(crystal_kw)
+    detector = {'class_name': 'XicsrtOpticDetector', 'origin': (np.array([0.0, 0.0, s]) + s_det * refl).tolist(),
+                'zaxis': (-refl).tolist(), 'xsize': 2.0 * size + 0.4 * s_det, 'ysize': 2.0 * size + 0.4 * s_det,
+                'pixel_size': (2.0 * size + 0.4 * s_det) / 100.0}
+    source = scenes.source_G(n, spread=float(np.radians(spread_deg)))
+    return scenes.assemble(source, {'crystal': crystal, 'detector': detector}, 0, keep_history=False)
+
+
+def _geometries():
+    import bench
+    g = {}
+    g['config2'] = bench.spectrometer(N_SCALE)
+    g['config2_reflectivity_0.37'] = bench.spectrometer(N_SCALE)
+    g['config2_reflectivity_0.37']['optics']['crystal']['reflectivity'] = 0.37
+    g['config2_step_curve'] = bench.spectrometer(N_SCALE)
+    g['config2_step_curve']['optics']['crystal'].update({'rocking_type': 'step', 'reflectivity': 0.9})
+    # |C - O|^2 = s^2 + R^2 - 2 s R sin(theta_B); the broad phase is enabled up to 4 R^2: s = 2.7120 -> 3.9950 R^2
+    # (on), s = 2.7160 -> 4.0103 R^2 (off: FP64 stage A for every ray)
+    g['broad_phase_threshold_inside'] = rowland(source_distance=2.7120, spread_deg=4.0)
+    g['broad_phase_threshold_outside'] = rowland(source_distance=2.7160, spread_deg=4.0)
+    # grazing incidence: sin(theta_B) just above / below the 0.1 enable threshold of the broad phase
+    g['sin_bragg_0.1002'] = rowland(sin_b=0.1002, spread_deg=12.0)
+    g['sin_bragg_0.0998'] = rowland(sin_b=0.0998, spread_deg=12.0)
+    # planar limit of testing/integrated_test_02.ipynb: radius 1e5 (point source, and its 0.1 m box source)
+    g['planar_limit_r1e5'] = rowland(radius=1e5, source_distance=0.80374151, detector_distance=0.80374151, spread_deg=5.0)
+    c = rowland(radius=1e5, source_distance=0.80374151, detector_distance=0.80374151, spread_deg=5.0)
+    c['sources']['source'].update({'xsize': 0.10, 'ysize': 0.10})
+    g['planar_limit_r1e5_box_source'] = c
+    # wide cone: most rays miss the crystal, many miss the sphere (NaN paths of the broad phase)
+    g['wide_cone_75deg'] = bench.spectrometer(N_SCALE)
+    g['wide_cone_75deg']['sources']['source']['spread'] = float(np.radians(75.0))
+    # broad line, narrow lossy curve
+    c = bench.spectrometer(N_SCALE)
+    c['sources']['source']['temperature'] = 40000.0
+    c['optics']['crystal'].update({'rocking_fwhm': 9e-6, 'reflectivity': 0.5})
+    g['broad_line_narrow_curve'] = c
+    # the generic fast path: box source, focused source, moving source
+    c = bench.spectrometer(N_SCALE)
+    c['sources']['source'].update({'xsize': 1e-3, 'ysize': 1e-3, 'zsize': 1e-3})
+    g['box_source_1mm'] = c
+    c = bench.spectrometer(N_SCALE)
+    c['sources']['source'].update({'class_name': 'XicsrtSourceFocused', 'target': [0.0, 0.0, 0.80374151],
+                                   'xsize': 0.02, 'ysize': 0.02, 'zsize': 0.02, 'spread': float(np.radians(8.0))})
+    g['focused_box_source_2cm'] = c
+    c = bench.spectrometer(N_SCALE)
+    c['sources']['source']['velocity'] = [0.0, 3.0e4, 1.0e5]
+    g['doppler_shifted_line'] = c
+    g['config5_plasma'] = bench.workload_config('config5', N_SCALE)
+    return g
+
+
+GEOMETRIES = ['config2', 'config2_reflectivity_0.37', 'config2_step_curve', 'broad_phase_threshold_inside',
+              'broad_phase_threshold_outside', 'sin_bragg_0.1002', 'sin_bragg_0.0998', 'planar_limit_r1e5',
+              'planar_limit_r1e5_box_source', 'wide_cone_75deg', 'broad_line_narrow_curve', 'box_source_1mm',
+              'focused_box_source_2cm', 'doppler_shifted_line', 'config5_plasma']
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('name', GEOMETRIES)
+def test_work_skipping_stages_change_no_result_at_bench_scale(torch, name, monkeypatch):
+    from xicsrt_b200 import _driver, config as xconfig
+    cfg = _geometries()[name]
+    cfg['general']['keep_history'] = False
+    results = []
+    for env in ENVS:
+        for key in ('XRT_NO_BROAD32', 'XRT_NO_CULL'):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        per_seed = []
+        for seed in SEEDS:
+            tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(copy.deepcopy(cfg))), seed=seed)
+            tracer.trace(1)                                  # history off: the launch bench.py times
+            packed_off = tracer.packed.clone()
+            found, lost = tracer.select_ids(1, 64)           # history on: found / lost lists
+            assert torch.equal(tracer.packed, packed_off), f'{name}: history-on launch counts differ from history-off'
+            per_seed.append((tracer.n_rays, packed_off, found.clone()))
+            tracer.close()
+        results.append(per_seed)
+    for s, seed in enumerate(SEEDS):
+        n0, packed0, found0 = results[0][s]
+        assert n0 >= 0.9 * N_SCALE
+        n_src, n_det = int(packed0[0]), int(packed0[2])
+        assert n_src == n0
+        assert int(found0.numel()) == n_det
+        if N_SCALE >= 10**8:
+            assert n_det > 1000, f'{name}: only {n_det} rays detected -- the geometry does not exercise the Bragg path'
+        for e, env in enumerate(ENVS[1:], start=1):
+            n1, packed1, found1 = results[e][s]
+            assert n1 == n0
+            assert torch.equal(packed1, packed0), f'{name} seed {seed}: counters / images differ with {env}'
+            assert torch.equal(found1, found0), f'{name} seed {seed}: found-id set differs with {env}'
+
+
+def _local_xy(res, elem):
+    from xicsrt_b200 import elements
+    from oracle import vecs
+    _, param = elements.prepare_optic(res['config']['optics'][elem])
+    h = res['found']['history'][elem]
+    return vecs.point_to_local(param, h['origin']), h['wavelength']
+
+
+@pytest.mark.timeout(1800)
+def test_found_ray_distributions_match_oracle_at_1e8(torch):
+    """RNG-driven end-to-end statistics with >= 1e8 rays on BOTH sides (config 1 / 2 geometry, history on)."""
+    from scipy import stats
+    import xicsrt_b200
+    from test_gpu_statistics import chi2_two_sample, binomial_z
+    runs, per_run = 100, 1_000_000
+    n = runs * per_run
+    cfg = scenes.get('sphere')
+    cfg['sources']['source']['intensity'] = per_run
+    cfg['general'].update({'number_of_runs': runs, 'keep_history': True, 'history_max_lost': 100, 'random_seed': 3})
+    ref = oracle.raytrace_mp(copy.deepcopy(cfg), processes=min(os.cpu_count() or 1, 64))
+    cfg = scenes.get('sphere')
+    cfg['sources']['source']['intensity'] = n
+    cfg['general'].update({'keep_history': True, 'history_max_lost': 100, 'random_seed': 77})
+    got = xicsrt_b200.raytrace(cfg)
+
+    assert got['total']['meta']['source']['num_out'] == n == ref['total']['meta']['source']['num_out']
+    for elem in ('crystal', 'detector'):
+        k1, k2 = got['total']['meta'][elem]['num_out'], ref['total']['meta'][elem]['num_out']
+        z = binomial_z(k1, n, k2, n)
+        assert abs(z) < 4.5, f'{elem}: {k1} vs {k2} of {n}, z = {z:.2f}'
+    for elem in ('crystal', 'detector'):
+        chi2, dof, p = chi2_two_sample(got['total']['image'][elem], ref['total']['image'][elem])
+        assert p > 1e-4, f'{elem} image: chi2 = {chi2:.1f} for {dof} dof, p = {p:.2e}'
+    n_found = got['total']['meta']['detector']['num_out']
+    assert len(got['found']['history']['detector']['mask']) == n_found > 1_000_000
+    for elem in ('crystal', 'detector'):
+        xg, wg = _local_xy(got, elem)
+        xr, wr = _local_xy(ref, elem)
+        for label, a, b in (('x', xg[:, 0], xr[:, 0]), ('y', xg[:, 1], xr[:, 1]), ('wavelength', wg, wr)):
+            ks = stats.ks_2samp(a, b)
+            assert ks.pvalue > 1e-4, f'{elem} {label}: KS D = {ks.statistic:.2e}, p = {ks.pvalue:.2e}'
+    # direction cosines of the found rays at the source as well (the cone sampler seen through the Bragg selection)
+    dg, dr = got['found']['history']['source']['direction'], ref['found']['history']['source']['direction']
+    for k in range(3):
+        ks = stats.ks_2samp(dg[:, k], dr[:, k])
+        assert ks.pvalue > 1e-4, f'source direction[{k}]: KS p = {ks.pvalue:.2e}'
