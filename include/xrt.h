@@ -392,6 +392,10 @@ int xrt_fp64_burn(uint64_t iters, double *out_dev, double *flops, void *stream);
 int xrt_launch_info(XrtScene *scene, int32_t *grid, int32_t *block, int32_t *regs,
                     int32_t *blocks_per_sm);
 
+/* The FP32 broad phase in front of xrt_trace (k_cull32): mode = -1 when it does not apply to the scene, else the
+   source kind it was built for (0 point, 1 box, 2 focused box, 3 plasma bundles); launch geometry as above. */
+int xrt_launch_info_cull(XrtScene *scene, int32_t *mode, int32_t *grid, int32_t *regs, int32_t *blocks_per_sm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -392,6 +392,8 @@ def test_fp32_broad_phase_changes_no_result(torch, name, monkeypatch):
         tracer.close()
     meta0, image0, found0, info0 = results[0]
     assert info0['registers'] > 100                      # the spectrometer variant (2 blocks / SM) is the kernel in use
+    assert info0['broad_phase'] is not None and info0['broad_phase']['source_kind'] == 'point'
+    assert results[1][3]['broad_phase'] is None and results[2][3]['broad_phase'] is None
     assert meta0['source'] == 3000000
     for meta, image, found, _ in results[1:]:
         assert meta == meta0 and np.array_equal(found, found0)

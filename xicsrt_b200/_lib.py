@@ -170,6 +170,7 @@ SYMBOLS = {
     'xrt_scene_set_bundle_tables': (C.c_int, [_vp, _vp, _vp, C.c_int32]),
     'xrt_fp64_burn': (C.c_int, [_u64, _vp, C.POINTER(C.c_double), _vp]),
     'xrt_launch_info': (C.c_int, [_vp, _pi32, _pi32, _pi32, _pi32]),
+    'xrt_launch_info_cull': (C.c_int, [_vp, _pi32, _pi32, _pi32, _pi32]),
 }
 
 _lib = None

@@ -1,0 +1,971 @@
+// xrt_kernels.cuh -- the kernels of libxrt.so (templates; instantiated per scene variant in v_*.cu).
+//
+//   k_cull32<SRC,HIST>   FP32 broad phase of the Bragg pre-test for scenes whose first optic is a spherical Bragg
+//                        crystal: every ray of the launch is generated in single precision from its Philox blocks
+//                        and tested with the conservative chord inequality; the rays it cannot reject (~20 % for a
+//                        spectrometer, a few % for an extended plasma) leave as 4-byte id offsets in a region-
+//                        partitioned list.  Integer / FP32 / MUFU only, ~40 registers: runs at full occupancy.
+//   k_trace<FT,..>       fused generate -> optic train -> bin in FP64 for the ids of that list (or for every id of
+//                        the launch when the broad phase does not apply); ray state in registers from the source to
+//                        the detector; the only global traffic is the id list, the per-element survivor counters
+//                        (one atomic per block), the pixel counters of surviving rays (warp-aggregated atomics) and
+//                        the optional found / lost id lists (ballot + prefix-sum compaction).
+//   k_record<FT,..>      same ray code, but every element's ray state is stored as struct-of-arrays history
+//                        (coalesced planes); rays come either from Philox by id (history of selected rays) or from
+//                        caller memory with injected draws (parity entry).
+//   k_source<..>         source only (history element 0).
+//   k_burn               dependent DFMA chains: the FP64 roofline denominator.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "xrt_trace.cuh"
+
+namespace xrt {
+
+#ifndef XRT_BLOCK
+#define XRT_BLOCK 256
+#endif
+#ifndef XRT_MIN_BLOCKS
+#define XRT_MIN_BLOCKS 3
+#endif
+#ifndef XRT_RECORD_BLOCKS
+#define XRT_RECORD_BLOCKS 3
+#endif
+constexpr int kBlock = XRT_BLOCK;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------
+// id source of a k_trace launch: the ray ids [ray_begin, ray_begin + ray_count) are cut into regions of `cap`
+// consecutive ids.  Sequence mode (ids == nullptr): every id of a region is traced (cap = 32: one warp pass per
+// region).  List mode: region r holds counts[r] surviving id offsets of its range at ids[r * cap ...], written by
+// k_cull32.  Warp w takes regions w, w + n_warps, ... in both modes: no atomics, and the order in which a warp
+// meets its rays does not depend on scheduling.
+struct IdList {
+    const uint32_t *ids;
+    const uint32_t *counts;
+    uint32_t n_regions, cap;
+};
+
+struct IdCursor {
+    const uint32_t *ids, *counts;
+    uint64_t base, n_rays;
+    uint32_t reg, n_regions, cap, pos, cnt, step;
+
+    __device__ __forceinline__ void load() {
+        cnt = 0;
+        if (reg < n_regions) {
+            if (ids) cnt = __ldg(counts + reg);
+            else {
+                const uint64_t left = n_rays - (uint64_t)reg * cap;
+                cnt = left < (uint64_t)cap ? (uint32_t)left : cap;
+            }
+        }
+    }
+    __device__ __forceinline__ void init(const IdList &L, uint64_t ray_begin, uint64_t ray_count, uint32_t warp_global,
+                                         uint32_t n_warps) {
+        ids = L.ids; counts = L.counts; n_regions = L.n_regions; cap = L.cap;
+        base = ray_begin; n_rays = ray_count;
+        reg = warp_global; step = n_warps; pos = 0;
+        load();
+    }
+    // warp-uniform: is there another group of <= 32 ids for this warp?
+    __device__ __forceinline__ bool more() {
+        while (pos >= cnt) {
+            if (reg >= n_regions) return false;
+            reg += step;
+            pos = 0;
+            load();
+        }
+        return true;
+    }
+    __device__ __forceinline__ void next(unsigned lane, uint64_t &id, bool &valid) {
+        id = base;
+        valid = false;
+        if (!more()) return;
+        const uint32_t p = pos + lane;
+        valid = p < cnt;
+        uint64_t off = (uint64_t)reg * cap + p;
+        if (ids) off = valid ? (uint64_t)__ldg(ids + off) : 0ull;
+        id = base + off;
+        pos += 32;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// fused kernel
+//
+// Each warp works through its share of the ray ids in stages and re-packs the survivors between them in per-warp
+// shared-memory queues (ballot + popc prefix sums), so that every stage runs with (nearly) all 32 lanes busy
+// although ~48 % of the rays of a typical spectrometer miss the crystal and ~98 % of the rest fail the Bragg test:
+//
+//   stage A  ids          source origin + direction, optics before the split optic, geometry (intersect + bounds)
+//                         of the split optic, both levels of the FP64 Bragg pre-test where it applies  -> queue 1
+//   stage B  queue 1      wavelength (drawn here when it does not depend on the source direction: Philox is counter
+//                         based), interaction of the split optic (Bragg / mosaic / mirror), its image -> queue 2
+//   stage C  queue 2      the remaining optics, images, found list
+//
+// Variants:
+//   spectrometer (KN)  AB  FP64 direction from the cone block, sphere chord, first level of the pre-test,
+//                          intersection point, bounds, second level (rocking uniform)      -> queue b
+//                      B2  exact wavelength, Bragg angle, rocking curve, reflection        -> queue 2, then C
+//   mesh split optic   A1 coarse mesh for every ray -> queue a; A2 refinement + interpolation -> queue 1
+//   mosaic split optic see stage S / E below
+//
+// The split optic is the first crystal of the train (0 if there is none).  SPLIT >= 0 makes its index a
+// compile-time constant, so its parameters are fetched from the constant bank at fixed offsets (uniform loads)
+// instead of register-indexed ones.  Warps never wait for one another: only __syncwarp and warp-uniform counters.
+// HIST = false compiles the found / lost list emission out (history-off launches: bench.py's timed launch).
+
+constexpr int kQ1Cap = 64;     // stage A pushes <= 32 per pass, stage B pops 32 when >= 32 are queued
+constexpr int kQaCap = 64;     // mesh variants: rays that hit the coarse mesh (id, coarse hit point), between the halves of stage A
+constexpr int kQaPlanes = 4;
+#ifndef XRT_UNROLL
+#define XRT_UNROLL 2
+#endif
+constexpr int kUnroll = XRT_UNROLL;   // spectrometer variant: groups of 32 rays per stage-AB pass (independent chains)
+constexpr int kQbPlanes = 5;          // id, direction, distance
+constexpr int kQbCap = 32 * (kUnroll + 1);   // spectrometer variant: rays inside the bounds that passed both pre-test levels
+constexpr int kQ2Cap = 64;     // stage B pushes <= 32 per pass, stage C pops 32 when >= 32 are queued
+constexpr int kQ2Planes = 8;   // id, origin, direction, wavelength
+
+template <uint32_t FT> __host__ __device__ constexpr int q1_planes() {
+    // id, intersection point, direction [, wavelength when it can be eager] [, normal for mesh shapes]
+    return 7 + (FT != 0 ? 1 : 0) + ((FT & FT_MESH) != 0 ? 3 : 0);
+}
+template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int q1_doubles() {
+    return ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQbPlanes * kQbCap
+                                                        : q1_planes<FT>() * kQ1Cap + ((FT & FT_MESH) != 0 ? kQaPlanes * kQaCap : 0);
+}
+template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr int warp_queue_doubles() {
+    return q1_doubles<FT, KN>() + kQ2Planes * kQ2Cap;
+}
+
+// shared-memory copy of the step-1 face operands of a mesh split optic (<= kStageFaces faces)
+constexpr int kStageFaces = 128;
+template <uint32_t FT, uint32_t KN = 0> __host__ __device__ constexpr size_t block_smem_bytes() {
+    return ((size_t)(XRT_BLOCK / 32) * warp_queue_doubles<FT, KN>() + ((FT & FT_MESH) != 0 ? 9 * kStageFaces : 0)) * sizeof(double);
+}
+
+struct WarpCtx {
+    unsigned lane, lt_mask;
+    unsigned long long *s_cnt;
+};
+
+__device__ __forceinline__ void count_alive(const WarpCtx &c, int elem, bool alive) {
+    unsigned m = __ballot_sync(kFull, alive);
+    if (c.lane == 0 && m) atomicAdd(&c.s_cnt[elem], (unsigned long long)__popc(m));
+}
+
+// pixel hit: one atomic per distinct pixel among the calling lanes
+__device__ __forceinline__ void add_pixel(const XrtOutputs &out, const XrtOpticDesc &op, const Ray &r, unsigned lt_mask) {
+    uint32_t pix;
+    if (pixel_index(op, r.o, pix)) {
+        unsigned act = __activemask();
+        unsigned same = __match_any_sync(act, pix);
+        if ((same & lt_mask) == 0)
+            atomicAdd((unsigned long long *)(out.images + op.image_offset + pix), (unsigned long long)__popc(same));
+    }
+}
+
+// found list: ballot + prefix-sum compaction, one atomic per warp (all 32 lanes call this)
+template <bool HIST>
+__device__ __forceinline__ void emit_found(const XrtOutputs &out, unsigned lane, unsigned lt_mask, bool found, uint64_t id) {
+    if constexpr (!HIST) return;
+    if (!out.found_count) return;
+    unsigned m = __ballot_sync(kFull, found);
+    if (!m) return;
+    unsigned long long off = 0;
+    if (lane == 0) off = atomicAdd((unsigned long long *)out.found_count, (unsigned long long)__popc(m));
+    off = __shfl_sync(kFull, off, 0);
+    if (found && out.found_ids) {
+        unsigned long long slot = off + __popc(m & lt_mask);
+        if (slot < out.found_capacity) out.found_ids[slot] = id;
+    }
+}
+
+// lost sample: a lost ray is kept when its 64-bit Philox key is below the threshold
+template <bool HIST>
+__device__ __forceinline__ void emit_lost(const XrtOutputs &out, unsigned lane, unsigned lt_mask, const PhiloxDraws &dr,
+                                          bool lost, uint64_t id) {
+    if constexpr (!HIST) return;
+    if (!out.lost_count) return;
+    bool keep = false;
+    uint64_t key = 0;
+    if (lost) {
+        key = dr.lost_key();
+        keep = key < out.lost_threshold;
+    }
+    unsigned m = __ballot_sync(kFull, keep);
+    if (!m) return;
+    unsigned long long off = 0;
+    if (lane == 0) off = atomicAdd((unsigned long long *)out.lost_count, (unsigned long long)__popc(m));
+    off = __shfl_sync(kFull, off, 0);
+    if (keep && out.lost_ids) {
+        unsigned long long slot = off + __popc(m & lt_mask);
+        if (slot < out.lost_capacity) {
+            out.lost_ids[slot] = id;
+            if (out.lost_keys) out.lost_keys[slot] = key;
+        }
+    }
+}
+
+// ---- stage C: the optics after the split optic, for the `cnt` rays in queue 2
+template <uint32_t FT, bool HIST>
+__device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs &out, const WarpCtx &c, int split,
+                                        const PhiloxKeys &pk, uint64_t stream_id, const double *q2, int first, int cnt) {
+    const bool active = (int)c.lane < cnt;
+    Ray r;
+    r.alive = false;
+    uint64_t id = 0;
+    PhiloxDraws dr;
+    if (active) {
+        const double *p = q2 + first + c.lane;
+        id = (uint64_t)__double_as_longlong(p[0]);
+        r.o = v3(p[1 * kQ2Cap], p[2 * kQ2Cap], p[3 * kQ2Cap]);
+        r.d = v3(p[4 * kQ2Cap], p[5 * kQ2Cap], p[6 * kQ2Cap]);
+        r.w = p[7 * kQ2Cap];
+        r.alive = true;
+    }
+    __syncwarp();
+    dr.init(pk, stream_id, id, split);
+    const int nopt = sc.n_optics;
+    for (int k = split + 1; k < nopt; ++k) {
+        const XrtOpticDesc &op = sc.optics[k];
+        if (r.alive) {
+            trace_optic<FT>(op, k, dr, r);
+            if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
+        }
+        count_alive(c, k + 1, r.alive);
+    }
+    emit_found<HIST>(out, c.lane, c.lt_mask, r.alive, id);
+    emit_lost<HIST>(out, c.lane, c.lt_mask, dr, active && !r.alive, id);
+}
+
+// ---- stage B: interaction of the split optic for `cnt` rays popped from queue 1
+template <uint32_t FT, uint32_t KN, bool HIST>
+__device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
+                                        const WarpCtx &c, int split, bool lazy, bool need_wave, bool defer, const PhiloxKeys &pk, uint64_t stream_id,
+                                        const double *q1, int first, int cnt, double *q2, int &n2, unsigned &n_split) {
+    constexpr int P = ((KN & KN_SPECTROMETER) == KN_SPECTROMETER) ? kQbCap : kQ1Cap;   // spectrometer: q1 = queue b here
+    const bool active = (int)c.lane < cnt;
+    Ray r;
+    r.alive = false;
+    r.w = 0.0;
+    V3 n = v3(0.0, 0.0, 1.0);
+    uint64_t id = 0;
+    constexpr bool SPECTRO = (KN & KN_SPECTROMETER) == KN_SPECTROMETER;
+    bool inside = active;
+    if (active) {
+        const double *p = q1 + first + c.lane;
+        id = (uint64_t)__double_as_longlong(p[0]);
+        if constexpr (SPECTRO) {
+            // queue b of the spectrometer variant: (id, direction, distance) of rays inside the bounds
+            const V3 d = v3(p[1 * P], p[2 * P], p[3 * P]);
+            const double t = p[4 * P];
+            const V3 o = v3(sc.source.origin);
+            const V3 X = v3(fma(d.x, t, o.x), fma(d.y, t, o.y), fma(d.z, t, o.z));
+            r.o = X;
+            r.d = d;
+        } else {
+            r.o = v3(p[1 * P], p[2 * P], p[3 * P]);
+            r.d = v3(p[4 * P], p[5 * P], p[6 * P]);
+            if constexpr (FT != 0) r.w = p[7 * P];
+            if constexpr ((FT & FT_MESH) != 0) n = v3(p[8 * P], p[9 * P], p[10 * P]);
+        }
+    }
+    __syncwarp();
+    PhiloxDraws dr;
+    dr.init(pk, stream_id, id, split);
+    if (inside) {
+        if (lazy && need_wave) {      // history is off here: a wavelength nobody tests is not drawn
+            SrcLocal L;
+            source_local<0, KN>(sc.source, id, L);
+            r.w = generate_wavelength<PhiloxDraws, KN, false>(sc.source, L, dr, r.d);   // lazy = no Doppler shift
+        }
+        if constexpr (FT != 0) {
+            if (defer) {              // r.w holds the Doppler factor (stage A); the same expressions as generate_wavelength
+                SrcLocal L;
+                source_local<FT, KN>(sc.source, id, L);
+                const double w0 = sc.source.wave_par[0] + L.wave_sigma * dr.wave_z();
+                r.w = (r.w != 1.0) ? w0 * r.w : w0;
+            }
+        }
+        bool analytic = true;
+        if constexpr ((FT & FT_MESH) != 0) analytic = ops.shape != XRT_SHAPE_MESH;
+        if (analytic) n = analytic_normal<FT, KN>(ops, r.o);
+        optic_interact<FT, PhiloxDraws, KN>(ops, split, dr, r, n);
+        if (r.alive && (flags_of<KN>(ops) & XRT_F_IMAGE) && out.images) add_pixel(out, ops, r, c.lt_mask);
+    }
+    const unsigned m = __ballot_sync(kFull, r.alive);
+    n_split += __popc(m);                  // survivors of the split optic: per-warp register counter
+    emit_lost<HIST>(out, c.lane, c.lt_mask, dr, active && !r.alive, id);
+
+    if (split + 1 >= sc.n_optics) {        // the split optic is the last one: survivors are found
+        emit_found<HIST>(out, c.lane, c.lt_mask, r.alive, id);
+        return;
+    }
+    // the caller keeps n2 <= kQ2Cap - 32
+    if (r.alive) {
+        double *p = q2 + n2 + __popc(m & c.lt_mask);
+        p[0] = __longlong_as_double((long long)id);
+        p[1 * kQ2Cap] = r.o.x; p[2 * kQ2Cap] = r.o.y; p[3 * kQ2Cap] = r.o.z;
+        p[4 * kQ2Cap] = r.d.x; p[5 * kQ2Cap] = r.d.y; p[6 * kQ2Cap] = r.d.z;
+        p[7 * kQ2Cap] = r.w;
+    }
+    n2 += __popc(m);
+    __syncwarp();
+}
+
+// ---- spectrometer variant, stage AB for one ray: direction from the cone block, the two lengths of the sphere
+// intersection, first level of the Bragg pre-test (sin(theta_i) = |D.n| is thc / R for a ray of unit direction:
+// D.(C - X) = tca - t = -thc, so the pre-test needs nothing else), intersection point and bounds (arithmetic of
+// optic_geometry), second level with the ray's rocking-curve uniform (the same Philox block stage B2 reads).
+// Returns true for a ray that goes on to stage B2.  A ray the pre-test rejects is lost at the crystal whether or
+// not it is inside the bounds.
+__device__ __forceinline__ bool spectro_stage_ab(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const PhiloxDraws &dr,
+                                                 int split, const double *s_sincos, bool valid, V3 &d_out, double &t_out) {
+    const XrtSourceDesc &src = sc.source;
+    double a, b;
+    dr.cone(0, a, b);
+    const double cs0 = src.cone_par[0];
+    const double z = cs0 + (1.0 - cs0) * a;
+    const double rho = fast_sqrt(fma(-z, z, 1.0));
+    double sn, cs;
+    sincos_2pi_tab(b, s_sincos, sn, cs);
+    const double lx = rho * cs, ly = rho * sn;
+    const double *B = src.axis_basis;
+    const V3 d = v3(lx * B[0] + ly * B[3] + z * B[6], lx * B[1] + ly * B[4] + z * B[7], lx * B[2] + ly * B[5] + z * B[8]);
+    // hit_sphere, concave
+    const V3 o = v3(src.origin);
+    const V3 Lc = v3(ops.center) - o;
+    const double tca = dot(Lc, d);
+    const double d2 = fma(-tca, tca, dot(Lc, Lc));
+    const double r2 = ops.radius * ops.radius;
+    const double thc = fast_sqrt(r2 - d2);          // NaN when d2 > r2
+    const double t = tca + thc;
+    d_out = d;
+    t_out = t;
+    bool cand = valid & (d2 >= 0.0) & (d2 <= r2);
+    double gap = -1.0, c2 = 1.0;
+    if (ops.cull_t2 > 0.0) cand &= !bragg_cull_sphere(src, ops, dr.wave_hi(), thc, gap, c2);
+    const V3 X = v3(fma(d.x, t, o.x), fma(d.y, t, o.y), fma(d.z, t, o.z));
+    const V3 Xl = to_local(ops.orient, X - v3(ops.origin));
+    cand &= (fabs(Xl.x) < ops.half_size[0]) & (fabs(Xl.y) < ops.half_size[1]);
+    if (ops.cull_t2 > 0.0 && ops.rocking_type != XRT_ROCK_STEP) {
+        const double u = dr.bragg_u(split, 0);
+        if (bragg_cull_uniform(ops, gap, c2, ops.cull_err, u)) cand = false;
+    }
+    return cand;
+}
+
+// Resident blocks per SM: 2 for the mesh variants (face loops and Clough-Tocher cubics keep many values live), for
+// the spectrometer variant (two ray groups per pass = two independent chains) and for the lean extended-source
+// variant (bundle lookup + focused cone basis); 3 otherwise.
+template <uint32_t FT, uint32_t KN> __host__ __device__ constexpr int trace_min_blocks() {
+    return (((FT & FT_MESH) != 0 || FT == FT_SRCLEAN || ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
+            XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS;
+}
+
+template <uint32_t FT, int SPLIT, uint32_t KN, bool HIST>
+__global__ void __launch_bounds__(kBlock, (trace_min_blocks<FT, KN>()))
+k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
+        const uint64_t ray_begin, const uint64_t ray_count, const XrtOutputs out, const IdList list, const int split_rt,
+        const int lazy_rt) {
+    extern __shared__ double s_queue[];
+    __shared__ unsigned long long s_cnt[XRT_MAX_OPTICS + 1];
+    if (threadIdx.x <= XRT_MAX_OPTICS) s_cnt[threadIdx.x] = 0ull;
+    // (cos, sin)(2 pi k / 256) for sincos_2pi_tab
+    __shared__ double s_sincos[2 * kSincosTable];
+    for (int i = threadIdx.x; i < kSincosTable; i += kBlock) {
+        double sn, cs;
+        sincos_2pi((double)i / (double)kSincosTable, sn, cs);
+        s_sincos[2 * i] = cs;
+        s_sincos[2 * i + 1] = sn;
+    }
+    __syncthreads();
+
+    constexpr bool SPECTRO = (KN & KN_SPECTROMETER) == KN_SPECTROMETER;
+    constexpr int P = SPECTRO ? kQbCap : kQ1Cap;
+    WarpCtx c;
+    c.lane = threadIdx.x & 31u;
+    c.lt_mask = (1u << c.lane) - 1u;
+    c.s_cnt = s_cnt;
+    const int warp = threadIdx.x >> 5;
+    double *q1 = s_queue + (size_t)warp * warp_queue_doubles<FT, KN>();     // spectrometer variant: queue b
+    double *q2 = q1 + q1_doubles<FT, KN>();
+
+    const int split = (SPLIT >= 0) ? SPLIT : split_rt;
+    const XrtOpticDesc &ops = sc.optics[split];
+    const bool lazy = (FT == 0) ? true : ((lazy_rt & 1) != 0);
+    const bool need_wave = (lazy_rt & 2) != 0;   // some optic from the split optic on reads the wavelength (Bragg test)
+    const bool defer = (FT == 0) ? false : ((lazy_rt & 4) != 0);   // eager normal line: exact deviate left to stage B
+    const bool count_src = list.ids == nullptr;  // list mode: k_cull32 has counted the rays out of the source
+
+    // mesh split optic: stage the face operands every ray is tested against in shared memory
+    const double *staged = nullptr;
+    if constexpr ((FT & FT_MESH) != 0) {
+        if (ops.shape == XRT_SHAPE_MESH) {
+            const double *geom;
+            const int nf = mesh_stage1_faces(ops, geom);
+            if (nf <= kStageFaces) {
+                double *dst = s_queue + (size_t)(kBlock / 32) * warp_queue_doubles<FT, KN>();
+                for (int i = threadIdx.x; i < 9 * nf; i += kBlock) dst[i] = __ldg(geom + i);
+                staged = dst;
+            }
+        }
+        __syncthreads();
+    }
+    int n1 = 0, n2 = 0;     // queue fill levels, warp-uniform
+    // mesh variants: queue a (coarse-mesh hits) after the planes of queue 1.  Stage A is split in two when the split
+    // optic is the first optic, a refining mesh, and the wavelength is lazy (a ray is rebuilt from its id in stage A2)
+    int na = 0;
+    double *qa = q1 + q1_planes<FT>() * kQ1Cap;
+    bool mesh_staged = false;
+    if constexpr ((FT & FT_MESH) != 0 && !SPECTRO) {
+        mesh_staged = split == 0 && ops.shape == XRT_SHAPE_MESH && (ops.flags & XRT_F_MESH_REFINE) && lazy &&
+                      sc.source.kind != XRT_SRC_BUNDLES && sc.source.cone != XRT_CONE_ISOTROPIC_XY;
+    }
+    unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
+
+    IdCursor cur;
+    cur.init(list, ray_begin, ray_count, blockIdx.x * (kBlock / 32) + warp, gridDim.x * (kBlock / 32));
+
+    // One loop, one copy of each stage: the deepest stage that has a full warp of work runs
+    // first; when the ids are exhausted the queues are drained with partial warps.
+    for (;;) {
+        const bool more = cur.more();
+        if (n2 >= 32 || (!more && n1 == 0 && na == 0 && n2 > 0)) {
+            const int cnt = n2 < 32 ? n2 : 32;
+            n2 -= cnt;
+            stage_c<FT, HIST>(sc, out, c, split, pk, stream_id, q2, n2, cnt);
+            continue;
+        }
+        if (n1 >= 32 || (!more && na == 0 && n1 > 0)) {
+            const int cnt = n1 < 32 ? n1 : 32;
+            n1 -= cnt;
+            stage_b<FT, KN, HIST>(sc, ops, out, c, split, lazy, need_wave, defer, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
+            continue;
+        }
+        if constexpr ((FT & FT_MESH) != 0 && !SPECTRO) {
+            if (na >= 32 || (!more && na > 0)) {
+                // ---- stage A2: the coarse-mesh hits, re-packed: rebuild the ray from its id, finish the mesh
+                // intersection from the coarse hit point (nearest vertex, candidate faces, interpolation), bounds
+                const int cnt = na < 32 ? na : 32;
+                na -= cnt;
+                const bool active = (int)c.lane < cnt;
+                uint64_t id = 0;
+                V3 Xc = nan3();
+                if (active) {
+                    const double *p = qa + na + c.lane;
+                    id = (uint64_t)__double_as_longlong(p[0]);
+                    Xc = v3(p[1 * kQaCap], p[2 * kQaCap], p[3 * kQaCap]);
+                }
+                __syncwarp();
+                PhiloxDraws dr;
+                dr.init(pk, stream_id, id, split);
+                Ray r;
+                r.alive = false;
+                r.w = 0.0;
+                V3 n = v3(0.0, 0.0, 1.0);
+                bool cand = false;
+                if (active) {
+                    SrcLocal L;
+                    source_local<FT, KN>(sc.source, id, L);
+                    generate_geometry<FT, PhiloxDraws, KN, true>(sc.source, L, dr, r, s_sincos);
+                    cand = optic_geometry<FT, true, KN>(ops, r, n, staged, &Xc) == HIT_INSIDE;
+                }
+                emit_lost<HIST>(out, c.lane, c.lt_mask, dr, active && !cand, id);
+                const unsigned m = __ballot_sync(kFull, cand);
+                if (cand) {
+                    double *p = q1 + n1 + __popc(m & c.lt_mask);
+                    p[0] = __longlong_as_double((long long)id);
+                    p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
+                    p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
+                    p[7 * P] = r.w;
+                    p[8 * P] = n.x; p[9 * P] = n.y; p[10 * P] = n.z;
+                }
+                n1 += __popc(m);
+                __syncwarp();
+                continue;
+            }
+        }
+        if (!more) break;
+
+        // ---- stage A
+        if constexpr (SPECTRO) {
+            // Straight-line code for the spectrometer (point source, concave sphere); kUnroll groups of 32 ids per
+            // pass: independent dependency chains for the scheduler.
+            uint64_t idv[kUnroll];
+            bool validv[kUnroll], candv[kUnroll];
+            V3 dv[kUnroll];
+            double tv[kUnroll];
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) cur.next(c.lane, idv[j], validv[j]);
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                PhiloxDraws dr;
+                dr.init(pk, stream_id, idv[j], split);
+                candv[j] = spectro_stage_ab(sc, ops, dr, split, s_sincos, validv[j], dv[j], tv[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                if (count_src) n_src += __popc(__ballot_sync(kFull, validv[j]));
+                if constexpr (HIST) {
+                    if (out.lost_count) {
+                        PhiloxDraws dr;
+                        dr.init(pk, stream_id, idv[j], split);
+                        emit_lost<HIST>(out, c.lane, c.lt_mask, dr, validv[j] && !candv[j], idv[j]);
+                    }
+                }
+                const unsigned m = __ballot_sync(kFull, candv[j]);
+                if (candv[j]) {
+                    double *p = q1 + n1 + __popc(m & c.lt_mask);
+                    p[0] = __longlong_as_double((long long)idv[j]);
+                    p[1 * P] = dv[j].x; p[2 * P] = dv[j].y; p[3 * P] = dv[j].z;
+                    p[4 * P] = tv[j];
+                }
+                n1 += __popc(m);
+            }
+            __syncwarp();
+        } else {
+            uint64_t id;
+            bool valid;
+            cur.next(c.lane, id, valid);
+            PhiloxDraws dr;
+            dr.init(pk, stream_id, id, split);
+            Ray r;
+            r.alive = false;
+            r.w = 0.0;
+            double sigma_a = 0.0;
+            if (valid) {
+                SrcLocal L;
+                source_local<FT, KN>(sc.source, id, L);
+                generate_geometry<FT, PhiloxDraws, KN, true>(sc.source, L, dr, r, s_sincos);
+                if (defer) {
+                    // normal line with a Doppler shift and / or a per-bundle sigma: the exact deviate (inverse normal
+                    // CDF, a second Philox block) is left to stage B; here the Doppler factor, and sigma for the pre-test
+                    const bool moving = L.vel.x != 0.0 || L.vel.y != 0.0 || L.vel.z != 0.0;
+                    r.w = moving ? 1.0 - dot(L.vel, r.d) : 1.0;
+                    sigma_a = L.wave_sigma;
+                } else if (!lazy) {
+                    r.w = generate_wavelength<PhiloxDraws, KN>(sc.source, L, dr, r.d);
+                }
+            }
+            if (count_src) n_src += __popc(__ballot_sync(kFull, r.alive));
+            for (int k = 0; k < split; ++k) {
+                const XrtOpticDesc &op = sc.optics[k];
+                if (r.alive) {
+                    trace_optic<FT>(op, k, dr, r);
+                    if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
+                }
+                count_alive(c, k + 1, r.alive);
+            }
+            V3 n = v3(0.0, 0.0, 1.0);
+            bool cand = false;
+            if constexpr ((FT & FT_MESH) != 0) {
+                if (mesh_staged) {
+                    // ---- stage A1: coarse mesh only; the hits go to queue a as (id, coarse hit point)
+                    V3 Xc = nan3();
+                    bool hit = false;
+                    if (r.alive) {
+                        V3 o = r.o, d = r.d;
+                        if (optic_is_local<FT>(ops)) {
+                            o = to_local(ops.orient, o - v3(ops.origin));
+                            d = to_local(ops.orient, d);
+                        }
+                        hit = mesh_coarse_hit(ops, o, d, Xc, staged);
+                    }
+                    emit_lost<HIST>(out, c.lane, c.lt_mask, dr, valid && !hit, id);
+                    const unsigned mh = __ballot_sync(kFull, hit);
+                    if (hit) {
+                        double *p = qa + na + __popc(mh & c.lt_mask);
+                        p[0] = __longlong_as_double((long long)id);
+                        p[1 * kQaCap] = Xc.x; p[2 * kQaCap] = Xc.y; p[3 * kQaCap] = Xc.z;
+                    }
+                    na += __popc(mh);
+                    __syncwarp();
+                    continue;
+                }
+            }
+            if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
+            // Bragg pre-test (bragg_cull_general): enabled by xrt_scene_create for a spherical Bragg crystal traced in
+            // global coordinates; first level with the (approximate / exact / deferred) wavelength, second level with
+            // the ray's rocking-curve uniform; the survivors take the exact path in stage B
+            if (ops.cull_t2 > 0.0) {
+                if (cand) {
+                    const int mode = defer ? WAVE_DEFERRED : (lazy ? WAVE_APPROX : WAVE_EXACT);
+                    double gap, c2, err;
+                    bool lost = bragg_cull_general(sc.source, ops, mode, r.w, sigma_a, dr.wave_hi(), r.o, r.d, gap, c2, err);
+                    if (!lost && ops.rocking_type != XRT_ROCK_STEP && gap >= 0.0)
+                        lost = bragg_cull_uniform(ops, gap, c2, err, dr.bragg_u(split, 0));
+                    if (lost) {
+                        cand = false;
+                        r.alive = false;
+                    }
+                }
+            }
+            emit_lost<HIST>(out, c.lane, c.lt_mask, dr, valid && !cand, id);
+
+            const unsigned m = __ballot_sync(kFull, cand);
+            if (cand) {
+                double *p = q1 + n1 + __popc(m & c.lt_mask);
+                p[0] = __longlong_as_double((long long)id);
+                p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
+                p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
+                if constexpr (FT != 0) p[7 * P] = r.w;
+                if constexpr ((FT & FT_MESH) != 0) { p[8 * P] = n.x; p[9 * P] = n.y; p[10 * P] = n.z; }
+            }
+            n1 += __popc(m);
+            __syncwarp();
+        }
+    }
+
+    if (c.lane == 0) {
+        if (n_src) atomicAdd(&s_cnt[0], (unsigned long long)n_src);
+        if (n_split) atomicAdd(&s_cnt[split + 1], (unsigned long long)n_split);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x <= sc.n_optics && out.counts) {
+        unsigned long long cc = s_cnt[threadIdx.x];
+        if (cc) atomicAdd((unsigned long long *)(out.counts + threadIdx.x), cc);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// FP32 broad phase (k_cull32)
+//
+// For a scene whose first optic is a spherical Bragg crystal (Gaussian or step rocking curve, traced in global
+// coordinates) almost every ray fails the rocking-curve test by many widths.  With sB = lambda / 2d = sin(theta_B) and
+// sI = |D.n| = sin(theta_i) = thc / R (thc = half chord of the ray through the sphere, |D| = 1),
+//     (|sB - sI| - err)^2 > T^2 ((1 - sI^2) + 2 |sB - sI|)   ==>   |theta_B - theta_i| > T,
+// T beyond the angle where the rocking curve is zero (step) or below 2^-57 (Gaussian).  Every quantity of that test
+// is a function of the ray's first Philox blocks; evaluated in single precision (MUFU sqrt / sin / cos / lg2) from
+// the same blocks it is within ~1e-6 of the FP64 value, and `err` carries a 2e-5 margin for it (x |C - O|^2 / R^2;
+// tests/test_host_logic.py restates the arithmetic in numpy float32 and checks the error budget).  A ray the test
+// rejects is lost at the crystal whatever its uniform; everything else -- including rays that miss the sphere, give
+// a NaN here or have a deviate beyond the range of normal_approx -- is written to the id list and decided in FP64
+// by k_trace, so results are identical with the phase switched off.
+//
+// SRC: 0 point source with a fixed axis; 1 box source with a fixed axis; 2 box source focused on a target; 3 plasma
+// bundles (per-ray voxel origin, cone, line width and velocity from the bundle table).  Lines: constant or normal,
+// with or without a Doppler shift.
+
+enum { CULL_POINT = 0, CULL_BOX = 1, CULL_FOCUSED = 2, CULL_BUNDLES = 3 };
+
+struct Cull32Par {
+    float one_m_cos;       // 1 - cos(spread)                                     (not bundles)
+    float basis[9];        // fixed axis: rows o_2, o_1, axis of the cone basis
+    float Lb[3];           // C - source origin                                   (not bundles)
+    float r2, inv_r, inv_r2;   // sphere
+    float lam0, sig, inv_two_d;
+    float t2, err;         // cull_t2; cull_err (+ the geometric margin for a point source, else added per ray from |C - O|^2)
+    float R[9];            // source orientation rows: world offset = off . R
+    float ext[3];          // box sizes (bundles: voxel size x 3)
+    float Tb[3];           // target - source origin                              (focused)
+    float xz[3];           // source xaxis + zaxis: o_1 = unit(axis x xz)
+    float vel[3];          // velocity / c                                        (not bundles)
+    float err_sig;         // 2e-3 |inv_two_d|: approximate-deviate term of err per unit sigma (bundles)
+    int32_t moving;        // Doppler shift present
+    int32_t normal_line;   // XRT_WAVE_NORMAL (else constant)
+    double C[3], T[3];     // sphere centre and target in FP64 (bundles: per-ray differences formed in FP64 once)
+};
+
+struct Cull32Out {
+    uint32_t *ids;         // [n_regions][cap]
+    uint32_t *counts;      // [n_regions]
+    uint32_t n_regions, cap;
+};
+
+#ifndef XRT_CULL_UNROLL
+#define XRT_CULL_UNROLL 2
+#endif
+#ifndef XRT_CULL_BLOCKS
+#define XRT_CULL_BLOCKS 6
+#endif
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// true = provably lost at the crystal
+template <int SRC>
+__device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
+                                           uint64_t id) {
+    const uint32_t lo = (uint32_t)id, hi = (uint32_t)(id >> 32);
+    const uint4 r = philox4x32_10(make_uint4(lo, hi, SITE_CONE, stream), pk);
+
+    float one_m_cos = K.one_m_cos, sig = K.sig, err = K.err;
+    float Lx = K.Lb[0], Ly = K.Lb[1], Lz = K.Lb[2];
+    float Tx = K.Tb[0], Ty = K.Tb[1], Tz = K.Tb[2];
+    float vx = K.vel[0], vy = K.vel[1], vz = K.vel[2];
+    if constexpr (SRC == CULL_BUNDLES) {
+        // bundle of this ray: first b with bundle_end[b] > id (same search as source_local)
+        uint64_t blo = 0, bhi = src.n_bundles - 1;
+        if (src.bundle_hint) {
+            const uint64_t j = id >> src.bundle_hint_shift;
+            blo = __ldg(src.bundle_hint + j);
+            bhi = __ldg(src.bundle_hint + j + 1);
+        }
+        while (blo < bhi) {
+            const uint64_t mid = (blo + bhi) >> 1;
+            if (__ldg(src.bundle_end + mid) > id) bhi = mid; else blo = mid + 1;
+        }
+        const XrtBundle *bd = src.bundles + blo;
+        const double ox = __ldg(&bd->origin[0]), oy = __ldg(&bd->origin[1]), oz = __ldg(&bd->origin[2]);
+        Lx = (float)(K.C[0] - ox); Ly = (float)(K.C[1] - oy); Lz = (float)(K.C[2] - oz);
+        Tx = (float)(K.T[0] - ox); Ty = (float)(K.T[1] - oy); Tz = (float)(K.T[2] - oz);
+        one_m_cos = (float)(1.0 - __ldg(&bd->cos_spread));
+        sig = (float)__ldg(&bd->wave_sigma);
+        err = fmaf(K.err_sig, fabsf(sig), K.err);
+        vx = (float)__ldg(&bd->velocity_c[0]); vy = (float)__ldg(&bd->velocity_c[1]); vz = (float)__ldg(&bd->velocity_c[2]);
+    }
+
+    // ---- origin offset in world coordinates (the exact path: u01_42x3 of one block, off_k = ext_k (u_k - 1/2))
+    if constexpr (SRC != CULL_POINT) {
+        const uint4 ro = philox4x32_10(make_uint4(lo, hi, SITE_ORIGIN_XY, stream), pk);
+        const float s32 = 2.3283064365386963e-10f;
+        const float o0 = K.ext[0] * fmaf((float)ro.x, s32, -0.5f);
+        const float o1 = K.ext[1] * fmaf((float)((ro.y << 10) | (ro.z >> 22)), s32, -0.5f);
+        const float o2 = K.ext[2] * fmaf((float)((ro.z << 20) | (ro.w >> 12)), s32, -0.5f);
+        const float wx = o0 * K.R[0] + o1 * K.R[3] + o2 * K.R[6];
+        const float wy = o0 * K.R[1] + o1 * K.R[4] + o2 * K.R[7];
+        const float wz = o0 * K.R[2] + o1 * K.R[5] + o2 * K.R[8];
+        Lx -= wx; Ly -= wy; Lz -= wz;
+        Tx -= wx; Ty -= wy; Tz -= wz;
+    }
+
+    // ---- local cone vector: 1 - a from all 52 bits of the polar uniform (complement of the mantissa): its RELATIVE
+    // precision is what rho = sqrt(w (2 - w)) near the cone axis needs
+    const float a1 = fmaf((float)((~r.y) >> 12), 2.220446049250313e-16f, fmaf((float)(~r.x), 2.3283064365386963e-10f,
+                                                                                2.220446049250313e-16f));
+    const float w = one_m_cos * a1;                                                     // 1 - z
+    const float z = 1.0f - w;
+    const float rho = sqrt_approx(w * (2.0f - w));
+    const uint32_t b24 = ((r.y & 0xfffu) << 12) | (r.z >> 20);                          // top 24 bits of the azimuth uniform
+    const float ang = 6.283185307179586f * ((float)b24 * 5.9604644775390625e-8f - 0.5f);
+    const float lx = -rho * __cosf(ang), ly = -rho * __sinf(ang);                       // cos(2 pi b) = -cos(2 pi (b - 1/2))
+
+    // ---- direction
+    float dx, dy, dz;
+    if constexpr (SRC == CULL_POINT || SRC == CULL_BOX) {
+        dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
+        dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
+        dz = lx * K.basis[2] + ly * K.basis[5] + z * K.basis[8];
+    } else {
+        // axis = unit(target - origin); o_1 = unit(axis x (xaxis + zaxis)); o_2 = axis x o_1 (unit up to rounding)
+        const float it = rsqrt_approx(Tx * Tx + Ty * Ty + Tz * Tz);
+        const float ax = Tx * it, ay = Ty * it, az = Tz * it;
+        float px = ay * K.xz[2] - az * K.xz[1], py = az * K.xz[0] - ax * K.xz[2], pz = ax * K.xz[1] - ay * K.xz[0];
+        const float ip = rsqrt_approx(px * px + py * py + pz * pz);
+        px *= ip; py *= ip; pz *= ip;
+        const float qx = ay * pz - az * py, qy = az * px - ax * pz, qz = ax * py - ay * px;
+        dx = lx * qx + ly * px + z * ax;
+        dy = lx * qy + ly * py + z * ay;
+        dz = lx * qz + ly * pz + z * az;
+    }
+
+    // ---- sphere chord
+    const float tca = Lx * dx + Ly * dy + Lz * dz;
+    const float ll = Lx * Lx + Ly * Ly + Lz * Lz;
+    const float d2 = fmaf(-tca, tca, ll);
+    const float thc = sqrt_approx(K.r2 - d2);
+    const float sI = thc * K.inv_r;
+    bool usable = true;
+    if constexpr (SRC != CULL_POINT) {
+        // geometric margin 2e-5 max(1, |C - O|^2 / R^2); beyond 2 R from the centre of curvature the ray is left to FP64
+        const float q = ll * K.inv_r2;
+        err = fmaf(2e-5f, fmaxf(1.0f, q), err);
+        usable = q <= 4.0f;
+    }
+
+    // ---- sin(theta_B)
+    float lam = K.lam0;
+    if (K.normal_line) {
+        bool in_range;
+        lam = fmaf(normal_approx(r.w, in_range), sig, lam);
+        usable &= in_range;
+    }
+    if (SRC == CULL_BUNDLES || K.moving) lam *= 1.0f - (vx * dx + vy * dy + vz * dz);
+    const float sB = lam * K.inv_two_d;
+
+    const float gap = fabsf(sB - sI);
+    const float diff = gap - err;
+    const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
+    return usable & (diff > 0.0f) & (diff * diff > K.t2 * c2);
+}
+
+template <int SRC, bool HIST>
+__global__ void __launch_bounds__(kBlock, XRT_CULL_BLOCKS)
+k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceDesc src, const __grid_constant__ PhiloxKeys pk,
+         const uint64_t stream_id, const uint64_t ray_begin, const uint64_t ray_count, const Cull32Out lst,
+         const XrtOutputs out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t n_warps = gridDim.x * (kBlock / 32);
+    const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const uint32_t stream = (uint32_t)stream_id;
+    unsigned long long n_src = 0;
+    for (uint32_t reg = warp_global; reg < lst.n_regions; reg += n_warps) {
+        const uint64_t first = (uint64_t)reg * lst.cap;
+        const uint64_t left = ray_count - first;
+        const uint32_t n_here = left < (uint64_t)lst.cap ? (uint32_t)left : lst.cap;
+        uint32_t *dst = lst.ids + first;
+        uint32_t kept = 0;
+        n_src += n_here;
+        for (uint32_t g = 0; g < n_here; g += 32u * XRT_CULL_UNROLL) {
+            bool valid[XRT_CULL_UNROLL], pass[XRT_CULL_UNROLL];
+            uint32_t off[XRT_CULL_UNROLL];
+#pragma unroll
+            for (int j = 0; j < XRT_CULL_UNROLL; ++j) {
+                off[j] = g + 32u * j + lane;
+                valid[j] = off[j] < n_here;
+                pass[j] = valid[j] && !cull32_ray<SRC>(K, src, pk, stream, ray_begin + first + off[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < XRT_CULL_UNROLL; ++j) {
+                if constexpr (HIST) {
+                    if (out.lost_count) {
+                        PhiloxDraws dr;
+                        dr.init(pk, stream_id, ray_begin + first + off[j], 0);
+                        emit_lost<true>(out, lane, lt_mask, dr, valid[j] && !pass[j], ray_begin + first + off[j]);
+                    }
+                }
+                const unsigned m = __ballot_sync(kFull, pass[j]);
+                if (pass[j]) dst[kept + __popc(m & lt_mask)] = (uint32_t)first + off[j];
+                kept += __popc(m);
+            }
+        }
+        if (lane == 0) lst.counts[reg] = kept;
+    }
+    // rays out of the source: one atomic per block
+    __shared__ unsigned long long s_src;
+    if (threadIdx.x == 0) s_src = 0ull;
+    __syncthreads();
+    if (lane == 0 && n_src) atomicAdd(&s_src, n_src);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_src && out.counts) atomicAdd((unsigned long long *)out.counts, s_src);
+}
+
+// ---------------------------------------------------------------------------
+// recording kernel: history of every element, optional counters / images
+
+// streaming stores (evict-first): history planes are written once and read back by the host
+__device__ __forceinline__ void store_history(const XrtHistory &h, int elem, uint64_t slot, const Ray &r) {
+    if (h.rays) {
+        double *p = h.rays + ((uint64_t)elem * 7) * h.capacity + slot;
+        const uint64_t c = h.capacity;
+        __stcs(p, r.o.x); __stcs(p + c, r.o.y); __stcs(p + 2 * c, r.o.z);
+        __stcs(p + 3 * c, r.d.x); __stcs(p + 4 * c, r.d.y); __stcs(p + 5 * c, r.d.z);
+        __stcs(p + 6 * c, r.w);
+    }
+    if (h.mask) h.mask[(uint64_t)elem * h.capacity + slot] = r.alive ? 1 : 0;
+}
+
+enum { REC_PHILOX = 0, REC_INJECT = 1 };
+
+// KN != 0: the scene has the known structure (split optic = optic 0), see k_trace
+template <uint32_t FT, int MODE, uint32_t KN = 0>
+__global__ void __launch_bounds__(kBlock, (FT & FT_MESH) != 0 ? 2 : XRT_RECORD_BLOCKS)   // 3 x 256 at 78 registers: the replay is latency bound
+k_record(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
+         const uint64_t *__restrict__ ids, const uint64_t ray_begin, const uint64_t n,
+         const XrtRaysIn in, const XrtInject inj, const XrtOutputs out, const XrtHistory hist, const int split) {
+    // the same azimuth routine as the fused kernel (sincos_2pi_tab), so that a replayed ray is bit for bit the ray
+    // the fused kernel classified
+    __shared__ double s_sincos[MODE == REC_PHILOX ? 2 * kSincosTable : 2];
+    if constexpr (MODE == REC_PHILOX) {
+        for (int i = threadIdx.x; i < kSincosTable; i += kBlock) {
+            double sn, cs;
+            sincos_2pi((double)i / (double)kSincosTable, sn, cs);
+            s_sincos[2 * i] = cs;
+            s_sincos[2 * i + 1] = sn;
+        }
+        __syncthreads();
+    }
+    const int nopt = sc.n_optics;
+    const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        Ray r;
+        PhiloxDraws pdr;
+        InjectedDraws idr;
+        if constexpr (MODE == REC_PHILOX) {
+            const uint64_t id = ids ? ids[i] : ray_begin + i;
+            pdr.init(pk, stream_id, id, split);
+            generate_ray<FT, PhiloxDraws, KN, true>(sc.source, pdr, id, r, s_sincos);
+        } else {
+            r.o = v3(in.origin + 3 * i);
+            r.d = v3(in.direction + 3 * i);
+            r.w = in.wavelength[i];
+            r.alive = in.mask[i] != 0;
+            idr.inj = &inj;
+            idr.i = i;
+            idr.n = n;
+        }
+        store_history(hist, 0, i, r);
+        if (out.counts && r.alive) atomicAdd((unsigned long long *)out.counts, 1ull);
+
+        for (int k = 0; k < nopt; ++k) {
+            const XrtOpticDesc &op = sc.optics[k];
+            if (r.alive) {
+                if constexpr (MODE == REC_PHILOX) {
+                    if (KN != 0 && k == 0) trace_optic<FT, PhiloxDraws, KN>(op, k, pdr, r);
+                    else trace_optic<FT>(op, k, pdr, r);
+                } else {
+                    trace_optic<FT>(op, k, idr, r);
+                }
+                if (r.alive) {
+                    if (out.counts) atomicAdd((unsigned long long *)(out.counts + k + 1), 1ull);
+                    uint32_t pix;
+                    if ((op.flags & XRT_F_IMAGE) && out.images && pixel_index(op, r.o, pix))
+                        atomicAdd((unsigned long long *)(out.images + op.image_offset + pix), 1ull);
+                }
+            } else {
+                pass_lost_ray<FT>(op, r);   // lost earlier: the reference carries NaN origins forward
+            }
+            store_history(hist, k + 1, i, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// source only
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_source(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
+         const uint64_t ray_begin, const uint64_t n, const XrtSourceInject sinj, const XrtHistory hist) {
+    __shared__ double s_sincos[MODE == REC_PHILOX ? 2 * kSincosTable : 2];
+    if constexpr (MODE == REC_PHILOX) {
+        for (int i = threadIdx.x; i < kSincosTable; i += kBlock) {
+            double sn, cs;
+            sincos_2pi((double)i / (double)kSincosTable, sn, cs);
+            s_sincos[2 * i] = cs;
+            s_sincos[2 * i + 1] = sn;
+        }
+        __syncthreads();
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        Ray r;
+        if constexpr (MODE == REC_PHILOX) {
+            PhiloxDraws dr;
+            dr.init(pk, stream_id, ray_begin + i, -1);
+            generate_ray<FT_FULL, PhiloxDraws, 0, true>(sc.source, dr, ray_begin + i, r, s_sincos);
+        } else {
+            SourceInjectedDraws dr;
+            dr.inj = &sinj;
+            dr.i = i;
+            dr.n = n;
+            generate_ray<FT_FULL>(sc.source, dr, ray_begin + i, r);
+        }
+        store_history(hist, 0, i, r);
+    }
+}
+
+}  // namespace xrt

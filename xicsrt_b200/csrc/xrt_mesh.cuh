@@ -210,7 +210,7 @@ __device__ __forceinline__ bool mesh_coarse_hit(const XrtOpticDesc &op, V3 o, V3
 
 // Not inlined: the fused kernel reaches it from four places (optics before / at / after the split optic, stage A2)
 // and four inlined copies made the mesh variants 250 kB of code -- instruction-cache stalls of 4.5 cycles per issue.
-__device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
+static __device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
                                             const double *staged = nullptr, const V3 *resume_Xc = nullptr) {
     const XrtMesh &m = *op.mesh;
     X = nan3();

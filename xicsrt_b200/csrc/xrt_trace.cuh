@@ -79,8 +79,10 @@ struct Ray {
 __device__ __forceinline__ uint32_t site_optic(int k, int layer, int which) {
     return ((uint32_t)(k + 1) << 16) | ((uint32_t)layer << 1) | (uint32_t)which;
 }
+// retries of the isotropic_xy rejection sampler live in their own tagged range (bit 30), disjoint from the optic
+// sites ((k + 1) << 16 | ...) for any number of attempts and from the plasma bundle sites (0xB0000000 | ...)
 enum : uint32_t { SITE_ORIGIN_XY = 0, SITE_ORIGIN_Z = 1, SITE_CONE = 2, SITE_WAVE = 3,
-                  SITE_LOSTKEY = 4, SITE_CONE_RETRY = 0x100 };
+                  SITE_LOSTKEY = 4, SITE_CONE_RETRY = 0x40000000u };
 
 struct PhiloxDraws {
     const PhiloxKeys *keys;   // round keys of (seed, stream_id): a __grid_constant__ kernel parameter
@@ -271,6 +273,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
 
     // ---- local cone vector (xicsrt_spread.py:80-294)
     V3 l;
+    bool xy_exhausted = false;      // isotropic_xy: no direction accepted in 100000 attempts (window of measure ~0)
     int cone = XRT_CONE_ISOTROPIC;
     if constexpr ((FT & FT_SRC_EXT) != 0) cone = s.cone;
     if (cone == XRT_CONE_ISOTROPIC) {
@@ -292,6 +295,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
         const double x_lo = per_bundle ? -v : s.cone_par[0], x_hi = per_bundle ? v : s.cone_par[1];
         const double y_lo = per_bundle ? -v : s.cone_par[2], y_hi = per_bundle ? v : s.cone_par[3];
         l = v3(0.0, 0.0, 1.0);
+        xy_exhausted = true;
         for (int attempt = 0; attempt < 100000; ++attempt) {
             double a, b;
             dr.cone(attempt, a, b);
@@ -303,7 +307,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
             double sx = x / sqrt(x * x + z * z);
             double sy = y / sqrt(y * y + z * z);
             l = v3(x, y, z);
-            if (sx > x_lo && sx <= x_hi && sy > y_lo && sy <= y_hi) break;
+            if (sx > x_lo && sx <= x_hi && sy > y_lo && sy <= y_hi) { xy_exhausted = false; break; }
         }
     } else {
         double a, b, a0, s1, c1;
@@ -346,7 +350,7 @@ __device__ __forceinline__ void generate_geometry(const XrtSourceDesc &s, const 
              l.x * o2.z + l.y * o1.z + l.z * ax.z);
 
     // ---- source-level sightline filters (_XicsrtBundleFilterSightline.py:31-56)
-    r.alive = true;
+    r.alive = !xy_exhausted;        // the reference loops until it has N accepted rays; a ray that cannot be drawn is dropped
     if constexpr ((FT & FT_SRC_EXT) != 0) {
         for (int f = 0; f < s.n_sightlines; ++f) {
             const XrtSightline &sl = s.sightlines[f];
@@ -391,11 +395,12 @@ __device__ __forceinline__ bool wavelength_is_lazy(const XrtSourceDesc &s) {
     return s.kind != XRT_SRC_BUNDLES && s.velocity_c[0] == 0.0 && s.velocity_c[1] == 0.0 && s.velocity_c[2] == 0.0;
 }
 
-template <uint32_t FT, class DR, uint32_t KN = 0>
-__device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &dr, uint64_t index, Ray &r) {
+template <uint32_t FT, class DR, uint32_t KN = 0, bool USE_TABLE = false>
+__device__ __forceinline__ void generate_ray(const XrtSourceDesc &s, const DR &dr, uint64_t index, Ray &r,
+                                             const double *sincos_table = nullptr) {
     SrcLocal L;
     source_local<FT, KN>(s, index, L);
-    generate_geometry<FT, DR, KN>(s, L, dr, r);
+    generate_geometry<FT, DR, KN, USE_TABLE>(s, L, dr, r, sincos_table);
     r.w = generate_wavelength<DR, KN>(s, L, dr, r.d);
 }
 
@@ -644,10 +649,10 @@ __device__ __forceinline__ bool bragg_cull_sphere(const XrtSourceDesc &s, const 
 // With the lower bound on |dtheta| of the first level, x >= (gap - err)^2 / (c2 two_sigma2); if that exceeds
 // ln(reflectivity / u) (taken 1e-3 + 0.1 % too large: FP32 logarithm of a rounded u) the ray is lost.
 // u = 0 gives an infinite bound: never rejected here.
-__device__ __forceinline__ bool bragg_cull_uniform(const XrtOpticDesc &op, double gap, double c2, double u) {
+__device__ __forceinline__ bool bragg_cull_uniform(const XrtOpticDesc &op, double gap, double c2, double err, double u) {
     const float lim = 0.6931471805599453f * (lg2_approx((float)op.reflectivity) - lg2_approx((float)u));   // ln(refl / u)
     const double bound = (double)fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * op.rock_two_sigma2;   // on dtheta^2
-    const double diff = gap - op.cull_err;
+    const double diff = gap - err;
     return (diff > 0.0) & (diff * diff > bound * c2) & (lim == lim);
 }
 
@@ -658,7 +663,8 @@ __device__ __forceinline__ bool bragg_cull_uniform(const XrtOpticDesc &op, doubl
 //                 `lambda` holds the Doppler factor 1 - v.D / c and `sigma` the line's sigma for this ray
 enum { WAVE_EXACT = 0, WAVE_APPROX = 1, WAVE_DEFERRED = 2 };
 __device__ __forceinline__ bool bragg_cull_general(const XrtSourceDesc &s, const XrtOpticDesc &op, int mode,
-                                                   double lambda, double sigma, uint32_t wave_hi, V3 X, V3 d) {
+                                                   double lambda, double sigma, uint32_t wave_hi, V3 X, V3 d,
+                                                   double &gap_out, double &c2_out, double &err_out) {
     bool usable = true;
     double err = op.cull_err;
     if (mode == WAVE_APPROX) {
@@ -670,7 +676,14 @@ __device__ __forceinline__ bool bragg_cull_general(const XrtSourceDesc &s, const
         err += err;
     }
     const double sI = fabs(dot(d, v3(op.center) - X)) * op.cull_inv_r;
-    return bragg_cull_test(op, lambda * op.inv_two_d, sI, usable, err);
+    const double sB = lambda * op.inv_two_d;
+    const double gap = fabs(sB - sI);
+    const double diff = gap - err;
+    const double c2 = fma(2.0, gap, fma(-sI, sI, 1.0));
+    gap_out = usable ? gap : -1.0;          // -1: no second level either (the approximate deviate is out of range)
+    c2_out = c2;
+    err_out = err;
+    return usable & (diff > 0.0) & (diff * diff > op.cull_t2 * c2);
 }
 
 // true = reflected.  p = rocking(dtheta) * reflectivity, keep when p >= u (:186-196).

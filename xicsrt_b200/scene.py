@@ -401,7 +401,14 @@ class DeviceScene:
     def launch_info(self):
         g, b, r, p = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         L.check(self.lib.xrt_launch_info(self.handle, C.byref(g), C.byref(b), C.byref(r), C.byref(p)))
-        return {'grid': g.value, 'block': b.value, 'registers': r.value, 'blocks_per_sm': p.value}
+        info = {'grid': g.value, 'block': b.value, 'registers': r.value, 'blocks_per_sm': p.value}
+        m = C.c_int32()
+        L.check(self.lib.xrt_launch_info_cull(self.handle, C.byref(m), C.byref(g), C.byref(r), C.byref(p)))
+        # FP32 broad phase in front of the fused kernel: None when it does not apply to this scene
+        info['broad_phase'] = None if m.value < 0 else {
+            'source_kind': ('point', 'box', 'focused', 'bundles')[m.value], 'grid': g.value, 'registers': r.value,
+            'blocks_per_sm': p.value}
+        return info
 
 
 def prepare(config, poisson=None):
