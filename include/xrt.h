@@ -166,6 +166,12 @@ typedef struct XrtOpticDesc {
     double cull_t2;          /* (1.05 angle beyond which the rocking curve is 0 or < 2^-57 + 2e-6)^2 */
     double cull_err;         /* bound on the error of the approximate sin theta_B                 */
     double cull_inv_r;       /* 1 / radius (sphere: n = (center - X) / radius)                    */
+    /* mosaic crystal as split optic: per-layer FP32 pre-test of the crystallite loop (stage S of the fused kernel);
+       filled in by xrt_scene_create: enable flag, first-level threshold (as cull_t2) and error margin on sin(theta). */
+    int32_t mosaic_scan;
+    int32_t pad2;
+    double mosaic_t2;
+    double mosaic_err;
 } XrtOpticDesc;
 
 typedef struct XrtSightline {    /* xicsrt/filters/_XicsrtBundleFilterSightline.py:31-56 */

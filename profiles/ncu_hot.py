@@ -11,8 +11,13 @@ top = int(sys.argv[5]) if len(sys.argv) > 5 else 60
 
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.run(['cuobjdump', '-xelf', 'all', lib], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-    dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    # one cubin per translation unit: take the one that holds the kernel
+    dis = ''
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith('.cubin')):
+        txt = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+        if kname in txt:
+            dis = txt
+            break
 
 line_of, text_of, cur, inside = {}, {}, ('?', 0), False
 for ln in dis.splitlines():

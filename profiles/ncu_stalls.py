@@ -8,8 +8,13 @@ rep, lib, kname = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.run(['cuobjdump', '-xelf', 'all', lib], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-    dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    # one cubin per translation unit: take the one that holds the kernel
+    dis = ''
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith('.cubin')):
+        txt = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+        if kname in txt:
+            dis = txt
+            break
 line_of, cur, inside = {}, ('?', 0), False
 for ln in dis.splitlines():
     if ln.startswith('\t.section\t.text.'):

@@ -64,7 +64,7 @@ int main(void) {
     S(XrtSceneDesc); S(XrtOutputs); S(XrtHistory); S(XrtRaysIn); S(XrtInject); S(XrtSourceInject);
     O(XrtOpticDesc, origin); O(XrtOpticDesc, center); O(XrtOpticDesc, root_idx); O(XrtOpticDesc, two_d);
     O(XrtOpticDesc, n_aperture); O(XrtOpticDesc, apertures); O(XrtOpticDesc, mesh); O(XrtOpticDesc, npix);
-    O(XrtOpticDesc, image_offset); O(XrtOpticDesc, cull_t2); O(XrtOpticDesc, cull_inv_r);
+    O(XrtOpticDesc, image_offset); O(XrtOpticDesc, cull_t2); O(XrtOpticDesc, cull_inv_r); O(XrtOpticDesc, mosaic_scan); O(XrtOpticDesc, mosaic_err);
     O(XrtSourceDesc, axis_basis); O(XrtSourceDesc, cone_par); O(XrtSourceDesc, wave_par); O(XrtSourceDesc, n_table);
     O(XrtSourceDesc, table_cdf); O(XrtSourceDesc, sightlines); O(XrtSourceDesc, n_bundles); O(XrtSourceDesc, voxel_size); O(XrtSourceDesc, bundle_x); O(XrtSourceDesc, bundle_hint_shift);
     O(XrtPlasmaDesc, cone); O(XrtPlasmaDesc, origin); O(XrtPlasmaDesc, inject_u); O(XrtPlasmaDesc, sightlines);

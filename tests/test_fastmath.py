@@ -90,11 +90,11 @@ def test_pretest_normal_deviate_coefficients_against_scipy():
     body = body[:body.index('\n}\n')]
     lead = float(re.search(r'float p = ([-0-9.e+]+)f;', body).group(1))
     coef = [float(c) for c in re.findall(r'p = fmaf\(p, w, ([-0-9.e+]+)f\);', body)]
-    assert len(coef) == 8 and 'w < 5.0f' in body
+    assert len(coef) == 4 and 'w < 5.0f' in body and '(hi >> 9)) - 3.0f' in body
     f32 = np.float32
     hi = np.random.default_rng(3).integers(0, 2**32, 2000000, dtype=np.uint64)
-    k = (hi >> np.uint64(8)).astype(f32)
-    x = (k * f32(2.0**-23) + f32(2.0**-24 - 1.0)).astype(f32)
+    k = (hi >> np.uint64(9)).astype(np.float64)
+    x = (k * 2.0**-22 - 1.0).astype(f32)                  # exact in float32: the [2, 4) bit pattern minus 3
     w = (f32(-0.6931471805599453) * np.log2((f32(1) - x * x).astype(f32)).astype(f32)).astype(f32)
     usable = w < f32(5)
     w = (w - f32(2.5)).astype(f32)
@@ -105,4 +105,4 @@ def test_pretest_normal_deviate_coefficients_against_scipy():
     u = (hi.astype(np.float64) + 0.5) * 2.0**-32          # any uniform whose top 32 bits are `hi`
     err = np.abs(z.astype(np.float64) - norm.ppf(u))[usable]
     assert usable.mean() > 0.99 and np.abs(z[usable]).max() < 2.95
-    assert err.max() < 2e-5, err.max()
+    assert err.max() < 1e-4, err.max()                    # 20 x inside the 2e-3 of cull_err

@@ -216,6 +216,52 @@ def test_fused_kernel_equals_replay_kernel(torch, name):
     tracer.close()
 
 
+@pytest.mark.parametrize('name,kind', [('sphere', 'point'), ('sphere_step_box', 'focused'), ('plasma_toroidal', 'bundles'),
+                                       ('plasma_cubic_poisson', 'bundles'), ('mosaic_sphere', None), ('mosaic_sphere_cutoff', None),
+                                       ('mosaic_plane', None)])
+def test_two_kernel_path_equals_replay_kernel(torch, name, kind, monkeypatch):
+    """
+    The same comparison with the FP32 broad phase forced on for a small launch (XRT_CULL32_MIN_RAYS=0: k_cull32 writes
+    the id list, k_trace consumes it) for every source kind it is built for, and for the mosaic scan stage: counters,
+    images, found set and lost sample must equal what the straight replay kernel gives ray for ray.
+    """
+    from xicsrt_b200 import _driver, config as xconfig, elements
+    monkeypatch.setenv('XRT_CULL32_MIN_RAYS', '0')
+    cfg = scenes.get(name)
+    if name.startswith('plasma'):
+        cfg['sources']['source']['time_resolution'] *= 500
+    else:
+        cfg['sources']['source']['intensity'] = 300000
+    if name == 'sphere_step_box':
+        cfg['sources']['source']['wavelength_dist'] = 'voigt'          # normal line (the uniform line has no broad phase)
+    tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), seed=1234)
+    info = tracer.scene.launch_info()
+    if kind is None:
+        assert info['broad_phase'] is None
+    else:
+        assert info['broad_phase'] is not None and info['broad_phase']['source_kind'] == kind, info
+    n = tracer.n_rays
+    found, lost = tracer.select_ids(2, 300)
+    meta, image = tracer.counts_and_images(True)
+    rays, mask = tracer.history(2, torch.arange(n, dtype=torch.int64, device=tracer.device))
+    rays, mask = rays.cpu().numpy(), mask.cpu().numpy().astype(bool)
+    names = tracer.layout.element_names
+    for e, elem in enumerate(names):
+        assert int(mask[e].sum()) == meta[elem], f'{name}/{elem}'
+    assert meta[names[-1]] > 50
+    assert np.array_equal(np.flatnonzero(mask[-1]), found.cpu().numpy())
+    lost_ids = lost.cpu().numpy()
+    assert len(lost_ids) == min(300, int((~mask[-1]).sum())) and not mask[-1][lost_ids].any()
+    assert len(np.unique(lost_ids)) == len(lost_ids)
+    for e, elem in enumerate(names[1:], start=1):
+        if image[elem] is None:
+            continue
+        _, param = elements.prepare_optic(tracer.config['optics'][elem])
+        ref = ooptics.bin_image(param, np.ascontiguousarray(rays[e, 0:3].T), mask[e])
+        assert np.array_equal(image[elem], ref), f'{name}/{elem}: image'
+    tracer.close()
+
+
 def _long_train(n_apertures):
     """n pass-through apertures in front of the crystal: the split optic moves down the train."""
     cfg = scenes.get('sphere')

@@ -220,29 +220,179 @@ def test_fp32_broad_phase_error_budget():
         hit = thc2 > 0
         sI64 = np.sqrt(np.where(hit, thc2, 1.0)) / R
         # ---- FP32, as spectro_cull32 (1 - a to 2^-24 relative, 24-bit azimuth, w (2 - w), constants rounded to float)
-        one_minus_a = (1.0 - a).astype(f32)               # all 52 bits of the uniform: 2^-24 relative
-        b24 = (np.floor(b * 2**24) / 2**24).astype(f32)
+        na = np.floor((1.0 - a) * 2.0**32)                # top 32 bits of 1 - a; rays with na < 256 are left to FP64
+        one_minus_a = ((na + 0.5) * 2.0**-32).astype(f32)
+        b24 = (np.floor(b * 2**23) / 2**23).astype(f32)   # 23-bit azimuth (float in [1, 2) bit trick)
         w = (f32(1.0 - cs0) * one_minus_a).astype(f32)
         z32 = (f32(1) - w).astype(f32)
         rho32 = np.sqrt((w * (f32(2) - w)).astype(f32)).astype(f32)
         ang = (f32(6.283185307179586) * (b24 - f32(0.5))).astype(f32)
         lx, ly = (-rho32 * np.cos(ang).astype(f32)).astype(f32), (-rho32 * np.sin(ang).astype(f32)).astype(f32)
-        B = basis.astype(f32)
-        d32 = [(lx * B[0, i] + ly * B[1, i] + z32 * B[2, i]).astype(f32) for i in range(3)]
-        L32 = Lc.astype(f32)
-        tca32 = (L32[0] * d32[0] + L32[1] * d32[1] + L32[2] * d32[2]).astype(f32)
+        m32 = (basis @ Lc).astype(f32)                    # point source: tca = l . (basis L), host-computed in FP64
+        tca32 = (lx * m32[0] + ly * m32[1] + z32 * m32[2]).astype(f32)
         d2 = (f32(Lc @ Lc) - tca32 * tca32).astype(f32)
         t2 = (f32(R * R) - d2).astype(f32)
         sI32 = (np.sqrt(np.where(t2 > 0, t2, f32(1))).astype(f32) * f32(1.0 / R)).astype(f32)
         # a wrong rejection needs |sI32 - sI| > margin where sI is within ~T of sin(theta_B): only chords near the
         # Bragg angle matter (elsewhere the gap is hundreds of margins wide)
         sB0 = float(sp['wavelength']) / (2.0 * float(cp['crystal_spacing']))
-        both = hit & (t2 > 0) & (np.abs(sI64 - sB0) < 0.05)
+        both = hit & (t2 > 0) & (np.abs(sI64 - sB0) < 0.05) & (na >= 256)
         err = np.abs(sI32.astype(np.float64) - sI64)[both].max()
         mufu = 2.0**-21 * 2.0 * np.abs(Lc).sum() / R + 2.4e-7          # sin / cos through rho <= 1 into tca, thc; sqrt ulps
         margin = 2e-5 * max(1.0, (Lc @ Lc) / (R * R))
         assert Lc @ Lc <= 4 * R * R
         assert err + mufu < margin / 5, (name, err, mufu, margin)
+
+
+def test_fp32_broad_phase_error_budget_extended_sources():
+    """
+    The same budget for the generalised broad phase (cull32_ray<CULL_BOX / CULL_FOCUSED / CULL_BUNDLES> in
+    csrc/xrt_kernels.cuh): per-ray origin inside a box or plasma voxel, cone axis towards a target with the basis
+    o_1 = unit(axis x (xaxis + zaxis)), o_2 = axis x o_1 built in float32, Doppler factor 1 - v.D / c.  The margin
+    added per ray is 2e-5 max(1, |C - O|^2 / R^2); sin(theta_i) and sin(theta_B) together must stay within a fifth
+    of it for chords near the Bragg angle.
+    """
+    f32 = np.float32
+    rng = np.random.default_rng(5)
+    n = 300000
+    a = np.concatenate([rng.random(n), 1.0 - 10.0**rng.uniform(-12, -1, n // 4), 10.0**rng.uniform(-12, -1, n // 4)])
+    b = rng.random(len(a))
+    m = len(a)
+    C = np.array([0.0, 0.59497864, 0.0])                       # centre of curvature of geometry G (R = 1)
+    R, lam0, two_d = 1.0, 3.9492, 2 * 2.45676
+    target = np.array([0.0, 0.0, 0.80374151])
+    xa, za = np.array([1.0, 0.0, 0.0]), np.array([0.0, 0.0, 1.0])
+    cases = {
+        'box_1mm_fixed_axis': dict(org=np.zeros(3), ext=1e-3, spread=np.radians(10.0), focused=False, vel=np.zeros(3)),
+        'box_10cm_fixed_axis': dict(org=np.zeros(3), ext=0.1, spread=np.radians(10.0), focused=False, vel=np.zeros(3)),
+        'focused_2cm': dict(org=np.zeros(3), ext=0.02, spread=np.radians(8.0), focused=True, vel=np.zeros(3)),
+        'plasma_voxels_10cm_moving': dict(org=None, ext=1e-3, spread=np.radians(2.0), focused=True,
+                                          vel=np.array([1e-4, -3e-4, 2e-4])),
+        # source 2.5 m in front of the crystal on the central ray: |C - O|^2 = 3.2 R^2 (the margin scales with it)
+        'far_source_1.8R': dict(org=np.array([0.0, 0.0, 0.80374151 - 2.5]), ext=0.01,
+                                spread=np.radians(3.0), focused=True, vel=np.zeros(3)),
+    }
+    for name, cs in cases.items():
+        org = cs['org']
+        if org is None:                                         # one voxel origin per ray inside the 10 cm plasma cube
+            org = rng.uniform(-0.05, 0.05, (m, 3))
+        org = np.broadcast_to(org, (m, 3))
+        u = rng.random((m, 3))
+        off = cs['ext'] * (u - 0.5)                              # source axes = identity here
+        O = org + off
+        cs0 = np.cos(cs['spread'])
+        # ---- FP64 (generate_geometry + hit_sphere)
+        z = cs0 + (1.0 - cs0) * a
+        rho = np.sqrt(1.0 - z * z)
+        lx, ly = rho * np.cos(2 * np.pi * b), rho * np.sin(2 * np.pi * b)
+        if cs['focused']:
+            ax = target - O
+            ax /= np.linalg.norm(ax, axis=1)[:, None]
+            o1 = np.cross(ax, xa) + np.cross(ax, za)
+            o1 /= np.linalg.norm(o1, axis=1)[:, None]
+            o2 = np.cross(ax, o1)
+            o2 /= np.linalg.norm(o2, axis=1)[:, None]
+        else:
+            ax = np.broadcast_to(za, (m, 3))
+            o1 = np.cross(za, xa) + np.cross(za, za)
+            o1 = np.broadcast_to(o1 / np.linalg.norm(o1), (m, 3))
+            o2 = np.cross(ax, o1)
+        d = lx[:, None] * o2 + ly[:, None] * o1 + z[:, None] * ax
+        L = C - O
+        tca = np.einsum('ij,ij->i', L, d)
+        ll = np.einsum('ij,ij->i', L, L)
+        thc2 = R * R - (ll - tca * tca)
+        hit = thc2 > 0
+        sI64 = np.sqrt(np.where(hit, thc2, 1.0)) / R
+        dop64 = 1.0 - d @ cs['vel']
+        sB64 = lam0 * dop64 / two_d
+        # ---- FP32 (cull32_ray): differences C - org, target - org formed in FP64 once, then float
+        Lb, Tb = (C - org).astype(f32), (target - org).astype(f32)
+        o32 = (f32(cs['ext']) * ((np.floor(u * 2**23) / 2**23).astype(f32) - f32(0.5))).astype(f32)
+        L32 = (Lb - o32).astype(f32)
+        T32 = (Tb - o32).astype(f32)
+        na = np.floor((1.0 - a) * 2.0**32)
+        one_minus_a = ((na + 0.5) * 2.0**-32).astype(f32)
+        b24 = (np.floor(b * 2**23) / 2**23).astype(f32)
+        w = (f32(1.0 - cs0) * one_minus_a).astype(f32)
+        z32 = (f32(1) - w).astype(f32)
+        rho32 = np.sqrt((w * (f32(2) - w)).astype(f32)).astype(f32)
+        ang = (f32(6.283185307179586) * (b24 - f32(0.5))).astype(f32)
+        lx32, ly32 = (-rho32 * np.cos(ang).astype(f32)).astype(f32), (-rho32 * np.sin(ang).astype(f32)).astype(f32)
+        if cs['focused']:
+            it = (f32(1) / np.sqrt(np.einsum('ij,ij->i', T32, T32).astype(f32))).astype(f32)
+            ax32 = (T32 * it[:, None]).astype(f32)
+            p32 = np.cross(ax32, (xa + za).astype(f32)).astype(f32)
+            ip = (f32(1) / np.sqrt(np.einsum('ij,ij->i', p32, p32).astype(f32))).astype(f32)
+            p32 = (p32 * ip[:, None]).astype(f32)
+            q32 = np.cross(ax32, p32).astype(f32)
+        else:
+            ax32, p32, q32 = ax.astype(f32), o1.astype(f32), o2.astype(f32)
+        d32 = (lx32[:, None] * q32 + ly32[:, None] * p32 + z32[:, None] * ax32).astype(f32)
+        tca32 = np.einsum('ij,ij->i', L32, d32).astype(f32)
+        ll32 = np.einsum('ij,ij->i', L32, L32).astype(f32)
+        d2 = (ll32 - tca32 * tca32).astype(f32)
+        t2 = (f32(R * R) - d2).astype(f32)
+        sI32 = (np.sqrt(np.where(t2 > 0, t2, f32(1))).astype(f32) * f32(1.0 / R)).astype(f32)
+        dop32 = (f32(1) - (d32 @ cs['vel'].astype(f32)).astype(f32)).astype(f32)
+        sB32 = (f32(lam0) * dop32 * f32(1.0 / two_d)).astype(f32)
+        near = hit & (t2 > 0) & (np.abs(sI64 - sB64) < 0.05) & (ll <= 4 * R * R) & (na >= 256)
+        assert near.sum() > 1000, name
+        err = (np.abs(sI32.astype(np.float64) - sI64) + np.abs(sB32.astype(np.float64) - sB64))[near]
+        q = ll[near] / (R * R)
+        margin = 2e-5 * np.maximum(1.0, q)
+        mufu = 2.0**-21 * 2.0 * np.sqrt(ll[near]) / R + 6e-7     # sin / cos / rsqrt units through tca, thc, the basis
+        worst = np.max((err + mufu) / margin)
+        assert worst < 0.2, (name, worst)
+
+
+def test_mosaic_scan_error_budget():
+    """
+    Stage S of the fused kernel (stage_mosaic in csrc/xrt_kernels.cuh) pre-tests every crystallite layer in float32:
+    x, y by Box-Muller from the layer's Philox words (1 - u1 from its top 32 bits, a 23-bit angle), then
+    sin(theta_i) = |x D.r_0 + y D.r_1 + D.n| / sqrt(x^2 + y^2 + 1) with the three dot products rounded from FP64.
+    Restated here in numpy float32 against the FP64 arithmetic of mosaic_xy / mosaic_normal / bragg_dtheta: the error
+    on sin(theta_i) must stay within a quarter of the margin mosaic_err = 2e-6 (the MUFU units add ~4e-7 at most:
+    2^-22 relative on rsqrt, 2^-21 absolute on sin / cos scaled by sin(sigma) r < 0.02).
+    """
+    f32 = np.float32
+    rng = np.random.default_rng(17)
+    m = 400000
+    n = rng.normal(size=(m, 3)); n /= np.linalg.norm(n, axis=1)[:, None]
+    d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    for sigma_deg in (0.4 / 2.3548, 2.0):
+        s = np.sin(np.radians(sigma_deg))
+        w1 = rng.integers(0, 2**32, m, dtype=np.uint64)        # Philox word x (top 32 bits of the 40-bit radius uniform)
+        w1[: m // 8] = 2**32 - 1 - rng.integers(256, 2**22, m // 8).astype(np.uint64)   # deep tail: 1 - u1 tiny
+        lo8 = rng.integers(0, 256, m, dtype=np.uint64)
+        ang24 = rng.integers(0, 2**24, m, dtype=np.uint64)
+        # ---- FP64 (mosaic_xy with box_muller(u01_40, u01_24), mosaic_normal, |D.n_m|)
+        u1 = (w1.astype(np.float64) * 256 + lo8) / 2.0**40
+        u2 = ang24 / 2.0**24
+        r = np.sqrt(-2.0 * np.log(1.0 - u1))
+        x, y = s * r * np.cos(2 * np.pi * u2), s * r * np.sin(2 * np.pi * u2)
+        r0 = np.stack([n[:, 1], n[:, 2] - n[:, 0], -n[:, 1]], axis=1); r0 /= np.linalg.norm(r0, axis=1)[:, None]
+        r1 = np.cross(n, r0); r1 /= np.linalg.norm(r1, axis=1)[:, None]
+        inv = 1.0 / np.sqrt(x * x + y * y + 1.0)
+        nm = (x * inv)[:, None] * r0 + (y * inv)[:, None] * r1 + inv[:, None] * n
+        sI64 = np.abs(np.einsum('ij,ij->i', d, nm))
+        # ---- float32 (stage_mosaic)
+        na = (2**32 - 1 - w1).astype(np.float64)
+        omu = (na.astype(f32) * f32(2.0**-32) + f32(2.0**-33)).astype(f32)
+        rr = np.sqrt((f32(-1.3862943611198906) * np.log2(omu).astype(f32)).astype(f32)).astype(f32)
+        a23 = (np.floor(ang24 / 2) / 2.0**23).astype(f32)
+        ang = (f32(6.283185307179586) * (a23 - f32(0.5))).astype(f32)
+        x32 = (-f32(s) * rr * np.cos(ang).astype(f32)).astype(f32)
+        y32 = (-f32(s) * rr * np.sin(ang).astype(f32)).astype(f32)
+        dr0 = np.einsum('ij,ij->i', d, r0).astype(f32)
+        dr1 = np.einsum('ij,ij->i', d, r1).astype(f32)
+        dn = np.einsum('ij,ij->i', d, n).astype(f32)
+        t = (x32 * dr0 + (y32 * dr1 + dn).astype(f32)).astype(f32)
+        q = (x32 * x32 + (y32 * y32 + f32(1)).astype(f32)).astype(f32)
+        sI32 = (np.abs(t) / np.sqrt(q).astype(f32)).astype(f32)
+        ok = na >= 65536                                        # below that the lane decides exactly
+        err = np.abs(sI32.astype(np.float64) - sI64)[ok]
+        assert err.max() < 5e-7, (sigma_deg, err.max())
 
 
 def test_bragg_pretest_inequalities_are_conservative():

@@ -69,7 +69,8 @@ class XrtOpticDesc(C.Structure):
                 ('rock_dtheta', _pd), ('rock_s', _pd), ('rock_p', _pd),
                 ('mesh', C.POINTER(XrtMesh)),
                 ('npix', C.c_int32 * 2), ('pixel_size', C.c_double), ('image_offset', C.c_uint64),
-                ('cull_t2', C.c_double), ('cull_err', C.c_double), ('cull_inv_r', C.c_double)]
+                ('cull_t2', C.c_double), ('cull_err', C.c_double), ('cull_inv_r', C.c_double),
+                ('mosaic_scan', C.c_int32), ('pad2', C.c_int32), ('mosaic_t2', C.c_double), ('mosaic_err', C.c_double)]
 
 
 class XrtSightline(C.Structure):

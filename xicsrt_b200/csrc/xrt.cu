@@ -62,6 +62,8 @@ struct XrtScene {
     uint32_t *list_ids = nullptr;   // id list between k_cull32 and k_trace (stream-ordered allocation, grown on demand)
     uint32_t *list_counts = nullptr;
     uint64_t list_ids_cap = 0, list_counts_cap = 0;
+    unsigned int *list_next = nullptr;   // [2] region counters of k_cull32, used alternately (each launch resets the other)
+    int list_phase = 0;
 };
 
 static thread_local char g_err[512] = "";
@@ -185,6 +187,7 @@ extern "C" int xrt_scene_destroy(XrtScene *s) {
     if (s->bundle_hint) cudaFreeAsync(s->bundle_hint, (cudaStream_t)0);
     if (s->list_ids) cudaFreeAsync(s->list_ids, (cudaStream_t)0);
     if (s->list_counts) cudaFreeAsync(s->list_counts, (cudaStream_t)0);
+    if (s->list_next) cudaFreeAsync(s->list_next, (cudaStream_t)0);
     delete s;
     return XRT_OK;
 }
@@ -273,7 +276,11 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
             m.mesh = nullptr;
         }
     }
-    for (int k = 0; k < d.n_optics; ++k) d.optics[k].cull_t2 = d.optics[k].cull_err = d.optics[k].cull_inv_r = 0.0;
+    for (int k = 0; k < d.n_optics; ++k) {
+        d.optics[k].cull_t2 = d.optics[k].cull_err = d.optics[k].cull_inv_r = 0.0;
+        d.optics[k].mosaic_scan = 0;
+        d.optics[k].mosaic_t2 = d.optics[k].mosaic_err = 0.0;
+    }
     for (int i = 0; i < 32; ++i) d.kn32[i] = 0.0f;
     s->features = scene_features(d);
     s->split = 0;
@@ -364,6 +371,16 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
                         K.C[i] = o.center[i];
                         K.T[i] = src.target[i];
                     }
+                    for (int i = 0; i < 3; ++i) {      // point source: basis rows dotted with C - O and with v / c
+                        double mi = 0.0, mvi = 0.0;
+                        for (int a = 0; a < 3; ++a) {
+                            mi += src.axis_basis[3 * i + a] * (o.center[a] - src.origin[a]);
+                            mvi += src.axis_basis[3 * i + a] * src.velocity_c[a];
+                        }
+                        K.m[i] = (float)mi;
+                        K.mv[i] = (float)mvi;
+                    }
+                    K.ll = (float)ll_max;              // point source: the one value of |C - O|^2
                     K.r2 = (float)r2;
                     K.inv_r2 = (float)(1.0 / r2);
                     K.inv_r = (float)(1.0 / o.radius);
@@ -382,8 +399,22 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
                     d.kn32[0] = 1.0f;       // reported to the caller: the broad phase is in use
                 }
             }
+            // (mosaic crystals: below)
             // eager normal line (plasma bundles, Doppler shift) with no optic before the crystal: defer the exact deviate
             s->defer_wavelength = (!s->lazy_wavelength && src.wave == XRT_WAVE_NORMAL && s->split == 0) ? 1 : 0;
+        }
+        // mosaic crystal as split optic: per-layer FP32 pre-test of the crystallite loop (stage_mosaic in xrt_kernels.cuh).
+        // Analytic shape traced in global coordinates, Bragg test on, Gaussian or step rocking curve; the layer index
+        // travels in the top byte of the queue's id word.
+        if (o.interact == XRT_INTERACT_MOSAIC && (o.flags & XRT_F_CHECK_BRAGG) && rock_ok && !(o.flags & XRT_F_TRACE_LOCAL) &&
+            o.shape != XRT_SHAPE_MESH && o.mosaic_depth >= 1 && o.mosaic_depth <= 255 && std::isfinite(o.inv_two_d) &&
+            std::isfinite(o.mosaic_sin_sigma) && std::getenv("XRT_NO_CULL") == nullptr) {
+            XrtOpticDesc &w = d.optics[s->split];
+            const double edge = o.rocking_type == XRT_ROCK_GAUSS ? std::sqrt(40.0 / o.rock_inv_two_sigma2) : 0.5 * o.rocking_fwhm;
+            const double t = 1.05 * edge + 2e-6;
+            w.mosaic_t2 = t * t;
+            w.mosaic_err = 2e-6;
+            w.mosaic_scan = 1;
         }
     }
     return XRT_OK;
@@ -487,6 +518,13 @@ extern "C" int xrt_launch_info_cull(XrtScene *s, int32_t *mode, int32_t *grid, i
 }
 
 static int ensure_list(XrtScene *s, uint64_t n_ids, uint64_t n_regions, cudaStream_t st) {
+    if (!s->list_next) {
+        void *p = nullptr;
+        CU(cudaMallocAsync(&p, 2 * sizeof(unsigned int), st));
+        CU(cudaMemsetAsync(p, 0, 2 * sizeof(unsigned int), st));
+        s->list_next = (unsigned int *)p;
+        s->list_phase = 0;
+    }
     // a plasma draws a new Poisson total every iteration: headroom, so that the list is not re-allocated (gigabytes
     // from the pool) whenever the total grows by a few rays
     if (s->list_ids_cap < n_ids) {
@@ -551,6 +589,7 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
             const uint64_t n_groups = (n + 31) / 32;
             uint64_t gpr = (n_groups + (uint64_t)s->sm_count * 384 - 1) / ((uint64_t)s->sm_count * 384);
             if (gpr < 32) gpr = 32;
+            gpr = (gpr + 3) & ~3ull;            // a multiple of the broad phase's groups per pass: only the last region is ragged
             const uint32_t cap = (uint32_t)(gpr * 32);
             const uint32_t n_regions = (uint32_t)((n + cap - 1) / cap);
             rc = ensure_list(s, (uint64_t)n_regions * cap, n_regions, st);
@@ -561,7 +600,10 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
             if (cbps < 1) return fail(XRT_ECUDA, "broad-phase kernel does not fit on an SM");
             const uint64_t want = ((uint64_t)n_regions + kBlock / 32 - 1) / (kBlock / 32);
             const uint64_t ccap = (uint64_t)s->sm_count * (uint64_t)cbps;
-            Cull32Out lst = {s->list_ids, s->list_counts, n_regions, cap};
+            // two counters used alternately: this launch claims regions from one and zeroes the other for the next launch
+            Cull32Out lst = {s->list_ids, s->list_counts, n_regions, cap, s->list_next + s->list_phase,
+                             s->list_next + (s->list_phase ^ 1)};
+            s->list_phase ^= 1;
             ck<<<(int)(want < ccap ? want : ccap), kBlock, 0, st>>>(s->cull, s->dev.source, pk, stream_id, begin, n, lst, *out);
             CU(cudaGetLastError());
             list = {s->list_ids, s->list_counts, n_regions, cap};

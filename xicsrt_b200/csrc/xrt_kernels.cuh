@@ -46,10 +46,17 @@ struct IdList {
     uint32_t n_regions, cap;
 };
 
+// U groups of <= 32 ids are fetched one pass ahead of their use, so that the list loads (L2 / DRAM latency) overlap the
+// arithmetic of the pass before.
+template <int U>
 struct IdCursor {
     const uint32_t *ids, *counts;
     uint64_t base, n_rays;
     uint32_t reg, n_regions, cap, pos, cnt, step;
+    uint64_t pbase[U];    // pending ids of this lane: region base + poff (the sum is formed when the id is handed out, so
+    uint32_t poff[U];     // that the list load stays in flight until then)
+    bool pvalid[U];
+    bool pany;            // warp-uniform: the pending groups hold at least one id
 
     __device__ __forceinline__ void load() {
         cnt = 0;
@@ -61,15 +68,8 @@ struct IdCursor {
             }
         }
     }
-    __device__ __forceinline__ void init(const IdList &L, uint64_t ray_begin, uint64_t ray_count, uint32_t warp_global,
-                                         uint32_t n_warps) {
-        ids = L.ids; counts = L.counts; n_regions = L.n_regions; cap = L.cap;
-        base = ray_begin; n_rays = ray_count;
-        reg = warp_global; step = n_warps; pos = 0;
-        load();
-    }
-    // warp-uniform: is there another group of <= 32 ids for this warp?
-    __device__ __forceinline__ bool more() {
+    // warp-uniform: move to the next non-empty region if the current one is used up
+    __device__ __forceinline__ bool advance() {
         while (pos >= cnt) {
             if (reg >= n_regions) return false;
             reg += step;
@@ -78,16 +78,37 @@ struct IdCursor {
         }
         return true;
     }
-    __device__ __forceinline__ void next(unsigned lane, uint64_t &id, bool &valid) {
-        id = base;
-        valid = false;
-        if (!more()) return;
-        const uint32_t p = pos + lane;
-        valid = p < cnt;
-        uint64_t off = (uint64_t)reg * cap + p;
-        if (ids) off = valid ? (uint64_t)__ldg(ids + off) : 0ull;
-        id = base + off;
-        pos += 32;
+    __device__ __forceinline__ void fetch(unsigned lane) {
+        pany = false;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            pbase[j] = base;
+            poff[j] = 0u;
+            pvalid[j] = false;
+            if (!advance()) continue;
+            pany = true;
+            const uint32_t p = pos + lane;
+            pvalid[j] = p < cnt;
+            const uint64_t off = (uint64_t)reg * cap + p;
+            if (ids) { if (pvalid[j]) poff[j] = __ldg(ids + off); }
+            else pbase[j] = base + off;
+            pos += 32;
+        }
+    }
+    __device__ __forceinline__ void init(const IdList &L, uint64_t ray_begin, uint64_t ray_count, uint32_t warp_global,
+                                         uint32_t n_warps, unsigned lane) {
+        ids = L.ids; counts = L.counts; n_regions = L.n_regions; cap = L.cap;
+        base = ray_begin; n_rays = ray_count;
+        reg = warp_global; step = n_warps; pos = 0;
+        load();
+        fetch(lane);
+    }
+    __device__ __forceinline__ bool more() const { return pany; }
+    // hand out the pending groups and start fetching the ones after them
+    __device__ __forceinline__ void take(unsigned lane, uint64_t (&id)[U], bool (&valid)[U]) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) { id[j] = pbase[j] + poff[j]; valid[j] = pvalid[j]; }
+        fetch(lane);
     }
 };
 
@@ -316,6 +337,171 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
     __syncwarp();
 }
 
+// ---- stage S: mosaic crystal as split optic (_InteractMosaicCrystal.py:53-139), for `cnt` rays popped from queue 1.
+//
+// The reference walks up to mosaic_depth layers of crystallites per ray; in each layer it draws a crystallite normal
+// (two normals) and a uniform u and reflects the ray if exp(-dtheta^2 / 2 sigma^2) reflectivity >= u.  Only ~3 % of
+// the (ray, layer) pairs of a HOPG-like crystal pass, so the FP64 evaluation of a layer (Box-Muller, two normalisations,
+// the Bragg angle, the exponential: ~400 instructions) is preceded by an FP32 pre-test of the same inequality, the one
+// of the Bragg pre-test with the layer's own uniform:  reflected  =>  dtheta^2 <= 2 sigma^2 ln(reflectivity / u), and
+// |sin(theta_B) - sin(theta_i)| <= |dtheta| cos(min angle).  sin(theta_i) = |D.n_m| / |D| with the crystallite normal
+// n_m = (x r_0 + y r_1 + n) / sqrt(x^2 + y^2 + 1) is three precomputed dot products and one rsqrt per layer; (x, y, u)
+// come from the layer's Philox block (the block the exact path reads).  Everything is within 5e-7 of the FP64 value
+// (margin cull_err = 2e-6, tests/test_host_logic.py), so a layer the pre-test rejects would be rejected by the exact
+// test too and results do not change (XRT_NO_CULL runs the plain loop).
+//
+// Lanes scan their own layers independently; a lane that meets a layer it cannot reject waits as a candidate.  When
+// fewer than kMinScan lanes are still scanning, the candidates evaluate their layer exactly (FP64, the code of
+// optic_interact): a pass reflects the ray, a fail resumes the scan at the next layer.  When neither is left to do, the
+// unfinished rays go back to queue 1 with their layer index (in the top byte of the id word) and their wavelength, and
+// are re-packed with new rays.  While the queues drain at the end of the launch the batch runs to completion.
+constexpr int kMinScan = 16;
+constexpr uint64_t kIdMask = (1ull << 56) - 1ull;
+
+template <uint32_t FT, uint32_t KN, bool HIST>
+__device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
+                                             const WarpCtx &c, int split, bool lazy, bool need_wave, bool defer, const PhiloxKeys &pk,
+                                             uint64_t stream_id, double *q1, int &n1, int cnt, bool drain, double *q2, int &n2,
+                                             unsigned &n_split) {
+    constexpr int P = kQ1Cap;
+    const bool active = (int)c.lane < cnt;
+    Ray r;
+    r.alive = false;
+    r.o = r.d = v3(0.0, 0.0, 1.0);
+    r.w = 1.0;
+    uint64_t id = 0;
+    int layer = 0;
+    if (active) {
+        const double *p = q1 + n1 + c.lane;
+        const uint64_t word = (uint64_t)__double_as_longlong(p[0]);
+        id = word & kIdMask;
+        layer = (int)(word >> 56);
+        r.o = v3(p[1 * P], p[2 * P], p[3 * P]);
+        r.d = v3(p[4 * P], p[5 * P], p[6 * P]);
+        r.w = p[7 * P];
+    }
+    __syncwarp();
+    PhiloxDraws dr;
+    dr.init(pk, stream_id, id, split);
+    const uint32_t flags = flags_of<KN>(ops);
+    const V3 n = analytic_normal<FT, KN>(ops, r.o);
+    bool scanning = active;
+    if (active && layer == 0) {
+        // first visit: the wavelength (lazy / deferred, as stage B) and the optional prefilter on the nominal normal
+        if (lazy && need_wave) {
+            SrcLocal L;
+            source_local<0, KN>(sc.source, id, L);
+            r.w = generate_wavelength<PhiloxDraws, KN, false>(sc.source, L, dr, r.d);
+        }
+        if (defer) {
+            SrcLocal L;
+            source_local<FT, KN>(sc.source, id, L);
+            const double w0 = sc.source.wave_par[0] + L.wave_sigma * dr.wave_z();
+            r.w = (r.w != 1.0) ? w0 * r.w : w0;
+        }
+        if (flags & XRT_F_MOSAIC_CUTOFF) scanning = fabs(bragg_dtheta(ops, r.d, r.w, n)) < ops.mosaic_angle_cut;
+    }
+    // single-precision constants of this ray's scan: D.r_0, D.r_1, D.n over |D| (r_0, r_1: basis of mosaic_normal)
+    float dr0, dr1, dn, sB;
+    {
+        V3 r0 = unit(v3(0.0 + n.y, n.z - n.x, -n.y + 0.0));
+        V3 r1 = unit(cross(n, r0));
+        const double il = fast_rsqrt(dot(r.d, r.d));
+        dr0 = (float)(dot(r.d, r0) * il);
+        dr1 = (float)(dot(r.d, r1) * il);
+        dn = (float)(dot(r.d, n) * il);
+        sB = (float)(r.w * ops.inv_two_d);
+    }
+    const float s32 = (float)ops.mosaic_sin_sigma, err = (float)ops.mosaic_err, t2 = (float)ops.mosaic_t2;
+    const bool gauss = ops.rocking_type != XRT_ROCK_STEP;
+    const float two_sigma2 = (float)ops.rock_two_sigma2;
+    const float lg_refl = lg2_approx((float)ops.reflectivity);
+    const int depth = ops.mosaic_depth;
+    const int min_scan = drain ? 1 : kMinScan;
+    bool cand = false, reflected = false;
+    if (layer >= depth) scanning = false;
+
+    for (;;) {
+        // ---- scan: FP32 pre-test of one layer per iteration and lane
+        while ((int)__popc(__ballot_sync(kFull, scanning)) >= min_scan) {
+            if (scanning) {
+                const uint4 b = dr.raw(site_optic(split, layer, 1));
+                const uint32_t na = ~b.x;
+                const float omu = fmaf((float)na, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // 1 - u1
+                const float rr = sqrt_approx(-1.3862943611198906f * lg2_approx(omu));                 // sqrt(-2 ln(1 - u1))
+                const float ang = 6.283185307179586f * (__uint_as_float(0x3f800000u | ((b.y & 0xffffffu) >> 1)) - 1.5f);
+                const float x = -s32 * rr * __cosf(ang), y = -s32 * rr * __sinf(ang);
+                const float t = fmaf(x, dr0, fmaf(y, dr1, dn));
+                const float sI = fabsf(t) * rsqrt_approx(fmaf(x, x, fmaf(y, y, 1.0f)));
+                const float gap = fabsf(sB - sI);
+                const float diff = gap - err;
+                const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
+                bool rej = (diff > 0.0f) & (diff * diff > t2 * c2);
+                if (gauss) {
+                    const float u = __uint_as_float(0x3f800000u | (b.z >> 9)) - 1.0f;          // top 23 bits: u32 <= u
+                    const float lim = 0.6931471805599453f * (lg_refl - lg2_approx(u));        // >= ln(reflectivity / u)
+                    const float bound = fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * two_sigma2;
+                    rej |= (diff > 0.0f) & (diff * diff > bound * c2) & (lim == lim);
+                }
+                rej &= na >= 65536u;      // 1 - u1 below 2^-16 (|z| > 4.7): its 32-bit truncation is not precise enough for
+                                          // the radius, the layer is decided exactly (1.5e-5 of the layers)
+                if (rej) {
+                    ++layer;
+                    if (layer >= depth) scanning = false;
+                } else {
+                    cand = true;
+                    scanning = false;
+                }
+            }
+        }
+        if (!__ballot_sync(kFull, cand)) break;
+        // ---- exact evaluation of the candidates' layers (optic_interact, one layer)
+        if (cand) {
+            double x, y;
+            dr.mosaic_xy(split, layer, ops.mosaic_sin_sigma, x, y);
+            const V3 nm = mosaic_normal(n, x, y);
+            const bool pass = bragg_pass<FT, PhiloxDraws, KN, true>(ops, split, layer, dr, bragg_dtheta(ops, r.d, r.w, nm));
+            cand = false;
+            if (pass) {
+                reflect(r, nm);
+                reflected = true;
+            } else {
+                ++layer;
+                scanning = layer < depth;
+            }
+        }
+    }
+
+    // ---- reflected rays leave for stage C, lost rays are done, the rest go back to queue 1
+    r.alive = reflected;
+    if (reflected && (flags & XRT_F_IMAGE) && out.images) add_pixel(out, ops, r, c.lt_mask);
+    const unsigned mr = __ballot_sync(kFull, reflected);
+    n_split += __popc(mr);
+    emit_lost<HIST>(out, c.lane, c.lt_mask, dr, active && !reflected && !scanning, id);
+    const unsigned ms = __ballot_sync(kFull, scanning);
+    if (scanning) {
+        double *p = q1 + n1 + __popc(ms & c.lt_mask);
+        p[0] = __longlong_as_double((long long)(id | ((uint64_t)layer << 56)));
+        p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
+        p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
+        p[7 * P] = r.w;
+    }
+    n1 += __popc(ms);
+    if (split + 1 >= sc.n_optics) {
+        emit_found<HIST>(out, c.lane, c.lt_mask, reflected, id);
+    } else {
+        if (reflected) {
+            double *p = q2 + n2 + __popc(mr & c.lt_mask);
+            p[0] = __longlong_as_double((long long)id);
+            p[1 * kQ2Cap] = r.o.x; p[2 * kQ2Cap] = r.o.y; p[3 * kQ2Cap] = r.o.z;
+            p[4 * kQ2Cap] = r.d.x; p[5 * kQ2Cap] = r.d.y; p[6 * kQ2Cap] = r.d.z;
+            p[7 * kQ2Cap] = r.w;
+        }
+        n2 += __popc(mr);
+    }
+    __syncwarp();
+}
+
 // ---- spectrometer variant, stage AB for one ray: direction from the cone block, the two lengths of the sphere
 // intersection, first level of the Bragg pre-test (sin(theta_i) = |D.n| is thc / R for a ray of unit direction:
 // D.(C - X) = tca - t = -thc, so the pre-test needs nothing else), intersection point and bounds (arithmetic of
@@ -359,10 +545,11 @@ __device__ __forceinline__ bool spectro_stage_ab(const XrtSceneDesc &sc, const X
 }
 
 // Resident blocks per SM: 2 for the mesh variants (face loops and Clough-Tocher cubics keep many values live), for
-// the spectrometer variant (two ray groups per pass = two independent chains) and for the lean extended-source
-// variant (bundle lookup + focused cone basis); 3 otherwise.
+// the mosaic variants (scan state + exact layer evaluation), for the spectrometer variant (two ray groups per pass =
+// two independent chains) and for the lean extended-source variant (bundle lookup + focused cone basis); 3 otherwise.
 template <uint32_t FT, uint32_t KN> __host__ __device__ constexpr int trace_min_blocks() {
-    return (((FT & FT_MESH) != 0 || FT == FT_SRCLEAN || ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
+    return (((FT & FT_MESH) != 0 || (FT & FT_MOSAIC) != 0 || FT == FT_SRCLEAN ||
+             ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
             XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS;
 }
 
@@ -427,8 +614,8 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     }
     unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
 
-    IdCursor cur;
-    cur.init(list, ray_begin, ray_count, blockIdx.x * (kBlock / 32) + warp, gridDim.x * (kBlock / 32));
+    IdCursor<SPECTRO ? kUnroll : 1> cur;
+    cur.init(list, ray_begin, ray_count, blockIdx.x * (kBlock / 32) + warp, gridDim.x * (kBlock / 32), c.lane);
 
     // One loop, one copy of each stage: the deepest stage that has a full warp of work runs
     // first; when the ids are exhausted the queues are drained with partial warps.
@@ -443,6 +630,13 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
         if (n1 >= 32 || (!more && na == 0 && n1 > 0)) {
             const int cnt = n1 < 32 ? n1 : 32;
             n1 -= cnt;
+            if constexpr ((FT & FT_MOSAIC) != 0 && !SPECTRO) {
+                if (ops.mosaic_scan) {
+                    stage_mosaic<FT, KN, HIST>(sc, ops, out, c, split, lazy, need_wave, defer, pk, stream_id, q1, n1, cnt,
+                                               !more && na == 0, q2, n2, n_split);
+                    continue;
+                }
+            }
             stage_b<FT, KN, HIST>(sc, ops, out, c, split, lazy, need_wave, defer, pk, stream_id, q1, n1, cnt, q2, n2, n_split);
             continue;
         }
@@ -499,8 +693,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             bool validv[kUnroll], candv[kUnroll];
             V3 dv[kUnroll];
             double tv[kUnroll];
-#pragma unroll
-            for (int j = 0; j < kUnroll; ++j) cur.next(c.lane, idv[j], validv[j]);
+            if constexpr (SPECTRO) cur.take(c.lane, idv, validv);
 #pragma unroll
             for (int j = 0; j < kUnroll; ++j) {
                 PhiloxDraws dr;
@@ -528,9 +721,11 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             }
             __syncwarp();
         } else {
-            uint64_t id;
-            bool valid;
-            cur.next(c.lane, id, valid);
+            uint64_t id1[1];
+            bool valid1[1];
+            if constexpr (!SPECTRO) cur.take(c.lane, id1, valid1);
+            const uint64_t id = id1[0];
+            const bool valid = valid1[0];
             PhiloxDraws dr;
             dr.init(pk, stream_id, id, split);
             Ray r;
@@ -656,6 +851,9 @@ struct Cull32Par {
     float one_m_cos;       // 1 - cos(spread)                                     (not bundles)
     float basis[9];        // fixed axis: rows o_2, o_1, axis of the cone basis
     float Lb[3];           // C - source origin                                   (not bundles)
+    float m[3];            // point source: basis . Lb, so that tca = l . m without forming the direction
+    float mv[3];           // point source: basis . velocity / c
+    float ll;              // point source: |Lb|^2
     float r2, inv_r, inv_r2;   // sphere
     float lam0, sig, inv_two_d;
     float t2, err;         // cull_t2; cull_err (+ the geometric margin for a point source, else added per ray from |C - O|^2)
@@ -674,6 +872,8 @@ struct Cull32Out {
     uint32_t *ids;         // [n_regions][cap]
     uint32_t *counts;      // [n_regions]
     uint32_t n_regions, cap;
+    unsigned int *next;        // region counter this launch claims from (zero on entry)
+    unsigned int *next_reset;  // the counter of the launch after this one: zeroed here
 };
 
 #ifndef XRT_CULL_UNROLL
@@ -683,22 +883,10 @@ struct Cull32Out {
 #define XRT_CULL_BLOCKS 6
 #endif
 
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rsqrt_approx(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 // true = provably lost at the crystal
 template <int SRC>
 __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
-                                           uint64_t id) {
-    const uint32_t lo = (uint32_t)id, hi = (uint32_t)(id >> 32);
+                                           uint32_t lo, uint32_t hi) {
     const uint4 r = philox4x32_10(make_uint4(lo, hi, SITE_CONE, stream), pk);
 
     float one_m_cos = K.one_m_cos, sig = K.sig, err = K.err;
@@ -707,6 +895,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
     float vx = K.vel[0], vy = K.vel[1], vz = K.vel[2];
     if constexpr (SRC == CULL_BUNDLES) {
         // bundle of this ray: first b with bundle_end[b] > id (same search as source_local)
+        const uint64_t id = ((uint64_t)hi << 32) | lo;
         uint64_t blo = 0, bhi = src.n_bundles - 1;
         if (src.bundle_hint) {
             const uint64_t j = id >> src.bundle_hint_shift;
@@ -730,10 +919,10 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
     // ---- origin offset in world coordinates (the exact path: u01_42x3 of one block, off_k = ext_k (u_k - 1/2))
     if constexpr (SRC != CULL_POINT) {
         const uint4 ro = philox4x32_10(make_uint4(lo, hi, SITE_ORIGIN_XY, stream), pk);
-        const float s32 = 2.3283064365386963e-10f;
-        const float o0 = K.ext[0] * fmaf((float)ro.x, s32, -0.5f);
-        const float o1 = K.ext[1] * fmaf((float)((ro.y << 10) | (ro.z >> 22)), s32, -0.5f);
-        const float o2 = K.ext[2] * fmaf((float)((ro.z << 20) | (ro.w >> 12)), s32, -0.5f);
+        // top 23 bits of each uniform as a float in [1, 2): u - 1/2 = f - 3/2, no integer-to-float conversion
+        const float o0 = K.ext[0] * (__uint_as_float(0x3f800000u | (ro.x >> 9)) - 1.5f);
+        const float o1 = K.ext[1] * (__uint_as_float(0x3f800000u | ((ro.y << 10) >> 9) | (ro.z >> 31)) - 1.5f);
+        const float o2 = K.ext[2] * (__uint_as_float(0x3f800000u | ((ro.z << 20) >> 9) | (ro.w >> 21)) - 1.5f);
         const float wx = o0 * K.R[0] + o1 * K.R[3] + o2 * K.R[6];
         const float wy = o0 * K.R[1] + o1 * K.R[4] + o2 * K.R[7];
         const float wz = o0 * K.R[2] + o1 * K.R[5] + o2 * K.R[8];
@@ -741,49 +930,55 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         Tx -= wx; Ty -= wy; Tz -= wz;
     }
 
-    // ---- local cone vector: 1 - a from all 52 bits of the polar uniform (complement of the mantissa): its RELATIVE
-    // precision is what rho = sqrt(w (2 - w)) near the cone axis needs
-    const float a1 = fmaf((float)((~r.y) >> 12), 2.220446049250313e-16f, fmaf((float)(~r.x), 2.3283064365386963e-10f,
-                                                                                2.220446049250313e-16f));
+    // ---- local cone vector.  1 - a from the top 32 bits of the polar uniform (their complement): its RELATIVE
+    // precision is what rho = sqrt(w (2 - w)) near the cone axis needs; the truncation error 2^-32 moves the direction
+    // by 0.09 2^-32 / sqrt(1 - a) < 1e-7 unless 1 - a < 2^-24, and those rays (6e-8 of all) are left to FP64
+    const uint32_t na = ~r.x;
+    bool usable = na >= 256u;
+    const float a1 = fmaf((float)na, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float w = one_m_cos * a1;                                                     // 1 - z
     const float z = 1.0f - w;
     const float rho = sqrt_approx(w * (2.0f - w));
-    const uint32_t b24 = ((r.y & 0xfffu) << 12) | (r.z >> 20);                          // top 24 bits of the azimuth uniform
-    const float ang = 6.283185307179586f * ((float)b24 * 5.9604644775390625e-8f - 0.5f);
-    const float lx = -rho * __cosf(ang), ly = -rho * __sinf(ang);                       // cos(2 pi b) = -cos(2 pi (b - 1/2))
+    // azimuth 2 pi (b - 1/2) from the top 23 bits of b as a float in [1, 2): cos(2 pi b) = -cos(2 pi (b - 1/2))
+    const float ang = 6.283185307179586f * (__uint_as_float(0x3f800000u | ((r.y & 0xfffu) << 11) | (r.z >> 21)) - 1.5f);
+    const float lx = -rho * __cosf(ang), ly = -rho * __sinf(ang);
 
-    // ---- direction
-    float dx, dy, dz;
-    if constexpr (SRC == CULL_POINT || SRC == CULL_BOX) {
-        dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
-        dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
-        dz = lx * K.basis[2] + ly * K.basis[5] + z * K.basis[8];
+    // ---- direction and sphere chord
+    float tca, ll, vd = 0.0f;
+    if constexpr (SRC == CULL_POINT) {
+        // fixed basis and fixed origin: L . D = l . (basis L), v . D = l . (basis v); |L|^2 is a constant
+        tca = lx * K.m[0] + ly * K.m[1] + z * K.m[2];
+        ll = K.ll;
+        if (K.moving) vd = lx * K.mv[0] + ly * K.mv[1] + z * K.mv[2];
     } else {
-        // axis = unit(target - origin); o_1 = unit(axis x (xaxis + zaxis)); o_2 = axis x o_1 (unit up to rounding)
-        const float it = rsqrt_approx(Tx * Tx + Ty * Ty + Tz * Tz);
-        const float ax = Tx * it, ay = Ty * it, az = Tz * it;
-        float px = ay * K.xz[2] - az * K.xz[1], py = az * K.xz[0] - ax * K.xz[2], pz = ax * K.xz[1] - ay * K.xz[0];
-        const float ip = rsqrt_approx(px * px + py * py + pz * pz);
-        px *= ip; py *= ip; pz *= ip;
-        const float qx = ay * pz - az * py, qy = az * px - ax * pz, qz = ax * py - ay * px;
-        dx = lx * qx + ly * px + z * ax;
-        dy = lx * qy + ly * py + z * ay;
-        dz = lx * qz + ly * pz + z * az;
-    }
-
-    // ---- sphere chord
-    const float tca = Lx * dx + Ly * dy + Lz * dz;
-    const float ll = Lx * Lx + Ly * Ly + Lz * Lz;
-    const float d2 = fmaf(-tca, tca, ll);
-    const float thc = sqrt_approx(K.r2 - d2);
-    const float sI = thc * K.inv_r;
-    bool usable = true;
-    if constexpr (SRC != CULL_POINT) {
+        float dx, dy, dz;
+        if constexpr (SRC == CULL_BOX) {
+            dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
+            dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
+            dz = lx * K.basis[2] + ly * K.basis[5] + z * K.basis[8];
+        } else {
+            // axis = unit(target - origin); o_1 = unit(axis x (xaxis + zaxis)); o_2 = axis x o_1 (unit up to rounding)
+            const float it = rsqrt_approx(Tx * Tx + Ty * Ty + Tz * Tz);
+            const float ax = Tx * it, ay = Ty * it, az = Tz * it;
+            float px = ay * K.xz[2] - az * K.xz[1], py = az * K.xz[0] - ax * K.xz[2], pz = ax * K.xz[1] - ay * K.xz[0];
+            const float ip = rsqrt_approx(px * px + py * py + pz * pz);
+            px *= ip; py *= ip; pz *= ip;
+            const float qx = ay * pz - az * py, qy = az * px - ax * pz, qz = ax * py - ay * px;
+            dx = lx * qx + ly * px + z * ax;
+            dy = lx * qy + ly * py + z * ay;
+            dz = lx * qz + ly * pz + z * az;
+        }
+        tca = Lx * dx + Ly * dy + Lz * dz;
+        ll = Lx * Lx + Ly * Ly + Lz * Lz;
+        if (SRC == CULL_BUNDLES || K.moving) vd = vx * dx + vy * dy + vz * dz;
         // geometric margin 2e-5 max(1, |C - O|^2 / R^2); beyond 2 R from the centre of curvature the ray is left to FP64
         const float q = ll * K.inv_r2;
         err = fmaf(2e-5f, fmaxf(1.0f, q), err);
-        usable = q <= 4.0f;
+        usable &= q <= 4.0f;
     }
+    const float d2 = fmaf(-tca, tca, ll);
+    const float thc = sqrt_approx(K.r2 - d2);
+    const float sI = thc * K.inv_r;
 
     // ---- sin(theta_B)
     float lam = K.lam0;
@@ -792,7 +987,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         lam = fmaf(normal_approx(r.w, in_range), sig, lam);
         usable &= in_range;
     }
-    if (SRC == CULL_BUNDLES || K.moving) lam *= 1.0f - (vx * dx + vy * dy + vz * dz);
+    if (SRC == CULL_BUNDLES || K.moving) lam = fmaf(-lam, vd, lam);
     const float sB = lam * K.inv_two_d;
 
     const float gap = fabsf(sB - sI);
@@ -801,8 +996,46 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
     return usable & (diff > 0.0f) & (diff * diff > K.t2 * c2);
 }
 
+// groups of 32 consecutive ids per pass (independent chains): one for the bundle lookup, whose loads already overlap
+template <int SRC> __host__ __device__ constexpr int cull_unroll() { return SRC == CULL_BUNDLES ? 1 : XRT_CULL_UNROLL; }
+
+// cull_unroll groups of 32 consecutive ids: test, then append the survivors to the region's list
+template <int SRC, bool HIST, bool CHECK>
+__device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint64_t stream_id,
+                                            const XrtOutputs &out, unsigned lane, unsigned lt_mask, uint64_t id_first,
+                                            uint32_t off_first, uint32_t g, uint32_t n_here, uint32_t *dst, uint32_t &kept) {
+    constexpr int U = cull_unroll<SRC>();
+    bool valid[U], pass[U];
+    uint32_t off[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        off[j] = g + 32u * j + lane;
+        valid[j] = CHECK ? off[j] < n_here : true;
+        const uint64_t id = id_first + (valid[j] ? off[j] : 0u);      // lanes past the end re-test the region's first ray
+        pass[j] = !cull32_ray<SRC>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32));
+        if constexpr (CHECK) pass[j] = pass[j] && valid[j];
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        if constexpr (HIST) {
+            if (out.lost_count) {
+                PhiloxDraws dr;
+                dr.init(pk, stream_id, id_first + off[j], 0);
+                emit_lost<true>(out, lane, lt_mask, dr, valid[j] && !pass[j], id_first + off[j]);
+            }
+        }
+        const unsigned m = __ballot_sync(kFull, pass[j]);
+        if (pass[j]) dst[kept + __popc(m & lt_mask)] = off_first + off[j];
+        kept += __popc(m);
+    }
+}
+
+// resident blocks per SM: the bundle lookup (64-bit search, FP64 differences) needs more registers than the rest
+#ifndef XRT_CULL_BLOCKS_BUNDLES
+#define XRT_CULL_BLOCKS_BUNDLES 4
+#endif
 template <int SRC, bool HIST>
-__global__ void __launch_bounds__(kBlock, XRT_CULL_BLOCKS)
+__global__ void __launch_bounds__(kBlock, (SRC == CULL_BUNDLES ? XRT_CULL_BLOCKS_BUNDLES : XRT_CULL_BLOCKS))
 k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceDesc src, const __grid_constant__ PhiloxKeys pk,
          const uint64_t stream_id, const uint64_t ray_begin, const uint64_t ray_count, const Cull32Out lst,
          const XrtOutputs out) {
@@ -810,38 +1043,28 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t n_warps = gridDim.x * (kBlock / 32);
     const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-    const uint32_t stream = (uint32_t)stream_id;
+    constexpr uint32_t kPass = 32u * cull_unroll<SRC>();
     unsigned long long n_src = 0;
-    for (uint32_t reg = warp_global; reg < lst.n_regions; reg += n_warps) {
+    // Regions are claimed from a global counter: with a static share per warp the scheduler's oldest-first policy lets
+    // the old warps of an SM finish early and the SM runs its last third at half occupancy (ncu: 49 % achieved of 75 %).
+    if (blockIdx.x == 0 && threadIdx.x == 0) *lst.next_reset = 0u;
+    (void)n_warps; (void)warp_global;
+    for (;;) {
+        uint32_t reg = 0;
+        if (lane == 0) reg = atomicAdd(lst.next, 1u);
+        reg = __shfl_sync(kFull, reg, 0);
+        if (reg >= lst.n_regions) break;
         const uint64_t first = (uint64_t)reg * lst.cap;
         const uint64_t left = ray_count - first;
         const uint32_t n_here = left < (uint64_t)lst.cap ? (uint32_t)left : lst.cap;
         uint32_t *dst = lst.ids + first;
         uint32_t kept = 0;
         n_src += n_here;
-        for (uint32_t g = 0; g < n_here; g += 32u * XRT_CULL_UNROLL) {
-            bool valid[XRT_CULL_UNROLL], pass[XRT_CULL_UNROLL];
-            uint32_t off[XRT_CULL_UNROLL];
-#pragma unroll
-            for (int j = 0; j < XRT_CULL_UNROLL; ++j) {
-                off[j] = g + 32u * j + lane;
-                valid[j] = off[j] < n_here;
-                pass[j] = valid[j] && !cull32_ray<SRC>(K, src, pk, stream, ray_begin + first + off[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < XRT_CULL_UNROLL; ++j) {
-                if constexpr (HIST) {
-                    if (out.lost_count) {
-                        PhiloxDraws dr;
-                        dr.init(pk, stream_id, ray_begin + first + off[j], 0);
-                        emit_lost<true>(out, lane, lt_mask, dr, valid[j] && !pass[j], ray_begin + first + off[j]);
-                    }
-                }
-                const unsigned m = __ballot_sync(kFull, pass[j]);
-                if (pass[j]) dst[kept + __popc(m & lt_mask)] = (uint32_t)first + off[j];
-                kept += __popc(m);
-            }
-        }
+        uint32_t g = 0;
+        for (; g + kPass <= n_here; g += kPass)
+            cull32_pass<SRC, HIST, false>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept);
+        if (g < n_here)
+            cull32_pass<SRC, HIST, true>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept);
         if (lane == 0) lst.counts[reg] = kept;
     }
     // rays out of the source: one atomic per block

@@ -595,26 +595,33 @@ __device__ __forceinline__ float lg2_approx(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-// Standard normal deviate of wave_z() from the top 32 bits of its uniform, in FP32:
-// z = sqrt(2) erfinv(2u - 1) with the central branch of Giles' single-precision erfinv
-// (w = -ln(1 - x^2) < 5, i.e. |z| < 2.93; relative error 2.5e-7, checked against scipy in
-// tests/test_fastmath.py).  u is known to 2^-25 here, so |z32 - z| < 2^-25 / pdf(2.93) + 1e-6 = 7e-6.
+
+// Standard normal deviate of wave_z() from the top bits of its uniform, in FP32: z = sqrt(2) erfinv(2u - 1) with a
+// central-branch polynomial of the form of Giles' single-precision erfinv (w = -ln(1 - x^2) < 5, i.e. |z| < 2.93),
+// refitted at degree 4: the pre-test's margin (cull_err) allows |z32 - z| < 2e-3, the fit is within 3.4e-5 and the
+// 23-bit argument adds 2^-23 / pdf(2.93) = 2.2e-5 (checked against scipy in tests/test_fastmath.py).  x = 2u - 1 is
+// built from the top 23 bits as a float in [2, 4) minus 3: no integer-to-float conversion (XU pipe).
 __device__ __forceinline__ float normal_approx(uint32_t hi, bool &usable) {
-    // x = 2 ((hi >> 8) 2^-24 + 2^-25) - 1, exact in FP32
-    const float x = fmaf((float)(hi >> 8), 1.1920928955078125e-7f, 5.9604644775390625e-8f - 1.0f);
+    const float x = __uint_as_float(0x40000000u | (hi >> 9)) - 3.0f;       // -1 + (hi >> 9) 2^-22, exact
     float w = -0.6931471805599453f * lg2_approx(fmaf(-x, x, 1.0f));
-    usable = w < 5.0f;
+    usable = w < 5.0f;                                                      // false for x = -1 (w = inf) as well
     w -= 2.5f;
-    float p = 2.81022636e-08f;
-    p = fmaf(p, w, 3.43273939e-07f);
-    p = fmaf(p, w, -3.5233877e-06f);
-    p = fmaf(p, w, -4.39150654e-06f);
-    p = fmaf(p, w, 0.00021858087f);
-    p = fmaf(p, w, -0.00125372503f);
-    p = fmaf(p, w, -0.00417768164f);
-    p = fmaf(p, w, 0.246640727f);
-    p = fmaf(p, w, 1.50140941f);
+    float p = 0.000186555306f;
+    p = fmaf(p, w, -0.00126819056f);
+    p = fmaf(p, w, -0.00410411088f);
+    p = fmaf(p, w, 0.246652201f);
+    p = fmaf(p, w, 1.50138509f);
     return 1.4142135623730951f * p * x;
 }
 
