@@ -296,10 +296,16 @@ typedef struct XrtOutputs {
 
 /* per-element history, struct-of-arrays: 7 double planes + 1 byte plane per element
    (_Dispatcher.py:161-162,186-187 deepcopy of the ray dict after each element) */
+enum { XRT_HIST_PLANES = 0,  /* struct-of-arrays planes: slot i of plane p at rays[(e * 7 + p) * capacity + i]         */
+       XRT_HIST_ROWS = 1 };  /* the reference's row arrays inside the same 7 * capacity doubles per element: origin
+                                rows [capacity][3], direction rows [capacity][3], wavelength [capacity]           */
+
 typedef struct XrtHistory {
-    double *rays;            /* [1 + n_optics][7][capacity]: ox oy oz dx dy dz wavelength        */
+    double *rays;            /* [1 + n_optics][7][capacity]: ox oy oz dx dy dz wavelength (XRT_HIST_PLANES)  */
     uint8_t *mask;           /* [1 + n_optics][capacity]                                         */
     uint64_t capacity;
+    int32_t layout;          /* XRT_HIST_*                                                       */
+    int32_t pad0;
 } XrtHistory;
 
 typedef struct XrtRaysIn {   /* array-of-rows input, as the reference holds rays                */

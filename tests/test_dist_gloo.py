@@ -48,8 +48,24 @@ def _worker(rank, world, port, out_dir):
         mine = packed.clone()
         _driver.allreduce_packed(packed)
 
-        out = {'found': {'history': res['found']['history']}, 'lost': {'history': res['lost']['history']}}
-        _driver._gather_histories(out, names)
+        # this rank's found + lost histories in the rows layout the replay kernel writes (XRT_HIST_ROWS)
+        n_found = len(res['found']['history'][names[-1]]['mask'])
+        n_lost = len(res['lost']['history'][names[-1]]['mask'])
+        n = n_found + n_lost
+        rays = torch.zeros((len(names), 7, n), dtype=torch.float64)
+        mask = torch.zeros((len(names), n), dtype=torch.uint8)
+        for e, name in enumerate(names):
+            for kind, lo, hi in (('found', 0, n_found), ('lost', n_found, n)):
+                v = _driver.rows_views(rays, mask, e, lo, hi)
+                h = res[kind]['history'][name]
+                v['origin'].copy_(torch.from_numpy(h['origin']))
+                v['direction'].copy_(torch.from_numpy(h['direction']))
+                v['wavelength'].copy_(torch.from_numpy(h['wavelength']))
+                v['mask'].copy_(torch.from_numpy(h['mask'].astype(np.uint8)))
+        g_rays, g_mask, g_found = _driver.gather_rows(torch, rays, mask, n_found)
+        h_rays, h_mask = _driver.to_host(torch, g_rays, g_mask)
+        found, lost = _driver._row_dicts(names, h_rays, h_mask, g_found)
+        out = {'found': {'history': found}, 'lost': {'history': lost}}
 
         seed = _driver._resolve_seed(None, world)
         assert _driver._dist_info() == (rank, world)

@@ -122,6 +122,7 @@ class Tracer:
                                                  self.optics)
         with self.torch.cuda.device(self.device):
             self.scene = xscene.DeviceScene(desc, self.layout)
+        self.upload_bytes = keep.nbytes()      # host -> device bytes of the tables behind the descriptor
         del keep
         self.n_rays = self.layout.n_rays
         self.bundles = None
@@ -150,10 +151,11 @@ class Tracer:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _outputs(self, keep_images, found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False):
+    def _outputs(self, keep_images, found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False, packed=None):
+        packed = self.packed if packed is None else packed
         out = L.XrtOutputs()
-        out.counts = self.packed.data_ptr()
-        out.images = self.packed.data_ptr() + 8 * self.n_elem if (keep_images and self.layout.n_pixels) else None
+        out.counts = packed.data_ptr()
+        out.images = packed.data_ptr() + 8 * self.n_elem if (keep_images and self.layout.n_pixels) else None
         if want_lists:
             torch = self.torch
             if self.found_ids is None or self.found_ids.numel() < found_cap:
@@ -172,23 +174,28 @@ class Tracer:
         return out
 
     def trace(self, stream_id, keep_images=True, ray_begin=None, ray_count=None, zero=True,
-              found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False):
-        """Enqueue one fused generate->trace->bin launch for this rank's ray range (asynchronous)."""
+              found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False, packed=None):
+        """
+        Enqueue one fused generate->trace->bin launch for this rank's ray range (asynchronous).  ``packed`` = another
+        [counts | images] buffer of the same shape to accumulate into (double buffering against an all-reduce in flight).
+        """
         if ray_begin is None:
             ray_begin, ray_count = shard_range(self.n_rays, self.rank, self.world)
         if zero:
-            self.packed.zero_()
+            (self.packed if packed is None else packed).zero_()
             self.scalars.zero_()
-        out = self._outputs(keep_images, found_cap, lost_cap, lost_threshold, want_lists)
+        out = self._outputs(keep_images, found_cap, lost_cap, lost_threshold, want_lists, packed)
         with self.torch.cuda.device(self.device):
             L.check(self.lib.xrt_trace(self.scene.handle, self.seed, int(stream_id), int(ray_begin), int(ray_count),
                                        C.byref(out), self._stream()))
         return ray_begin, ray_count
 
-    def history(self, stream_id, ids, out=None):
+    def history(self, stream_id, ids, out=None, rows=False):
         """
         Replay the given global ray ids (int64 device tensor); returns (rays[E,7,n], mask[E,n]) on
         device.  ``out`` = (rays, mask) tensors of a previous call may be passed to reuse their memory.
+        ``rows=True``: the 7 n doubles of an element hold the reference's row arrays instead of planes --
+        origin (n,3), direction (n,3), wavelength (n,) back to back (XRT_HIST_ROWS; capacity is exactly n).
         """
         torch = self.torch
         n = int(ids.numel())
@@ -202,6 +209,7 @@ class Tracer:
         if n:
             h = L.XrtHistory()
             h.rays, h.mask, h.capacity = rays.data_ptr(), mask.data_ptr(), cap
+            h.layout = L.HIST_ROWS if rows else L.HIST_PLANES
             with torch.cuda.device(self.device):
                 L.check(self.lib.xrt_trace_history(self.scene.handle, self.seed, int(stream_id), ids.data_ptr(),
                                                    0, n, C.byref(h), self._stream()))
@@ -224,10 +232,10 @@ class Tracer:
                     image[name] = host[self.n_elem + off:self.n_elem + off + nx * ny].astype(np.float64).reshape(nx, ny)
         return meta, image
 
-    def allreduce(self):
-        """Sum counters + images over ranks (one collective on the packed buffer)."""
+    def allreduce(self, packed=None):
+        """Sum counters + images over ranks (one collective on the packed buffer), on the current stream."""
         if self.world > 1:
-            allreduce_packed(self.packed)
+            allreduce_packed(self.packed if packed is None else packed)
 
     def select_ids(self, stream_id, max_lost, keep_images=True):
         """
@@ -283,6 +291,90 @@ def _history_dicts(names, rays, mask):
     return out
 
 
+def rows_views(rays, mask, e, lo, hi):
+    """
+    Views of rows [lo, hi) of element e in a rows-layout history (XRT_HIST_ROWS): rays [E,7,n] holds, per element,
+    origin (n,3), direction (n,3), wavelength (n,) back to back.  Works on torch tensors and numpy arrays alike.
+    """
+    n = rays.shape[2]
+    flat = rays[e].reshape(-1)
+    return {'origin': flat[0:3 * n].reshape(n, 3)[lo:hi],
+            'direction': flat[3 * n:6 * n].reshape(n, 3)[lo:hi],
+            'wavelength': flat[6 * n:7 * n][lo:hi],
+            'mask': mask[e][lo:hi]}
+
+
+def to_host(torch, rays, mask):
+    """Device -> host through pinned memory (torch's caching host allocator), one synchronisation; numpy views."""
+    if rays.device.type != 'cuda':
+        return rays.numpy(), mask.numpy()
+    h_rays = torch.empty(rays.shape, dtype=rays.dtype, pin_memory=True)
+    h_mask = torch.empty(mask.shape, dtype=mask.dtype, pin_memory=True)
+    h_rays.copy_(rays, non_blocking=True)
+    h_mask.copy_(mask, non_blocking=True)
+    torch.cuda.current_stream(rays.device).synchronize()
+    return h_rays.numpy(), h_mask.numpy()
+
+
+def _row_dicts(names, rays, mask, n_found):
+    """Host rows-layout arrays -> (found, lost) history dicts: zero-copy views, found rays first."""
+    n = rays.shape[2]
+    found, lost = {}, {}
+    for e, name in enumerate(names):
+        for box, lo, hi in ((found, 0, n_found), (lost, n_found, n)):
+            v = rows_views(rays, mask, e, lo, hi)
+            v['mask'] = v['mask'].view(np.bool_)
+            box[name] = {key: v[key] for key in RAY_KEYS}
+    return found, lost
+
+
+def gather_rows(torch, rays, mask, n_found):
+    """
+    Variable-length gather of rows-layout histories onto rank 0 without pickling: one all_gather of the
+    (found, lost) counts, then each rank sends its two buffers as they are (NCCL send / recv on the GPUs, gloo in
+    the CPU tests) and rank 0 copies the row ranges into place -- found rays of all ranks first (rank order =
+    ascending global ray id), then the lost samples.  Returns (rays, mask, n_found_total); other ranks keep their own.
+    """
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n_elem, n = rays.shape[0], rays.shape[2]
+    mine = torch.tensor([n_found, n - n_found], dtype=torch.int64, device=rays.device)
+    table = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(table, mine)
+    table = [[int(v) for v in t.cpu()] for t in table]
+    if rank != 0:
+        if n:
+            dist.send(rays.contiguous(), dst=0)
+            dist.send(mask.contiguous(), dst=0)
+        return rays, mask, n_found
+    tot_found = sum(t[0] for t in table)
+    tot = tot_found + sum(t[1] for t in table)
+    out_rays = torch.empty((n_elem, 7, max(tot, 1)), dtype=rays.dtype, device=rays.device)
+    out_mask = torch.empty((n_elem, max(tot, 1)), dtype=mask.dtype, device=rays.device)
+    f_at, l_at = 0, tot_found
+    for r in range(world):
+        nf, nl = table[r]
+        if r == 0:
+            part_rays, part_mask = rays, mask
+        elif nf + nl:
+            part_rays = torch.empty((n_elem, 7, nf + nl), dtype=rays.dtype, device=rays.device)
+            part_mask = torch.empty((n_elem, nf + nl), dtype=mask.dtype, device=rays.device)
+            dist.recv(part_rays, src=r)
+            dist.recv(part_mask, src=r)
+        for e in range(n_elem):
+            if nf:
+                src, dst = rows_views(part_rays, part_mask, e, 0, nf), rows_views(out_rays[:, :, :tot], out_mask[:, :tot], e, f_at, f_at + nf)
+                for key in RAY_KEYS:
+                    dst[key].copy_(src[key])
+            if nl:
+                src, dst = rows_views(part_rays, part_mask, e, nf, nf + nl), rows_views(out_rays[:, :, :tot], out_mask[:, :tot], e, l_at, l_at + nl)
+                for key in RAY_KEYS:
+                    dst[key].copy_(src[key])
+        f_at += nf
+        l_at += nl
+    return out_rays[:, :, :tot], out_mask[:, :tot], tot_found
+
+
 def run_iteration(tracer, stream_id, keep_history=True, keep_images=True, keep_meta=True, max_lost=1000):
     """
     ``_raytrace_iter`` + ``_sort_raytrace`` (xicsrt_raytrace.py:178-278) on the device;
@@ -304,30 +396,21 @@ def run_iteration(tracer, stream_id, keep_history=True, keep_images=True, keep_m
     if keep_images:
         out['total']['image'] = image
     if keep_history:
+        # the replay writes the reference's row arrays directly (found rays first, then the lost sample); one
+        # device -> host copy through pinned memory, the dict entries are views of it
         n_found = int(found.numel())
         ids = tracer.torch.cat([found, lost])
-        rays, mask = tracer.history(stream_id, ids)
-        out['found']['history'] = _history_dicts(names, rays[:, :, :n_found], mask[:, :n_found])
-        out['lost']['history'] = _history_dicts(names, rays[:, :, n_found:], mask[:, n_found:])
+        rays, mask = tracer.history(stream_id, ids, rows=True)
         if tracer.world > 1:
-            _gather_histories(out, names)
+            rays, mask, n_found = gather_rows(tracer.torch, rays, mask, n_found)
+        h_rays, h_mask = to_host(tracer.torch, rays, mask)
+        out['found']['history'], out['lost']['history'] = _row_dicts(names, h_rays, h_mask, n_found)
     return out
 
 
 def merge_histories(parts, names):
     """Concatenate per-rank {element: rays} dicts in rank order (= ascending global ray id for 'found')."""
     return {name: {key: np.concatenate([p[name][key] for p in parts]) for key in RAY_KEYS} for name in names}
-
-
-def _gather_histories(out, names):
-    """Variable-length gather of the found / lost histories onto rank 0 (other ranks keep their own)."""
-    import torch.distributed as dist
-    rank, world = dist.get_rank(), dist.get_world_size()
-    box = [None] * world if rank == 0 else None
-    dist.gather_object((out['found']['history'], out['lost']['history']), box, dst=0)
-    if rank == 0:
-        out['found']['history'] = merge_histories([b[0] for b in box], names)
-        out['lost']['history'] = merge_histories([b[1] for b in box], names)
 
 
 def run_iterations_fused(tracer, num_iter, keep_images=True):
@@ -382,9 +465,12 @@ def combine_raytrace(input_list, keep_images=True, components=None):
     if len(input_list[0]['found']['history']) > 0:
         for kind in ('found', 'lost'):
             for name in names:
-                out[kind]['history'][name] = {
-                    key: np.concatenate([part[kind]['history'][name][key] for part in input_list])
-                    for key in RAY_KEYS}
+                if len(input_list) == 1:       # nothing to concatenate: hand the arrays on as they are
+                    out[kind]['history'][name] = {key: input_list[0][kind]['history'][name][key] for key in RAY_KEYS}
+                else:
+                    out[kind]['history'][name] = {
+                        key: np.concatenate([part[kind]['history'][name][key] for part in input_list])
+                        for key in RAY_KEYS}
     return out
 
 

@@ -128,7 +128,10 @@ class XrtOutputs(C.Structure):
 
 
 class XrtHistory(C.Structure):
-    _fields_ = [('rays', C.c_void_p), ('mask', C.c_void_p), ('capacity', C.c_uint64)]
+    _fields_ = [('rays', C.c_void_p), ('mask', C.c_void_p), ('capacity', C.c_uint64), ('layout', C.c_int32), ('pad0', C.c_int32)]
+
+
+HIST_PLANES, HIST_ROWS = 0, 1
 
 
 class XrtRaysIn(C.Structure):

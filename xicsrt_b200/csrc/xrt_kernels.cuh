@@ -421,36 +421,51 @@ __device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOp
     bool cand = false, reflected = false;
     if (layer >= depth) scanning = false;
 
+    // FP32 pre-test of one layer: true = the layer provably does not reflect the ray
+    auto pretest = [&](int lay) -> bool {
+        const uint4 b = dr.raw(site_optic(split, lay, 1));
+        const uint32_t na = ~b.x;
+        const float omu = fmaf((float)na, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // 1 - u1
+        const float rr = sqrt_approx(-1.3862943611198906f * lg2_approx(omu));                 // sqrt(-2 ln(1 - u1))
+        const float ang = 6.283185307179586f * (__uint_as_float(0x3f800000u | ((b.y & 0xffffffu) >> 1)) - 1.5f);
+        const float x = -s32 * rr * __cosf(ang), y = -s32 * rr * __sinf(ang);
+        const float t = fmaf(x, dr0, fmaf(y, dr1, dn));
+        const float sI = fabsf(t) * rsqrt_approx(fmaf(x, x, fmaf(y, y, 1.0f)));
+        const float gap = fabsf(sB - sI);
+        const float diff = gap - err;
+        const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
+        bool rej = (diff > 0.0f) & (diff * diff > t2 * c2);
+        if (gauss) {
+            const float u = __uint_as_float(0x3f800000u | (b.z >> 9)) - 1.0f;          // top 23 bits: u32 <= u
+            const float lim = 0.6931471805599453f * (lg_refl - lg2_approx(u));        // >= ln(reflectivity / u)
+            const float bound = fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * two_sigma2;
+            rej |= (diff > 0.0f) & (diff * diff > bound * c2) & (lim == lim);
+        }
+        // 1 - u1 below 2^-16 (|z| > 4.7): its 32-bit truncation is not precise enough for the radius, the layer is
+        // decided exactly (1.5e-5 of the layers)
+        return rej & (na >= 65536u);
+    };
+
     for (;;) {
-        // ---- scan: FP32 pre-test of one layer per iteration and lane
+        // ---- scan: two layers per iteration and lane (independent chains; the second is wasted only when the first
+        // is a candidate, 3 % of the time)
         while ((int)__popc(__ballot_sync(kFull, scanning)) >= min_scan) {
             if (scanning) {
-                const uint4 b = dr.raw(site_optic(split, layer, 1));
-                const uint32_t na = ~b.x;
-                const float omu = fmaf((float)na, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // 1 - u1
-                const float rr = sqrt_approx(-1.3862943611198906f * lg2_approx(omu));                 // sqrt(-2 ln(1 - u1))
-                const float ang = 6.283185307179586f * (__uint_as_float(0x3f800000u | ((b.y & 0xffffffu) >> 1)) - 1.5f);
-                const float x = -s32 * rr * __cosf(ang), y = -s32 * rr * __sinf(ang);
-                const float t = fmaf(x, dr0, fmaf(y, dr1, dn));
-                const float sI = fabsf(t) * rsqrt_approx(fmaf(x, x, fmaf(y, y, 1.0f)));
-                const float gap = fabsf(sB - sI);
-                const float diff = gap - err;
-                const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
-                bool rej = (diff > 0.0f) & (diff * diff > t2 * c2);
-                if (gauss) {
-                    const float u = __uint_as_float(0x3f800000u | (b.z >> 9)) - 1.0f;          // top 23 bits: u32 <= u
-                    const float lim = 0.6931471805599453f * (lg_refl - lg2_approx(u));        // >= ln(reflectivity / u)
-                    const float bound = fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * two_sigma2;
-                    rej |= (diff > 0.0f) & (diff * diff > bound * c2) & (lim == lim);
-                }
-                rej &= na >= 65536u;      // 1 - u1 below 2^-16 (|z| > 4.7): its 32-bit truncation is not precise enough for
-                                          // the radius, the layer is decided exactly (1.5e-5 of the layers)
-                if (rej) {
-                    ++layer;
-                    if (layer >= depth) scanning = false;
-                } else {
+                const bool rej0 = pretest(layer);
+                const bool rej1 = pretest(layer + 1);        // a layer index past the depth is never used
+                if (!rej0) {
                     cand = true;
                     scanning = false;
+                } else if (layer + 1 >= depth) {
+                    layer = depth;
+                    scanning = false;
+                } else if (!rej1) {
+                    layer += 1;
+                    cand = true;
+                    scanning = false;
+                } else {
+                    layer += 2;
+                    if (layer >= depth) scanning = false;
                 }
             }
         }
@@ -1082,11 +1097,21 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
 // streaming stores (evict-first): history planes are written once and read back by the host
 __device__ __forceinline__ void store_history(const XrtHistory &h, int elem, uint64_t slot, const Ray &r) {
     if (h.rays) {
-        double *p = h.rays + ((uint64_t)elem * 7) * h.capacity + slot;
         const uint64_t c = h.capacity;
-        __stcs(p, r.o.x); __stcs(p + c, r.o.y); __stcs(p + 2 * c, r.o.z);
-        __stcs(p + 3 * c, r.d.x); __stcs(p + 4 * c, r.d.y); __stcs(p + 5 * c, r.d.z);
-        __stcs(p + 6 * c, r.w);
+        double *e = h.rays + ((uint64_t)elem * 7) * c;
+        if (h.layout == XRT_HIST_ROWS) {
+            // the reference's (n, 3) row arrays: a warp writes 768 contiguous bytes per array, three 8-byte stores per
+            // thread that the L2 merges into full lines; the host then needs no transposition at all
+            double *po = e + 3 * slot, *pd = e + 3 * c + 3 * slot;
+            __stcs(po, r.o.x); __stcs(po + 1, r.o.y); __stcs(po + 2, r.o.z);
+            __stcs(pd, r.d.x); __stcs(pd + 1, r.d.y); __stcs(pd + 2, r.d.z);
+            __stcs(e + 6 * c + slot, r.w);
+        } else {
+            double *p = e + slot;
+            __stcs(p, r.o.x); __stcs(p + c, r.o.y); __stcs(p + 2 * c, r.o.z);
+            __stcs(p + 3 * c, r.d.x); __stcs(p + 4 * c, r.d.y); __stcs(p + 5 * c, r.d.z);
+            __stcs(p + 6 * c, r.w);
+        }
     }
     if (h.mask) h.mask[(uint64_t)elem * h.capacity + slot] = r.alive ? 1 : 0;
 }

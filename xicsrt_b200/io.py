@@ -1,10 +1,12 @@
 # -*- coding: utf-8 -*-
 """
 Files written after a trace (host side, outside the hot path): config / results
-as json, pickle or hdf5 and per-optic images as TIFF.  File naming and the
-``rot90`` image orientation follow the reference (``xicsrt/xicsrt_io.py:27-146``)
-so that files written here load with the reference's ``load_results`` and the
-other way round.
+as json, pickle or hdf5 and per-optic images as TIFF.  File naming, the ``rot90``
+image orientation (``xicsrt/xicsrt_io.py:27-146``) and the hdf5 group / attribute
+conventions (``xicsrt/util/mirhdf5.py``) follow the reference, so that files written
+here load with the reference's ``load_results`` and the other way round
+(``tests/test_io_reference_files.py`` loads files the reference itself wrote).  hdf5 needs
+h5py on both sides; without it ``results_ext`` must be ``.pkl`` or ``.json``.
 """
 import copy
 import json
@@ -81,12 +83,35 @@ def write_dict(data, filename, mkdir=False, overwrite=False):
         _write_hdf5(data, path)
 
 
+class RayArray(dict):
+    """Stand-in for the reference's dict subclass of the same name (xicsrt/objects/_RayArray.py:12-96)."""
+
+
+class _ReferenceUnpickler(pickle.Unpickler):
+    """
+    Result pickles written by the reference hold its ``RayArray`` dict subclass by class reference
+    (the lost histories, xicsrt_raytrace.py:268-276): map it to a plain dict subclass so that such files load
+    where the reference package is not installed.
+    """
+
+    def find_class(self, module, name):
+        if module.split('.')[0] == 'xicsrt' and name == 'RayArray':
+            return RayArray
+        return super().find_class(module, name)
+
+
+def _plain(tree):
+    if isinstance(tree, dict):
+        return {k: _plain(v) for k, v in tree.items()}
+    return tree
+
+
 def read_dict(filename):
     path = pathlib.Path(filename).expanduser()
     kind = _kind_of(path)
     if kind == 'pickle':
         with open(path, 'rb') as ff:
-            return pickle.load(ff)
+            return _plain(_ReferenceUnpickler(ff).load())
     if kind == 'json':
         with open(path, 'r') as ff:
             return xconfig.to_numpy(json.load(ff))
@@ -102,47 +127,80 @@ def _h5py():
     return h5py
 
 
+# The hdf5 layout is the one of the reference's util/mirhdf5.py (:185-245 writing, :248-330 reading), so that
+# result files move between the two programs:
+#   dict  -> group with attrs '_mirhdf5 python object type' = b'dict' and '_mirhdf5 dictionary order' = [key bytes]
+#   list  -> group with attr  '_mirhdf5 python object type' = b'list', items under '0000', '0001', ...
+#   None  -> dataset False with attr '_mirhdf5 python None' = True
+#   str   -> scalar dataset with attr '_mirhdf5 python str' = True
+#   other -> dataset (numpy arrays, numbers, bools)
+# The functions take any object with h5py's group interface (tests drive them with an in-memory stand-in when h5py
+# is not installed).
+H5_TYPE, H5_ORDER, H5_NONE, H5_STR = ('_mirhdf5 python object type', '_mirhdf5 dictionary order',
+                                      '_mirhdf5 python None', '_mirhdf5 python str')
+
+
+def hdf5_put_item(group, key, item):
+    if isinstance(item, dict):
+        hdf5_put_dict(group.create_group(key), item)
+    elif isinstance(item, (list, tuple)):
+        sub = group.create_group(key)
+        sub.attrs[H5_TYPE] = 'list'.encode()
+        for ii, val in enumerate(item):
+            hdf5_put_item(sub, '{:04d}'.format(ii), val)
+    elif item is None:
+        group[key] = False
+        group[key].attrs[H5_NONE] = True
+    elif isinstance(item, str):
+        group.create_dataset(key, data=item)
+        group[key].attrs[H5_STR] = True
+    else:
+        group.create_dataset(key, data=item if np.isscalar(item) else np.asarray(item))
+
+
+def hdf5_put_dict(group, tree):
+    group.attrs[H5_TYPE] = 'dict'.encode()
+    group.attrs[H5_ORDER] = [str(key).encode() for key in tree.keys()]
+    for key, val in tree.items():
+        hdf5_put_item(group, str(key), val)
+
+
+def hdf5_get(node, is_group):
+    """node: a group or dataset; is_group(node) tells which."""
+    attrs = node.attrs
+    if is_group(node):
+        kind = attrs[H5_TYPE] if H5_TYPE in attrs else 'dict'
+        kind = kind.decode() if hasattr(kind, 'decode') else kind
+        if kind == 'list':
+            return [hdf5_get(node[key], is_group) for key in node.keys()]
+        if kind != 'dict':
+            raise Exception('Unknown group type: {}'.format(kind))
+        keys = attrs[H5_ORDER] if H5_ORDER in attrs else node.keys()
+        out = {}
+        for key in keys:
+            key = key.decode() if hasattr(key, 'decode') else key
+            out[key] = hdf5_get(node[key], is_group)
+        return out
+    if H5_NONE in attrs:
+        return None
+    val = node[()]
+    if H5_STR in attrs:
+        val = val.decode() if hasattr(val, 'decode') else str(val)
+    return val
+
+
 def _write_hdf5(data, path):
     h5py = _h5py()
-
-    def put(group, tree):
-        for key, val in tree.items():
-            if isinstance(val, dict):
-                put(group.create_group(str(key)), val)
-            elif val is None:
-                group.attrs[f'{key}__none'] = True
-            elif isinstance(val, str):
-                group.attrs[str(key)] = val
-            else:
-                arr = np.asarray(val)
-                if arr.dtype.kind in 'OU':
-                    group.attrs[str(key)] = json.dumps(_jsonable(val))
-                    group.attrs[f'{key}__json'] = True
-                else:
-                    group.create_dataset(str(key), data=arr)
+    if not isinstance(data, dict):
+        raise Exception('Incorrect input type. Dictionary expected.')
     with h5py.File(path, 'w') as ff:
-        put(ff, data)
+        hdf5_put_dict(ff, data)
 
 
 def _read_hdf5(path):
     h5py = _h5py()
-
-    def get(group):
-        out = {}
-        for key, val in group.items():
-            out[key] = get(val) if isinstance(val, h5py.Group) else val[()]
-        for key, val in group.attrs.items():
-            if key.endswith('__none'):
-                out[key[:-6]] = None
-            elif key.endswith('__json'):
-                continue
-            elif f'{key}__json' in group.attrs:
-                out[key] = json.loads(val)
-            else:
-                out[key] = val
-        return out
     with h5py.File(path, 'r') as ff:
-        return get(ff)
+        return hdf5_get(ff, lambda node: isinstance(node, h5py.Group))
 
 
 def load_config(filename):

@@ -46,6 +46,19 @@ class _Keep:
         self.items.append(o)
         return o
 
+    def nbytes(self):
+        """Bytes of the tables xrt_scene_create copies to the device (numpy buffers and ctypes tables)."""
+        total = 0
+        for it in self.items:
+            if isinstance(it, np.ndarray):
+                total += int(it.nbytes)
+            else:
+                try:
+                    total += int(C.sizeof(it))
+                except TypeError:
+                    pass
+        return total
+
 
 # ---------------------------------------------------------------------------
 # source
