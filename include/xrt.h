@@ -125,6 +125,12 @@ typedef struct XrtMesh {
                                     vertex query, replaces the reference's kd-tree)      */
     const int32_t *vgrid_items;
     const double *vgrid_xyz;     /* [items][4]: x, y, z of vgrid_items[k] (cell-ordered), pad */
+    /* the same lookups with the data inline, cell- / vertex-ordered (fewer dependent loads per ray):       */
+    const int32_t *nb_start;     /* [grid_nx*grid_ny + 1] vertices of the 3 x 3 block of cells around each cell */
+    const double *nb_rec;        /* [items][4]: x, y, z, vertex index                                   */
+    const double *tri_rec;       /* [grid_items][8]: barycentric transform (6), triangle index, pad      */
+    const double *vertex_face_rec; /* [n_points][8][16]: face_rec of the faces around each vertex, [12] < 0 = no face,
+                                      [13] = face index                                                  */
 } XrtMesh;
 
 typedef struct XrtOpticDesc {

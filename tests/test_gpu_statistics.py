@@ -10,6 +10,7 @@ at large N: partition invariance (any split of the ray-id range gives identical
 counters and images), determinism, image sum == num_out, found-history consistency.
 """
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -175,6 +176,29 @@ def test_runs_use_cumulative_seeds_and_combine(torch):
     total = sum(p['total']['image']['detector'] for p in parts)
     assert np.array_equal(res['total']['image']['detector'], total)
     assert res['config']['general']['random_seed'] == 5
+
+
+def test_images_are_saved_per_run_and_combined(torch, tmp_path):
+    """raytrace_single saves its images whenever save_images is set, also as a run inside raytrace()
+    (xicsrt_raytrace.py:168-169): one TIFF per run with the run suffix, plus the combined one."""
+    import xicsrt_b200
+    from PIL import Image
+    cfg = scenes.get('sphere')
+    cfg['sources']['source']['intensity'] = 50000
+    cfg['general'].update({'keep_history': False, 'number_of_runs': 2, 'random_seed': 3, 'save_images': True,
+                           'output_path': str(tmp_path), 'output_prefix': 'run'})
+    res = xicsrt_b200.raytrace(cfg)
+    files = sorted(os.listdir(tmp_path))
+    assert files == ['run_crystal.tif', 'run_crystal_0000.tif', 'run_crystal_0001.tif',
+                     'run_detector.tif', 'run_detector_0000.tif', 'run_detector_0001.tif'], files
+    parts = [np.array(Image.open(tmp_path / f'run_detector_{k:04d}.tif')) for k in range(2)]
+    total = np.array(Image.open(tmp_path / 'run_detector.tif'))
+    assert np.array_equal(parts[0] + parts[1], total)
+    assert np.array_equal(total, np.rot90(res['total']['image']['detector']).astype(np.float32))
+    # a direct raytrace_single call writes its images too
+    cfg['general'].update({'number_of_runs': 1, 'output_prefix': 'single'})
+    xicsrt_b200.raytrace_single(cfg)
+    assert os.path.exists(tmp_path / 'single_detector.tif')
 
 
 @pytest.mark.parametrize('name', ['sphere', 'sphere_step_box', 'apertures', 'mosaic_sphere', 'torus_bragg',

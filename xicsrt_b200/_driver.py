@@ -535,6 +535,11 @@ def raytrace_single(config, _internal=False):
         tracer.close()
     if _internal is False:
         _finish(output, g, single=True)
+    # per-run images carry the run suffix and are written for direct calls and for every run inside raytrace()
+    # (xicsrt_raytrace.py:168-169: outside the `_internal is False` block)
+    if g['save_images'] and _dist_info()[0] == 0:
+        from . import io as xio
+        xio.save_images(output)
     return output
 
 
@@ -577,6 +582,10 @@ def raytrace_mp(config, processes=None):
     The reference's multiprocessing entry (xicsrt_multiprocessing.py:12-81) splits *runs*
     over host processes.  Here the parallel resource is the GPU (and, under torchrun, the
     GPUs of the box: rays of every iteration are sharded over ranks inside
-    :func:`raytrace_single`), so this is :func:`raytrace`; ``processes`` is accepted and ignored.
+    :func:`raytrace_single`), so this is :func:`raytrace`.  ``processes`` has no meaning for a GPU
+    run: it is accepted for drop-in compatibility and a value other than None / 1 is logged, not
+    silently dropped.
     """
+    if processes not in (None, 1):
+        log.warning('raytrace_mp: processes=%s ignored -- runs execute on the GPU(s) of this process group', processes)
     return raytrace(config)

@@ -52,7 +52,8 @@ class XrtMesh(C.Structure):
                 ('grid_x0', C.c_double), ('grid_y0', C.c_double),
                 ('grid_inv_dx', C.c_double), ('grid_inv_dy', C.c_double),
                 ('grid_start', _pi32), ('grid_items', _pi32),
-                ('vgrid_start', _pi32), ('vgrid_items', _pi32), ('vgrid_xyz', _pd)]
+                ('vgrid_start', _pi32), ('vgrid_items', _pi32), ('vgrid_xyz', _pd),
+                ('nb_start', _pi32), ('nb_rec', _pd), ('tri_rec', _pd), ('vertex_face_rec', _pd)]
 
 
 class XrtOpticDesc(C.Structure):

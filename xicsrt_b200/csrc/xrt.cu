@@ -121,9 +121,11 @@ static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     if (m.n_points <= 0 || m.n_faces <= 0 || !m.points || !m.faces || !m.face_normals || !m.face_geom || !m.face_area || !m.face_rec || !m.vertex_faces)
         return fail(XRT_EINVAL, "mesh: points / faces missing");
     size_t cells = (size_t)m.grid_nx * (size_t)m.grid_ny;
-    int32_t n_items = 0, n_vitems = 0;
+    int32_t n_items = 0, n_vitems = 0, n_nb = 0;
     if (cells && m.grid_start) n_items = m.grid_start[cells];
     if (cells && m.vgrid_start) n_vitems = m.vgrid_start[cells];
+    if (cells && m.nb_start) n_nb = m.nb_start[cells];
+    if (!m.nb_start || !m.nb_rec) { m.nb_start = nullptr; m.nb_rec = nullptr; }
     UP(m.points, 3 * (size_t)m.n_points);
     UP(m.faces, 3 * (size_t)m.n_faces);
     UP(m.face_normals, 3 * (size_t)m.n_faces);
@@ -143,6 +145,10 @@ static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     UP(m.vgrid_start, (cells && m.vgrid_start) ? cells + 1 : 0);
     UP(m.vgrid_items, n_vitems);
     UP(m.vgrid_xyz, (cells && m.vgrid_start && m.vgrid_xyz) ? 4 * (size_t)n_vitems : 0);
+    UP(m.nb_start, (cells && m.nb_start) ? cells + 1 : 0);
+    UP(m.nb_rec, (cells && m.nb_start) ? 4 * (size_t)n_nb : 0);
+    UP(m.tri_rec, (cells && m.grid_start && m.tri_rec) ? 8 * (size_t)n_items : 0);
+    UP(m.vertex_face_rec, m.vertex_face_rec ? 128 * (size_t)m.n_points : 0);
     const XrtMesh *d = nullptr;
     int rc = upload(s, &m, 1, &d);
     if (rc != XRT_OK) return rc;

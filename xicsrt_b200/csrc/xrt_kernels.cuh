@@ -31,6 +31,12 @@ namespace xrt {
 #ifndef XRT_RECORD_BLOCKS
 #define XRT_RECORD_BLOCKS 3
 #endif
+#ifndef XRT_MESH_BLOCKS
+#define XRT_MESH_BLOCKS 2      // resident blocks per SM of the mesh variants
+#endif
+#ifndef XRT_MIN_SCAN
+#define XRT_MIN_SCAN 8         // mosaic scan stage: lanes that must still be scanning for another scan iteration
+#endif
 constexpr int kBlock = XRT_BLOCK;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -253,7 +259,7 @@ __device__ __forceinline__ void stage_c(const XrtSceneDesc &sc, const XrtOutputs
     for (int k = split + 1; k < nopt; ++k) {
         const XrtOpticDesc &op = sc.optics[k];
         if (r.alive) {
-            trace_optic<FT>(op, k, dr, r);
+            trace_optic_any<FT, PhiloxDraws>(op, k, dr, r);
             if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
         }
         count_alive(c, k + 1, r.alive);
@@ -355,7 +361,7 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
 // optic_interact): a pass reflects the ray, a fail resumes the scan at the next layer.  When neither is left to do, the
 // unfinished rays go back to queue 1 with their layer index (in the top byte of the id word) and their wavelength, and
 // are re-packed with new rays.  While the queues drain at the end of the launch the batch runs to completion.
-constexpr int kMinScan = 16;
+constexpr int kMinScan = XRT_MIN_SCAN;
 constexpr uint64_t kIdMask = (1ull << 56) - 1ull;
 
 template <uint32_t FT, uint32_t KN, bool HIST>
@@ -563,6 +569,7 @@ __device__ __forceinline__ bool spectro_stage_ab(const XrtSceneDesc &sc, const X
 // the mosaic variants (scan state + exact layer evaluation), for the spectrometer variant (two ray groups per pass =
 // two independent chains) and for the lean extended-source variant (bundle lookup + focused cone basis); 3 otherwise.
 template <uint32_t FT, uint32_t KN> __host__ __device__ constexpr int trace_min_blocks() {
+    if ((FT & FT_MESH) != 0) return XRT_MESH_BLOCKS;
     return (((FT & FT_MESH) != 0 || (FT & FT_MOSAIC) != 0 || FT == FT_SRCLEAN ||
              ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
             XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS;
@@ -603,15 +610,31 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     const bool defer = (FT == 0) ? false : ((lazy_rt & 4) != 0);   // eager normal line: exact deviate left to stage B
     const bool count_src = list.ids == nullptr;  // list mode: k_cull32 has counted the rays out of the source
 
-    // mesh split optic: stage the face operands every ray is tested against in shared memory
+    // mesh split optic: stage the face operands every ray is tested against in shared memory.  When every ray starts
+    // at the same point (point source in front of a refining mesh as first optic) the staged values are the per-face
+    // constants of mesh_all_faces_point instead, and stage A1 runs its dot-product pre-selection.
     const double *staged = nullptr;
+    bool mesh_staged = false, mesh_point = false;
     if constexpr ((FT & FT_MESH) != 0) {
+        if constexpr (!SPECTRO) {
+            mesh_staged = split == 0 && ops.shape == XRT_SHAPE_MESH && (ops.flags & XRT_F_MESH_REFINE) && lazy &&
+                          sc.source.kind != XRT_SRC_BUNDLES && sc.source.cone != XRT_CONE_ISOTROPIC_XY;
+        }
         if (ops.shape == XRT_SHAPE_MESH) {
             const double *geom;
             const int nf = mesh_stage1_faces(ops, geom);
             if (nf <= kStageFaces) {
                 double *dst = s_queue + (size_t)(kBlock / 32) * warp_queue_doubles<FT, KN>();
-                for (int i = threadIdx.x; i < 9 * nf; i += kBlock) dst[i] = __ldg(geom + i);
+                const XrtSourceDesc &src = sc.source;
+                mesh_point = mesh_staged && src.extent[0] == 0.0 && src.extent[1] == 0.0 && src.extent[2] == 0.0 &&
+                             src.spatial == XRT_SPATIAL_UNIFORM && kPointRec * nf <= 9 * kStageFaces;
+                if (mesh_point) {
+                    V3 o = v3(src.origin);
+                    if (optic_is_local<FT>(ops)) o = to_local(ops.orient, o - v3(ops.origin));
+                    for (int i = threadIdx.x; i < nf; i += kBlock) mesh_point_constants(geom + 9 * i, o, dst + kPointRec * i);
+                } else {
+                    for (int i = threadIdx.x; i < 9 * nf; i += kBlock) dst[i] = __ldg(geom + i);
+                }
                 staged = dst;
             }
         }
@@ -622,11 +645,6 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     // optic is the first optic, a refining mesh, and the wavelength is lazy (a ray is rebuilt from its id in stage A2)
     int na = 0;
     double *qa = q1 + q1_planes<FT>() * kQ1Cap;
-    bool mesh_staged = false;
-    if constexpr ((FT & FT_MESH) != 0 && !SPECTRO) {
-        mesh_staged = split == 0 && ops.shape == XRT_SHAPE_MESH && (ops.flags & XRT_F_MESH_REFINE) && lazy &&
-                      sc.source.kind != XRT_SRC_BUNDLES && sc.source.cone != XRT_CONE_ISOTROPIC_XY;
-    }
     unsigned n_src = 0, n_split = 0;   // rays out of the source / the split optic (warp-uniform registers)
 
     IdCursor<SPECTRO ? kUnroll : 1> cur;
@@ -681,7 +699,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
                     SrcLocal L;
                     source_local<FT, KN>(sc.source, id, L);
                     generate_geometry<FT, PhiloxDraws, KN, true>(sc.source, L, dr, r, s_sincos);
-                    cand = optic_geometry<FT, true, KN>(ops, r, n, staged, &Xc) == HIT_INSIDE;
+                    cand = optic_geometry<FT, true, KN>(ops, r, n, mesh_point ? nullptr : staged, &Xc) == HIT_INSIDE;
                 }
                 emit_lost<HIST>(out, c.lane, c.lt_mask, dr, active && !cand, id);
                 const unsigned m = __ballot_sync(kFull, cand);
@@ -765,7 +783,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             for (int k = 0; k < split; ++k) {
                 const XrtOpticDesc &op = sc.optics[k];
                 if (r.alive) {
-                    trace_optic<FT>(op, k, dr, r);
+                    trace_optic_any<FT, PhiloxDraws>(op, k, dr, r);
                     if (r.alive && (op.flags & XRT_F_IMAGE) && out.images) add_pixel(out, op, r, c.lt_mask);
                 }
                 count_alive(c, k + 1, r.alive);
@@ -783,7 +801,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
                             o = to_local(ops.orient, o - v3(ops.origin));
                             d = to_local(ops.orient, d);
                         }
-                        hit = mesh_coarse_hit(ops, o, d, Xc, staged);
+                        hit = mesh_coarse_hit(ops, o, d, Xc, staged, mesh_point);
                     }
                     emit_lost<HIST>(out, c.lane, c.lt_mask, dr, valid && !hit, id);
                     const unsigned mh = __ballot_sync(kFull, hit);
@@ -797,7 +815,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
                     continue;
                 }
             }
-            if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, staged) == HIT_INSIDE;
+            if (r.alive) cand = optic_geometry<FT, (FT & FT_MESH) != 0, KN>(ops, r, n, mesh_point ? nullptr : staged) == HIT_INSIDE;
             // Bragg pre-test (bragg_cull_general): enabled by xrt_scene_create for a spherical Bragg crystal traced in
             // global coordinates; first level with the (approximate / exact / deferred) wavelength, second level with
             // the ray's rocking-curve uniform; the survivors take the exact path in stage B

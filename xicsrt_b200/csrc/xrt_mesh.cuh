@@ -77,6 +77,68 @@ __device__ __forceinline__ int mesh_all_faces(const double *__restrict__ geom, i
     return hit;
 }
 
+// step 1 for rays that all start at one point o (a point source in front of the first optic): with s = o - p0 fixed,
+// the three triple products of Moeller-Trumbore are dot products of the direction with per-face constants,
+//     a = e1.(d x e2) = d.N,  N = e2 x e1;    s.(d x e2) = d.A,  A = e2 x s;    d.(s x e1) = d.Q,  Q = s x e1,
+// nine multiply-adds per face instead of two cross products.  They are not the reference's operation order, so they
+// only PRE-SELECT (1e-9 relative slack on every edge, degenerate faces kept): the faces that survive are tested with
+// the reference's own arithmetic from the global operands, in ascending order, and the last hit wins as before.
+// naq: [n_faces][10] = N, A, Q, slack in shared memory (built by the block from face_geom and o).
+constexpr int kPointRec = 10;
+__device__ __forceinline__ void mesh_point_constants(const double *__restrict__ g, V3 o, double *__restrict__ out) {
+    const V3 p0 = ld3(g), e1 = ld3(g + 3), e2 = ld3(g + 6);
+    const V3 s = o - p0;
+    const V3 N = cross(e2, e1), A = cross(e2, s), Q = cross(s, e1);
+    out[0] = N.x; out[1] = N.y; out[2] = N.z;
+    out[3] = A.x; out[4] = A.y; out[5] = A.z;
+    out[6] = Q.x; out[7] = Q.y; out[8] = Q.z;
+    // absolute slack of the pre-selection: 1e-12 of the operand scale (rounding is 1e-16 of it), for grazing rays
+    // whose |a| is itself of the order of the rounding
+    out[9] = 1e-12 * (sqrt(dot(N, N)) + sqrt(dot(A, A)) + sqrt(dot(Q, Q)));
+}
+
+__device__ __forceinline__ int mesh_all_faces_point(const double *__restrict__ naq, const double *__restrict__ geom, int n_faces,
+                                                    V3 o, V3 d, V3 &X) {
+    const double eps = 1e-15, tol = 1e-9;
+    int hit = -1;
+    for (int base = 0; base < n_faces; base += 32) {
+        const int cnt = min(32, n_faces - base);
+        unsigned cand = 0u;
+        for (int j = 0; j < cnt; ++j) {
+            const double *c = naq + kPointRec * (base + j);
+            const double a = d.x * c[0] + d.y * c[1] + d.z * c[2];
+            double ua = d.x * c[3] + d.y * c[4] + d.z * c[5];
+            double va = d.x * c[6] + d.y * c[7] + d.z * c[8];
+            const double aa = fabs(a);
+            if (a < 0.0) { ua = -ua; va = -va; }
+            const double slack = fma(tol, aa, c[9]);
+            const double lo = -slack, hi = aa + slack;
+            const bool out_side = (ua < lo) | (ua > hi) | (va < lo) | (ua + va > hi);
+            if (!out_side || aa < 4.0 * eps) cand |= 1u << j;
+        }
+        while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            V3 p0, e1, e2;
+            mesh_face_operands<false>(geom + 9 * (base + j), p0, e1, e2);
+            const V3 h = cross(d, e2);
+            const double a = dot(e1, h);
+            if (a > -eps && a < eps) continue;
+            const double inv = 1.0 / a;
+            const V3 s = o - p0;
+            const double u = inv * dot(s, h);
+            if (u < 0.0 || u > 1.0) continue;
+            const V3 q = cross(s, e1);
+            const double v = inv * dot(d, q);
+            if (v < 0.0 || u + v > 1.0) continue;
+            const double t = inv * dot(e2, q);
+            hit = base + j;
+            X = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+        }
+    }
+    return hit;
+}
+
 // step 2: exact nearest vertex through the uniform xy grid -- rings of cells around the query
 // cell until no unvisited cell can hold a closer vertex (the xy distance to the ring bounds
 // the 3-D distance from below).
@@ -87,6 +149,30 @@ __device__ __forceinline__ int mesh_nearest_vertex(const XrtMesh &m, V3 q) {
     int cy = (int)floor((q.y - m.grid_y0) * m.grid_inv_dy);
     cx = min(max(cx, 0), nx - 1);
     cy = min(max(cy, 0), ny - 1);
+    if (m.nb_start) {
+        // One contiguous list holds the vertices of the 3 x 3 block of cells around (cx, cy), coordinates and index
+        // inline: two dependent loads instead of a walk over nine cells.  The winner is exact when it is closer than
+        // the rim of the block (sides on the edge of the grid have nothing beyond them); otherwise the ring search
+        // below decides.
+        const int c = cy * nx + cx;
+        const int b = __ldg(m.nb_start + c), e = __ldg(m.nb_start + c + 1);
+        int bi = -1;
+        double bd2 = CUDART_INF;
+        for (int k = b; k < e; ++k) {
+            const double2 xy = __ldg((const double2 *)(m.nb_rec + 4 * (size_t)k));
+            const double2 zi = __ldg((const double2 *)(m.nb_rec + 4 * (size_t)k + 2));
+            const V3 p = v3(xy.x, xy.y, zi.x) - q;
+            const double d2 = dot(p, p);
+            if (d2 < bd2) { bd2 = d2; bi = (int)zi.y; }
+        }
+        const double inf = CUDART_INF;
+        const double rx0 = (cx > 0) ? q.x - (m.grid_x0 + (cx - 1) * dx) : inf;
+        const double rx1 = (cx < nx - 1) ? (m.grid_x0 + (cx + 2) * dx) - q.x : inf;
+        const double ry0 = (cy > 0) ? q.y - (m.grid_y0 + (cy - 1) * dy) : inf;
+        const double ry1 = (cy < ny - 1) ? (m.grid_y0 + (cy + 2) * dy) - q.y : inf;
+        const double rim = fmax(fmin(fmin(rx0, rx1), fmin(ry0, ry1)), 0.0);
+        if (bi >= 0 && bd2 < rim * rim) return bi;
+    }
     int best = -1;
     double best_d2 = CUDART_INF;
     const int max_ring = max(nx, ny);
@@ -120,32 +206,59 @@ __device__ __forceinline__ int mesh_nearest_vertex(const XrtMesh &m, V3 q) {
 
 // step 3: the faces around vertex `vert`.  face_geom gives p0 and the two edges, face_area the
 // constant |(p0 - p1) x (p0 - p2)| of the reference's area-sum test.
+struct FaceRec { double2 g0, g1, g2, g3, g4, g5, g6; };
+
+__device__ __forceinline__ FaceRec load_face_rec(const double *rec) {
+    const double2 *g = (const double2 *)rec;
+    FaceRec r;
+    r.g0 = __ldg(g); r.g1 = __ldg(g + 1); r.g2 = __ldg(g + 2); r.g3 = __ldg(g + 3); r.g4 = __ldg(g + 4);
+    r.g5 = __ldg(g + 5); r.g6 = __ldg(g + 6);
+    return r;
+}
+
+// one candidate face (_ShapeMesh.py:350-426): ray / plane point, inside test by the area sum, distance >= 0
+__device__ __forceinline__ bool mesh_test_face(const FaceRec &r, V3 o, V3 d, V3 &X) {
+    const V3 p0 = v3(r.g0.x, r.g0.y, r.g1.x), e1 = v3(r.g1.y, r.g2.x, r.g2.y), e2 = v3(r.g3.x, r.g3.y, r.g4.x);
+    const V3 n = v3(r.g4.y, r.g5.x, r.g5.y);
+    const double area = r.g6.x;
+    const double dist = dot(p0 - o, n) / dot(d, n);
+    if (!(dist >= 0.0)) return false;
+    const V3 P = v3(d.x * dist + o.x, d.y * dist + o.y, d.z * dist + o.z);
+    const V3 a = P - p0, b = a - e1, c = a - e2;
+    // P lies in the face plane, so b x c, c x a and a x b are parallel to the unit normal n:
+    // their lengths are |(.) . n| -- the reference's three norms without a square root
+    const double diff = fabs(dot(cross(b, c), n)) + fabs(dot(cross(c, a), n)) + fabs(dot(cross(a, b), n)) - area;
+    if (diff < 1e-10) {
+        X = P;
+        return true;
+    }
+    return false;
+}
+
 __device__ __forceinline__ int mesh_candidate_faces(const XrtMesh &m, int vert, V3 o, V3 d, V3 &X) {
+    if (m.vertex_face_rec) {
+        // the vertex's <= 8 face records sit back to back (no hop through the face index); a rolled loop: the mesh
+        // variants are bound by instruction fetch as much as by loads (ncu: no_instruction 4.4 stall cycles per issue
+        // with this loop unrolled)
+        const double *base = m.vertex_face_rec + 128 * (size_t)vert;
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            const FaceRec cur = load_face_rec(base + 16 * k);
+            if (cur.g6.x < 0.0) break;          // records are packed: the first empty slot ends the list
+            if (mesh_test_face(cur, o, d, X)) return (int)cur.g6.y;
+        }
+        return -1;
+    }
     // the <= 8 face ids of the vertex in two 16-byte loads, then one 128-byte record per face
     const int4 fa = __ldg((const int4 *)(m.vertex_faces + 8 * (size_t)vert));
     const int4 fb = __ldg((const int4 *)(m.vertex_faces + 8 * (size_t)vert + 4));
     const int ids[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 8; ++k) {
         const int f = ids[k];
         if (f < 0) continue;
-        const double2 *g = (const double2 *)(m.face_rec + 16 * (size_t)f);
-        const double2 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3), g4 = __ldg(g + 4),
-                      g5 = __ldg(g + 5), g6 = __ldg(g + 6);
-        const V3 p0 = v3(g0.x, g0.y, g1.x), e1 = v3(g1.y, g2.x, g2.y), e2 = v3(g3.x, g3.y, g4.x);
-        const V3 n = v3(g4.y, g5.x, g5.y);
-        const double area = g6.x;
-        const double dist = dot(p0 - o, n) / dot(d, n);
-        if (!(dist >= 0.0)) continue;
-        const V3 P = v3(d.x * dist + o.x, d.y * dist + o.y, d.z * dist + o.z);
-        const V3 a = P - p0, b = a - e1, c = a - e2;
-        // P lies in the face plane, so b x c, c x a and a x b are parallel to the unit normal n:
-        // their lengths are |(.) . n| -- the reference's three norms without a square root
-        const double diff = fabs(dot(cross(b, c), n)) + fabs(dot(cross(c, a), n)) + fabs(dot(cross(a, b), n)) - area;
-        if (diff < 1e-10) {
-            X = P;
-            return f;
-        }
+        const FaceRec r = load_face_rec(m.face_rec + 16 * (size_t)f);
+        if (mesh_test_face(r, o, d, X)) return f;
     }
     return -1;
 }
@@ -162,6 +275,19 @@ __device__ __forceinline__ int mesh_find_triangle(const XrtMesh &m, double x, do
     const int c = cy * m.grid_nx + cx;
     const int b = __ldg(m.grid_start + c), e = __ldg(m.grid_start + c + 1);
     const double eps = 100.0 * 2.220446049250313e-16;
+    if (m.tri_rec) {
+        // transform and triangle index inline in the cell's list: no hop through the triangle id
+        for (int k = b; k < e; ++k) {
+            const double2 *T = (const double2 *)(m.tri_rec + 8 * (size_t)k);
+            const double2 t01 = __ldg(T), t23 = __ldg(T + 1), t45 = __ldg(T + 2), ti = __ldg(T + 3);
+            const double ddx = x - t45.x, ddy = y - t45.y;
+            b0 = t01.x * ddx + t01.y * ddy;
+            b1 = t23.x * ddx + t23.y * ddy;
+            b2 = 1.0 - b0 - b1;
+            if (b0 >= -eps && b0 <= 1.0 + eps && b1 >= -eps && b1 <= 1.0 + eps && b2 >= -eps && b2 <= 1.0 + eps) return (int)ti.x;
+        }
+        return -1;
+    }
     for (int k = b; k < e; ++k) {
         const int t = __ldg(m.grid_items + k);
         const double *T = m.tri_transform + 6 * (size_t)t;
@@ -200,11 +326,14 @@ __device__ __forceinline__ int mesh_stage1_faces(const XrtOpticDesc &op, const d
 // shared-memory copy of the step-1 face operands.
 // The coarse step alone (step 1 of a refining mesh): true = some coarse face is hit, Xc = the hit point.
 // The fused kernel runs it for every ray, re-packs the ~half that hit and resumes mesh_intersect with Xc.
-__device__ __forceinline__ bool mesh_coarse_hit(const XrtOpticDesc &op, V3 o, V3 d, V3 &Xc, const double *staged = nullptr) {
+__device__ __forceinline__ bool mesh_coarse_hit(const XrtOpticDesc &op, V3 o, V3 d, V3 &Xc, const double *staged = nullptr,
+                                                bool point_constants = false) {
     const double *geom;
     const int n1 = mesh_stage1_faces(op, geom);
     Xc = nan3();
-    const int face = staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
+    int face;
+    if (staged && point_constants) face = mesh_all_faces_point(staged, geom, n1, o, d, Xc);
+    else face = staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
     return face >= 0;
 }
 

@@ -955,4 +955,18 @@ __device__ __forceinline__ void trace_optic(const XrtOpticDesc &op, int k, const
     if (optic_geometry<FT, true, KN>(op, r, n) == HIT_INSIDE) optic_interact<FT, DR, KN>(op, k, dr, r, n);
 }
 
+// One out-of-line copy for the variants whose code is large (mesh optics): the fused kernel reaches trace_optic from
+// the optics before the split optic and from stage C, and two inlined copies of every shape and interaction cost more
+// in instruction fetch (the mesh variants are 180 kB of code) than the call does.
+template <uint32_t FT, class DR>
+static __device__ __noinline__ void trace_optic_shared(const XrtOpticDesc &op, int k, const DR &dr, Ray &r) {
+    trace_optic<FT, DR, 0>(op, k, dr, r);
+}
+
+template <uint32_t FT, class DR>
+__device__ __forceinline__ void trace_optic_any(const XrtOpticDesc &op, int k, const DR &dr, Ray &r) {
+    if constexpr ((FT & FT_MESH) != 0) trace_optic_shared<FT, DR>(op, k, dr, r);
+    else trace_optic<FT, DR, 0>(op, k, dr, r);
+}
+
 }  // namespace xrt

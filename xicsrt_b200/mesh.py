@@ -383,8 +383,20 @@ def lookup_grids(points_xy, tri_simplices, cells_per_axis=None):
             items.append(np.flatnonzero(ok))
             cells.append((cy * nx + cx)[ok])
     tstart, titems = _cell_lists(nx, ny, (np.concatenate(items), np.concatenate(cells)))
+    # vertices of the 3 x 3 block of cells around each cell, cell-ordered: the nearest-vertex query reads one
+    # contiguous list instead of walking nine cells
+    items, cells = [], []
+    vcx, vcy = vc[:, 0], vc[:, 1]
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            cx, cy = vcx + dx, vcy + dy                  # the cell (cx, cy) has this vertex in its neighbourhood
+            ok = (cx >= 0) & (cx < nx) & (cy >= 0) & (cy < ny)
+            items.append(np.flatnonzero(ok))
+            cells.append((cy * nx + cx)[ok])
+    nstart, nitems = _cell_lists(nx, ny, (np.concatenate(items), np.concatenate(cells)))
     return {'nx': nx, 'ny': ny, 'x0': float(lo[0]), 'y0': float(lo[1]), 'inv_dx': float(inv[0]), 'inv_dy': float(inv[1]),
-            'tri_start': tstart, 'tri_items': titems, 'vert_start': vstart, 'vert_items': vitems}
+            'tri_start': tstart, 'tri_items': titems, 'vert_start': vstart, 'vert_items': vitems,
+            'nb_start': nstart, 'nb_items': nitems}
 
 
 def face_geometry(points, faces):
@@ -438,6 +450,27 @@ def device_tables(param):
         xyz = np.zeros((len(t['grid']['vert_items']), 4))
         xyz[:, 0:3] = t['points'][t['grid']['vert_items']]
         t['grid']['vert_xyz'] = xyz
+        # 3 x 3 neighbourhood lists with the coordinates and the vertex index inline (32-byte records)
+        nb = np.zeros((len(t['grid']['nb_items']), 4))
+        nb[:, 0:3] = t['points'][t['grid']['nb_items']]
+        nb[:, 3] = t['grid']['nb_items']
+        t['grid']['nb_rec'] = nb
+        # triangle records per cell: barycentric transform (6) + triangle index inline (64-byte records)
+        if interp:
+            tr = np.zeros((len(t['grid']['tri_items']), 8))
+            tr[:, 0:6] = t['tri_transform'].reshape(-1, 6)[t['grid']['tri_items']]
+            tr[:, 6] = t['grid']['tri_items']
+            t['grid']['tri_rec'] = tr
+    if refine:
+        # the <= 8 candidate faces of every vertex as consecutive 128-byte records (area < 0: no face), so that the
+        # candidate loop needs no index hop and can fetch the next record while it tests the current one
+        vf = t['vertex_faces']
+        rec8 = np.zeros((len(vf), 8, 16))
+        rec8[:, :, 12] = -1.0
+        ok = vf >= 0
+        rec8[ok] = t['face_rec'][vf[ok]]
+        rec8[:, :, 13] = vf
+        t['vertex_face_rec'] = rec8
     return t
 
 
@@ -478,5 +511,11 @@ def fill_mesh(param, keep):
         m.vgrid_start = keep.arr(g['vert_start'], np.int32, C.c_int32)
         m.vgrid_items = keep.arr(g['vert_items'], np.int32, C.c_int32)
         m.vgrid_xyz = keep.f64(g['vert_xyz'])
+        m.nb_start = keep.arr(g['nb_start'], np.int32, C.c_int32)
+        m.nb_rec = keep.f64(g['nb_rec'])
+        if 'tri_rec' in g:
+            m.tri_rec = keep.f64(g['tri_rec'])
+    if 'vertex_face_rec' in t:
+        m.vertex_face_rec = keep.f64(t['vertex_face_rec'])
     keep.obj(m)
     return C.pointer(m), flags
