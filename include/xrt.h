@@ -61,7 +61,9 @@ enum { XRT_F_TRACE_LOCAL = 1 << 0, XRT_F_CHECK_SIZE = 1 << 1,
        XRT_F_CONVEX = 1 << 4, XRT_F_HAS_XSIZE = 1 << 5, XRT_F_HAS_YSIZE = 1 << 6,
        XRT_F_HAS_ZSIZE = 1 << 7, XRT_F_IMAGE = 1 << 8,
        XRT_F_MOSAIC_CUTOFF = 1 << 9, XRT_F_MESH_REFINE = 1 << 10,
-       XRT_F_MESH_INTERP = 1 << 11 };
+       XRT_F_MESH_INTERP = 1 << 11,
+       XRT_F_MESH_LOSSLESS = 1 << 12 };  /* refining mesh: find the fine face by the full test (through the face grid)
+                                            instead of the reference's lossy coarse -> nearest-vertex pre-selection */
 
 /* aperture shapes and logic: xicsrt/tools/xicsrt_aperture.py:13-204 */
 enum { XRT_AP_NONE = 0, XRT_AP_CIRCLE = 1, XRT_AP_SQUARE = 2, XRT_AP_RECTANGLE = 3,
@@ -131,6 +133,12 @@ typedef struct XrtMesh {
     const double *tri_rec;       /* [grid_items][8]: barycentric transform (6), triangle index, pad      */
     const double *vertex_face_rec; /* [n_points][8][16]: face_rec of the faces around each vertex, [12] < 0 = no face,
                                       [13] = face index                                                  */
+    /* uniform xy grid of the FINE faces (un-refined meshes with many faces, and XRT_F_MESH_LOSSLESS): a ray is tested
+       against the faces of the cells its xy track crosses inside [z_min, z_max] only; NULL = test every face      */
+    int32_t fgrid_nx, fgrid_ny;
+    double fgrid_x0, fgrid_y0, fgrid_inv_dx, fgrid_inv_dy, fgrid_z_min, fgrid_z_max;
+    const int32_t *fgrid_start;  /* [fgrid_nx*fgrid_ny + 1]                                               */
+    const int32_t *fgrid_items;  /* face ids, ascending inside a cell                                     */
 } XrtMesh;
 
 typedef struct XrtOpticDesc {
@@ -298,6 +306,11 @@ typedef struct XrtOutputs {
     uint64_t *lost_count;    /* [1]                                                              */
     uint64_t lost_capacity;
     uint64_t lost_threshold; /* keep a lost ray when its key < threshold (2^64-1 = keep all)     */
+    /* the same selections as bitmaps indexed by ray id - bits_begin (caller-zeroed, one bit per ray of the launch):
+       no list capacity to guess, and xrt_bits_to_ids returns the ids in ascending (= the reference's ray) order  */
+    uint32_t *found_bits;    /* optional: bit set for every ray alive after the last optic       */
+    uint32_t *lost_bits;     /* optional: bit set for every lost ray whose key < lost_threshold  */
+    uint64_t bits_begin;
 } XrtOutputs;
 
 /* per-element history, struct-of-arrays: 7 double planes + 1 byte plane per element
@@ -400,6 +413,18 @@ int xrt_bundle_voigt_tables(const XrtBundle *table_dev, const int64_t *counts_de
 
 /* Attach per-bundle wavelength tables to a plasma scene (after xrt_scene_set_bundles). */
 int xrt_scene_set_bundle_tables(XrtScene *scene, const double *x_dev, const double *cdf_dev, int32_t n_table);
+
+/* Ascending list of the ray ids whose bit is set in a bitmap written by xrt_trace (found_bits / lost_bits):
+   ids_dev[k] = id_begin + index of the k-th set bit; *count_dev = number of set bits (may exceed capacity).
+   Count / scan / emit kernels, no sort. */
+int xrt_bits_to_ids(const uint32_t *bits_dev, uint64_t n_bits, uint64_t id_begin, uint64_t *ids_dev,
+                    uint64_t capacity, uint64_t *count_dev, void *stream);
+
+/* The lost sample of the reference (`_sort_raytrace`, xicsrt_raytrace.py:262-266: a shuffle, then the first
+   max_lost): of the n candidate ids, the m with the smallest Philox sampling keys of (seed, stream_id) -- a
+   uniform random subset -- written to out_dev in ascending id order; *count_dev = min(m, n). */
+int xrt_lost_select(uint64_t seed, uint64_t stream_id, const uint64_t *ids_dev, uint64_t n, uint64_t m,
+                    uint64_t *out_dev, uint64_t *count_dev, void *stream);
 
 /* FP64 FMA-chain microbenchmark: runs `iters` dependent-chain DFMA steps per thread on a
    full grid and reports the number of FP64 flops issued; the caller times it with CUDA

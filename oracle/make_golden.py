@@ -121,9 +121,13 @@ def make(scene_name):
     return path, sum(v.nbytes for v in out.values())
 
 
+# scenes that use product-only options (the reference does not know the keys): no fixture
+NO_REFERENCE = ('mesh_torus_lossless',)
+
+
 def main(argv):
     from oracle import scenes
-    todo = argv or scenes.names()
+    todo = argv or [n for n in scenes.names() if n not in NO_REFERENCE]
     for name in todo:
         path, raw = make(name)
         print(f'{name:28s} {os.path.getsize(path)/1e6:7.2f} MB on disk ({raw/1e6:6.2f} MB raw)')

@@ -89,7 +89,8 @@ def candidate_faces(mesh, O, D, alive, faces_idx, faces_mask):
 def intersect(param, O, D, alive):
     """ShapeMesh.intersect (:135-170).  Returns (X, normals, alive)."""
     mesh = param['mesh']
-    if not param['mesh_refine']:
+    if not param['mesh_refine'] or param.get('mesh_lossless'):
+        # mesh_lossless (product option, not in the reference): the full test on the fine mesh = mesh_refine off
         X, alive, hits = moeller_trumbore(mesh, O, D, alive.copy())
     else:
         Xc, alive_c, _ = moeller_trumbore(param['mesh_coarse'], O, D, alive.copy())

@@ -148,6 +148,10 @@ EXTRA = {
     'mesh_torus': mesh_torus,
     # config 4 of BASELINE.json at its stated size: 41 x 41 fine (1681 points / 3200 faces), 5 x 5 coarse
     'mesh_torus_41': lambda: mesh_torus(n=6000, seed=38, mesh_size=(41, 41)),
+    # the full Moeller-Trumbore test on 3200 fine faces (mesh_refine off): the face-grid path of the kernels
+    'mesh_torus_norefine': lambda: mesh_torus(n=5000, seed=39, mesh_size=(41, 41), mesh_refine=False),
+    # product option mesh_lossless: a refining mesh traced with the full test; same rays as the scene above
+    'mesh_torus_lossless': lambda: mesh_torus(n=5000, seed=39, mesh_size=(41, 41), mesh_lossless=True),
     'mesh_torus_convex': lambda: mesh_torus(seed=37, convex=[True, False], mesh_size=(15, 15)),
     'mesh_sphere': mesh_sphere,
     'mesh_cylinder': mesh_cylinder,

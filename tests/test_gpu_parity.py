@@ -75,6 +75,22 @@ def test_injected_trace_matches_reference_golden(torch, golden_dir, name):
             assert np.array_equal(images[elem], ref)
 
 
+def test_lossless_mesh_equals_the_unrefined_reference_run(torch, golden_dir):
+    """
+    mesh_lossless (product option): a refining mesh traced by the full Moeller-Trumbore test through the face grid.  Its
+    result is, ray for ray, what the unmodified reference gives for the same mesh with mesh_refine off (fixture
+    mesh_torus_norefine: same seed, same rays) -- and that fixture also pins the face-grid path of un-refined meshes.
+    """
+    gold = np.load(os.path.join(golden_dir, 'mesh_torus_norefine.npz'))
+    for name in ('mesh_torus_lossless', 'mesh_torus_norefine'):
+        single, hist, counts, images, layout = harness.oracle_and_cuda(torch, scenes.get(name))
+        for elem in layout.element_names:
+            ref = {k: gold[f'iter/{elem}/{k}'] for k in ('origin', 'direction', 'wavelength', 'mask')}
+            harness.assert_rays_close(hist[elem], ref, f'{name}/{elem} (golden, mesh_refine off)', RTOL)
+            assert counts[elem] == int(gold[f'iter_meta/{elem}'])
+        assert np.array_equal(images['detector'], gold['iter_image/detector'])
+
+
 def test_empty_and_all_dead_inputs(torch):
     """n = 0 is a no-op; rays that enter dead stay dead with NaN origins downstream."""
     cfg = scenes.get('sphere')

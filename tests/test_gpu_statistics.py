@@ -286,6 +286,67 @@ def test_two_kernel_path_equals_replay_kernel(torch, name, kind, monkeypatch):
     tracer.close()
 
 
+def test_lossless_mesh_recovers_the_rays_the_preselection_loses(torch):
+    """
+    N4 (reference _ShapeMesh.py:52-79, TODO:3-8): the coarse -> nearest-vertex pre-selection of
+    a refining mesh loses rays.  With mesh_lossless the mesh crystal finds (statistically) as many rays as the
+    analytic torus it samples; the reference's refinement finds fewer.
+    """
+    import xicsrt_b200
+    n = 2_000_000
+    counts = {}
+    for label, kw in (('analytic', None), ('refine', {}), ('lossless', {'mesh_lossless': True})):
+        cfg = scenes.get('mesh_torus_41') if kw is not None else scenes.get('torus_ff')
+        cfg['optics']['crystal'].update(kw or {})
+        if kw is None:      # the same footprint, bounds and detector as the mesh scene
+            mesh = scenes.get('mesh_torus_41')
+            cfg['optics']['detector'] = mesh['optics']['detector']
+        cfg['sources']['source']['intensity'] = n
+        cfg['general'].update({'keep_history': False, 'random_seed': 5})
+        res = xicsrt_b200.raytrace(cfg)
+        counts[label] = res['total']['meta']['crystal']['num_out']
+    lost = counts['analytic'] - counts['refine']
+    assert lost > 0.005 * counts['analytic'], counts                      # the pre-selection does lose rays (~1-3 %)
+    assert abs(counts['lossless'] - counts['analytic']) < 0.25 * lost, counts
+
+
+def test_selection_kernels_against_numpy(torch):
+    """xrt_bits_to_ids (count / scan / emit) and xrt_lost_select (radix select of the smallest sampling keys)."""
+    import ctypes as C
+    from xicsrt_b200 import _lib as L
+    lib = L.load()
+    dev = torch.device('cuda', 0)
+    rng = np.random.default_rng(9)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    for n_bits, density in ((1, 1.0), (31, 0.5), (65536 * 3 + 17, 0.013), (5_000_003, 0.3), (70_000, 0.0)):
+        flags = rng.random(n_bits) < density
+        words = np.zeros((n_bits + 31) // 32, dtype=np.uint32)
+        idx = np.flatnonzero(flags)
+        np.bitwise_or.at(words, idx // 32, (np.uint32(1) << (idx % 32).astype(np.uint32)))
+        bits = torch.from_numpy(words.view(np.int32)).to(dev)
+        out = torch.full((max(len(idx), 1),), -1, dtype=torch.int64, device=dev)
+        base = (1 << 35) + 7
+        L.check(lib.xrt_bits_to_ids(bits.data_ptr(), n_bits, base, out.data_ptr(), len(idx), cnt.data_ptr(), None))
+        assert int(cnt.cpu()[0]) == len(idx)
+        assert np.array_equal(out.cpu().numpy()[:len(idx)], idx + base)
+    # lost sample: m smallest keys, ascending ids, nested for growing m, everything when m >= n
+    ids = torch.from_numpy(np.sort(rng.choice(10**9, 30000, replace=False)).astype(np.int64)).to(dev)
+    picks = {}
+    for m in (1, 100, 5000, 29999, 30000, 40000):
+        out = torch.full((max(min(m, 30000), 1),), -1, dtype=torch.int64, device=dev)
+        L.check(lib.xrt_lost_select(12345, 3, ids.data_ptr(), 30000, m, out.data_ptr(), cnt.data_ptr(), None))
+        k = int(cnt.cpu()[0])
+        assert k == min(m, 30000)
+        got = out.cpu().numpy()[:k]
+        assert np.all(np.diff(got) > 0) and np.isin(got, ids.cpu().numpy()).all()
+        picks[m] = set(got.tolist())
+    assert picks[1] < picks[100] < picks[5000] < picks[29999] < picks[30000] == picks[40000]
+    # a different stream draws a different sample
+    out = torch.empty(100, dtype=torch.int64, device=dev)
+    L.check(lib.xrt_lost_select(12345, 4, ids.data_ptr(), 30000, 100, out.data_ptr(), cnt.data_ptr(), None))
+    assert set(out.cpu().numpy().tolist()) != picks[100]
+
+
 def _long_train(n_apertures):
     """n pass-through apertures in front of the crystal: the split optic moves down the train."""
     cfg = scenes.get('sphere')

@@ -151,11 +151,14 @@ class Tracer:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _outputs(self, keep_images, found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False, packed=None):
+    def _outputs(self, keep_images, found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False, packed=None, bitmaps=None):
         packed = self.packed if packed is None else packed
         out = L.XrtOutputs()
         out.counts = packed.data_ptr()
         out.images = packed.data_ptr() + 8 * self.n_elem if (keep_images and self.layout.n_pixels) else None
+        if bitmaps is not None:
+            out.found_bits, out.lost_bits, out.bits_begin = bitmaps
+            out.lost_threshold = lost_threshold
         if want_lists:
             torch = self.torch
             if self.found_ids is None or self.found_ids.numel() < found_cap:
@@ -174,7 +177,7 @@ class Tracer:
         return out
 
     def trace(self, stream_id, keep_images=True, ray_begin=None, ray_count=None, zero=True,
-              found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False, packed=None):
+              found_cap=0, lost_cap=0, lost_threshold=0, want_lists=False, packed=None, bitmaps=None):
         """
         Enqueue one fused generate->trace->bin launch for this rank's ray range (asynchronous).  ``packed`` = another
         [counts | images] buffer of the same shape to accumulate into (double buffering against an all-reduce in flight).
@@ -184,7 +187,7 @@ class Tracer:
         if zero:
             (self.packed if packed is None else packed).zero_()
             self.scalars.zero_()
-        out = self._outputs(keep_images, found_cap, lost_cap, lost_threshold, want_lists, packed)
+        out = self._outputs(keep_images, found_cap, lost_cap, lost_threshold, want_lists, packed, bitmaps)
         with self.torch.cuda.device(self.device):
             L.check(self.lib.xrt_trace(self.scene.handle, self.seed, int(stream_id), int(ray_begin), int(ray_count),
                                        C.byref(out), self._stream()))
@@ -239,38 +242,53 @@ class Tracer:
 
     def select_ids(self, stream_id, max_lost, keep_images=True):
         """
-        One launch that also compacts found ids and a random sample of lost ids.
-        Returns (found_ids sorted, lost_ids) as int64 device tensors; the lost sample is the
-        ``max_lost`` rays with the smallest Philox keys, i.e. a uniform random subset in random
-        order, as ``_sort_raytrace`` draws with a shuffle (xicsrt_raytrace.py:262-266).
+        One launch that also marks the found rays and the candidates of the lost sample in two bitmaps indexed by
+        ray id; the library's count / scan / emit kernels turn them into id lists (``xrt_bits_to_ids``) and
+        ``xrt_lost_select`` picks the ``max_lost`` candidates with the smallest Philox keys.  Returns
+        (found_ids, lost_ids) as int64 device tensors, both in ascending id order: the found rays are in the
+        reference's ray order, the lost sample is a uniform random subset as ``_sort_raytrace`` draws with a shuffle
+        (xicsrt_raytrace.py:262-266).  A second launch happens only when the candidate sample turns out too small
+        (almost every ray found).
         """
         torch = self.torch
         begin, count = shard_range(self.n_rays, self.rank, self.world)
-        found_cap = min(count, max(1 << 20, count // 16))
+        n_words = (count + 31) // 32
+        if getattr(self, 'bits', None) is None or self.bits.numel() < 2 * n_words:
+            self.bits = torch.empty(max(2 * n_words, 2), dtype=torch.int32, device=self.device)
+        bits = self.bits[:2 * n_words]
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
         want = 2 * max_lost + 10 * int(np.sqrt(max_lost)) + 64
         prob = min(1.0, want / max(count, 1))
+
+        def ids_of(ptr, capacity):
+            buf = torch.empty(max(capacity, 1), dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                L.check(self.lib.xrt_bits_to_ids(ptr, count, begin, buf.data_ptr(), capacity, cnt.data_ptr(), self._stream()))
+            return buf, int(cnt.cpu()[0])
+
         while True:
             thr = U64_MAX if prob >= 1.0 else int(prob * float(1 << 64))
-            lost_cap = min(count, int(prob * count * 1.5) + 4096)
-            self.trace(stream_id, keep_images, begin, count, True, found_cap, lost_cap, thr, True)
-            n_found, n_kept = (int(v) for v in self.scalars.cpu().numpy())
+            bits.zero_()
+            self.trace(stream_id, keep_images, begin, count, True, lost_threshold=thr,
+                       bitmaps=(bits.data_ptr(), bits.data_ptr() + 4 * n_words, begin))
+            n_found = int(self.packed[self.n_elem - 1].cpu())
             n_lost = count - n_found
-            if n_found > found_cap:
-                found_cap = n_found
-                continue
-            if n_kept > lost_cap:
-                lost_cap = n_kept
-                continue
-            if n_kept < min(max_lost, n_lost) and prob < 1.0:
-                prob = min(1.0, 4.0 * prob * max(1.0, min(max_lost, n_lost) / max(n_kept, 1)))
+            cap = min(n_lost, int(prob * count * 1.5) + 4096)
+            cand, n_cand = ids_of(bits.data_ptr() + 4 * n_words, cap)
+            if n_cand > cap:
+                cand, n_cand = ids_of(bits.data_ptr() + 4 * n_words, n_cand)
+            if n_cand < min(max_lost, n_lost) and prob < 1.0:
+                prob = min(1.0, 4.0 * prob * max(1.0, min(max_lost, n_lost) / max(n_cand, 1)))
                 continue
             break
-        found = torch.sort(self.found_ids[:n_found]).values
-        keys = self.lost_keys[:n_kept]
-        # keys are unsigned 64-bit stored in int64: flip the sign bit to sort as unsigned
-        order = torch.argsort(keys ^ torch.tensor(-(1 << 63), dtype=torch.int64, device=self.device))
-        lost = self.lost_ids[:n_kept][order[:max_lost]]
-        return found, lost
+        found, n_f = ids_of(bits.data_ptr(), n_found)
+        assert n_f == n_found, (n_f, n_found)
+        m = min(max_lost, n_cand)
+        lost = torch.empty(max(m, 1), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.xrt_lost_select(self.seed, int(stream_id), cand.data_ptr(), n_cand, m, lost.data_ptr(),
+                                             cnt.data_ptr(), self._stream()))
+        return found[:n_found], lost[:m]
 
     def close(self):
         self.scene.close()

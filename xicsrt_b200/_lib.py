@@ -22,6 +22,7 @@ ROCK = {'step': 0, 'gauss': 1, 'table': 2}
 F_TRACE_LOCAL, F_CHECK_SIZE, F_CHECK_APERTURE, F_CHECK_BRAGG = 1 << 0, 1 << 1, 1 << 2, 1 << 3
 F_CONVEX, F_HAS_XSIZE, F_HAS_YSIZE, F_HAS_ZSIZE = 1 << 4, 1 << 5, 1 << 6, 1 << 7
 F_IMAGE, F_MOSAIC_CUTOFF, F_MESH_REFINE, F_MESH_INTERP = 1 << 8, 1 << 9, 1 << 10, 1 << 11
+F_MESH_LOSSLESS = 1 << 12
 AP_SHAPE = {'none': 0, 'circle': 1, 'square': 2, 'rectangle': 3, 'ellipse': 4, 'triangle': 5}
 AP_LOGIC = {'and': 0, 'not': 1, 'or': 2, 'nand': 3, 'nor': 4, 'xor': 5, 'xnor': 6}
 SRC_FIXED_AXIS, SRC_FOCUSED, SRC_BUNDLES = 0, 1, 2
@@ -53,7 +54,11 @@ class XrtMesh(C.Structure):
                 ('grid_inv_dx', C.c_double), ('grid_inv_dy', C.c_double),
                 ('grid_start', _pi32), ('grid_items', _pi32),
                 ('vgrid_start', _pi32), ('vgrid_items', _pi32), ('vgrid_xyz', _pd),
-                ('nb_start', _pi32), ('nb_rec', _pd), ('tri_rec', _pd), ('vertex_face_rec', _pd)]
+                ('nb_start', _pi32), ('nb_rec', _pd), ('tri_rec', _pd), ('vertex_face_rec', _pd),
+                ('fgrid_nx', C.c_int32), ('fgrid_ny', C.c_int32),
+                ('fgrid_x0', C.c_double), ('fgrid_y0', C.c_double), ('fgrid_inv_dx', C.c_double), ('fgrid_inv_dy', C.c_double),
+                ('fgrid_z_min', C.c_double), ('fgrid_z_max', C.c_double),
+                ('fgrid_start', _pi32), ('fgrid_items', _pi32)]
 
 
 class XrtOpticDesc(C.Structure):
@@ -125,7 +130,8 @@ class XrtOutputs(C.Structure):
     _fields_ = [('counts', C.c_void_p), ('images', C.c_void_p),
                 ('found_ids', C.c_void_p), ('found_count', C.c_void_p), ('found_capacity', C.c_uint64),
                 ('lost_ids', C.c_void_p), ('lost_keys', C.c_void_p), ('lost_count', C.c_void_p),
-                ('lost_capacity', C.c_uint64), ('lost_threshold', C.c_uint64)]
+                ('lost_capacity', C.c_uint64), ('lost_threshold', C.c_uint64),
+                ('found_bits', C.c_void_p), ('lost_bits', C.c_void_p), ('bits_begin', C.c_uint64)]
 
 
 class XrtHistory(C.Structure):
@@ -173,6 +179,8 @@ SYMBOLS = {
     'xrt_scene_set_bundles': (C.c_int, [_vp, _vp, _vp, _u64, _u64]),
     'xrt_bundle_voigt_tables': (C.c_int, [_vp, _vp, _u64, C.c_double, C.c_int32, _vp, _vp, _vp]),
     'xrt_scene_set_bundle_tables': (C.c_int, [_vp, _vp, _vp, C.c_int32]),
+    'xrt_bits_to_ids': (C.c_int, [_vp, _u64, _u64, _vp, _u64, _vp, _vp]),
+    'xrt_lost_select': (C.c_int, [_u64, _u64, _vp, _u64, _u64, _vp, _vp, _vp]),
     'xrt_fp64_burn': (C.c_int, [_u64, _vp, C.POINTER(C.c_double), _vp]),
     'xrt_launch_info': (C.c_int, [_vp, _pi32, _pi32, _pi32, _pi32]),
     'xrt_launch_info_cull': (C.c_int, [_vp, _pi32, _pi32, _pi32, _pi32]),

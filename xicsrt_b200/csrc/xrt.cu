@@ -12,6 +12,7 @@
 
 #include "xrt_variants.h"
 #include "xrt_plasma.cuh"
+#include "xrt_select.cuh"
 
 namespace xrt {
 
@@ -149,6 +150,14 @@ static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
     UP(m.nb_rec, (cells && m.nb_start) ? 4 * (size_t)n_nb : 0);
     UP(m.tri_rec, (cells && m.grid_start && m.tri_rec) ? 8 * (size_t)n_items : 0);
     UP(m.vertex_face_rec, m.vertex_face_rec ? 128 * (size_t)m.n_points : 0);
+    {
+        const size_t fcells = (size_t)m.fgrid_nx * (size_t)m.fgrid_ny;
+        const bool have = fcells > 0 && m.fgrid_start && m.fgrid_items;
+        const int32_t n_f = have ? m.fgrid_start[fcells] : 0;
+        if (!have) { m.fgrid_start = nullptr; m.fgrid_items = nullptr; m.fgrid_nx = m.fgrid_ny = 0; }
+        UP(m.fgrid_start, have ? fcells + 1 : 0);
+        UP(m.fgrid_items, n_f);
+    }
     const XrtMesh *d = nullptr;
     int rc = upload(s, &m, 1, &d);
     if (rc != XRT_OK) return rc;
@@ -565,7 +574,8 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
         return fail(XRT_EINVAL, "plasma scene without a bundle table: call xrt_scene_set_bundles first");
     if (s->dev.source.kind == XRT_SRC_BUNDLES && s->dev.source.wave == XRT_WAVE_TABLE && !s->dev.source.bundle_cdf)
         return fail(XRT_EINVAL, "plasma scene with a natural linewidth: call xrt_scene_set_bundle_tables first");
-    const bool hist = out->found_count != nullptr || out->lost_count != nullptr;
+    const bool hist = out->found_count != nullptr || out->lost_count != nullptr || out->found_bits != nullptr ||
+                      out->lost_bits != nullptr;
     TraceKernel kern;
     size_t smem;
     int bps = 0;
@@ -822,6 +832,49 @@ extern "C" int xrt_bundles_generate(const XrtPlasmaDesc *desc, uint64_t seed, ui
     k_bundles<<<grid, 256, 0, (cudaStream_t)stream>>>(*desc, seed, stream_id, n_bundles, table_dev, intensity_dev,
                                                      (long long *)counts_dev);
     CU(cudaGetLastError());
+    return XRT_OK;
+}
+
+extern "C" int xrt_bits_to_ids(const uint32_t *bits_dev, uint64_t n_bits, uint64_t id_begin, uint64_t *ids_dev,
+                               uint64_t capacity, uint64_t *count_dev, void *stream) {
+    if (!bits_dev || (!ids_dev && capacity) || !count_dev) return fail(XRT_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_bits == 0) {
+        CU(cudaMemsetAsync(count_dev, 0, sizeof(uint64_t), st));
+        return XRT_OK;
+    }
+    const uint64_t n_words = (n_bits + 31) / 32;
+    const uint64_t n_blocks = (n_words + kSelWordsPerBlock - 1) / kSelWordsPerBlock;
+    if (n_blocks > 0x7fffffffull) return fail(XRT_EINVAL, "bitmap too large");
+    void *scratch = nullptr;
+    CU(cudaMallocAsync(&scratch, n_blocks * (sizeof(uint32_t) + sizeof(unsigned long long)) + 16, st));
+    unsigned long long *offsets = (unsigned long long *)scratch;
+    uint32_t *sums = (uint32_t *)(offsets + n_blocks);
+    k_bits_count<<<(unsigned)n_blocks, kSelBlock, 0, st>>>(bits_dev, n_words, sums);
+    k_bits_scan<<<1, 1024, 0, st>>>(sums, (uint32_t)n_blocks, offsets, (unsigned long long *)count_dev);
+    k_bits_emit<<<(unsigned)n_blocks, kSelBlock, 0, st>>>(bits_dev, n_words, id_begin, offsets, ids_dev, capacity);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(scratch, st));
+    return XRT_OK;
+}
+
+extern "C" int xrt_lost_select(uint64_t seed, uint64_t stream_id, const uint64_t *ids_dev, uint64_t n, uint64_t m,
+                               uint64_t *out_dev, uint64_t *count_dev, void *stream) {
+    if (!count_dev || (n && (!ids_dev || !out_dev))) return fail(XRT_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0 || m == 0) {
+        CU(cudaMemsetAsync(count_dev, 0, sizeof(uint64_t), st));
+        return XRT_OK;
+    }
+    void *keys = nullptr;
+    CU(cudaMallocAsync(&keys, n * sizeof(uint64_t), st));
+    PhiloxKeys pk;
+    philox_round_keys(seed, stream_id, pk);
+    const uint64_t want = (n + 255) / 256;
+    k_lost_keys<<<(unsigned)(want < 4096 ? want : 4096), 256, 0, st>>>(pk, stream_id, ids_dev, n, (uint64_t *)keys);
+    k_select_smallest<<<1, 1024, 0, st>>>(ids_dev, (const uint64_t *)keys, n, m, out_dev, (unsigned long long *)count_dev);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(keys, st));
     return XRT_OK;
 }
 

@@ -198,6 +198,10 @@ __device__ __forceinline__ void add_pixel(const XrtOutputs &out, const XrtOpticD
 template <bool HIST>
 __device__ __forceinline__ void emit_found(const XrtOutputs &out, unsigned lane, unsigned lt_mask, bool found, uint64_t id) {
     if constexpr (!HIST) return;
+    if (out.found_bits && found) {
+        const uint64_t b = id - out.bits_begin;
+        atomicOr(out.found_bits + (b >> 5), 1u << (b & 31u));
+    }
     if (!out.found_count) return;
     unsigned m = __ballot_sync(kFull, found);
     if (!m) return;
@@ -215,13 +219,18 @@ template <bool HIST>
 __device__ __forceinline__ void emit_lost(const XrtOutputs &out, unsigned lane, unsigned lt_mask, const PhiloxDraws &dr,
                                           bool lost, uint64_t id) {
     if constexpr (!HIST) return;
-    if (!out.lost_count) return;
+    if (!out.lost_count && !out.lost_bits) return;
     bool keep = false;
     uint64_t key = 0;
     if (lost) {
         key = dr.lost_key();
         keep = key < out.lost_threshold;
     }
+    if (out.lost_bits && keep) {
+        const uint64_t b = id - out.bits_begin;
+        atomicOr(out.lost_bits + (b >> 5), 1u << (b & 31u));
+    }
+    if (!out.lost_count) return;
     unsigned m = __ballot_sync(kFull, keep);
     if (!m) return;
     unsigned long long off = 0;
@@ -617,7 +626,8 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
     bool mesh_staged = false, mesh_point = false;
     if constexpr ((FT & FT_MESH) != 0) {
         if constexpr (!SPECTRO) {
-            mesh_staged = split == 0 && ops.shape == XRT_SHAPE_MESH && (ops.flags & XRT_F_MESH_REFINE) && lazy &&
+            mesh_staged = split == 0 && ops.shape == XRT_SHAPE_MESH && (ops.flags & XRT_F_MESH_REFINE) &&
+                          !(ops.flags & XRT_F_MESH_LOSSLESS) && lazy &&
                           sc.source.kind != XRT_SRC_BUNDLES && sc.source.cone != XRT_CONE_ISOTROPIC_XY;
         }
         if (ops.shape == XRT_SHAPE_MESH) {
@@ -737,7 +747,7 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             for (int j = 0; j < kUnroll; ++j) {
                 if (count_src) n_src += __popc(__ballot_sync(kFull, validv[j]));
                 if constexpr (HIST) {
-                    if (out.lost_count) {
+                    if (out.lost_count || out.lost_bits) {
                         PhiloxDraws dr;
                         dr.init(pk, stream_id, idv[j], split);
                         emit_lost<HIST>(out, c.lane, c.lt_mask, dr, validv[j] && !candv[j], idv[j]);
@@ -1051,7 +1061,7 @@ __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceD
 #pragma unroll
     for (int j = 0; j < U; ++j) {
         if constexpr (HIST) {
-            if (out.lost_count) {
+            if (out.lost_count || out.lost_bits) {
                 PhiloxDraws dr;
                 dr.init(pk, stream_id, id_first + off[j], 0);
                 emit_lost<true>(out, lane, lt_mask, dr, valid[j] && !pass[j], id_first + off[j]);

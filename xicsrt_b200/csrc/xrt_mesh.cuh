@@ -139,6 +139,71 @@ __device__ __forceinline__ int mesh_all_faces_point(const double *__restrict__ n
     return hit;
 }
 
+// step 1 through the face grid (un-refined meshes with many faces, XRT_F_MESH_LOSSLESS): the reference's loop tests
+// every face and the last one hit wins.  A hit point lies on its face, i.e. inside the mesh's z range and inside the xy
+// bounding box of that face, so only the faces registered in the cells that the ray's xy track crosses while it is
+// inside [z_min, z_max] can be hit; they are tested with the same arithmetic and the highest face index among the hits
+// wins -- the result of the full loop.  Rays nearly parallel to the xy plane, whose track covers more than 16 cells, take
+// the full loop.
+__device__ __forceinline__ bool mesh_test_face_mt(const double *__restrict__ g, V3 o, V3 d, V3 &X) {
+    const double eps = 1e-15;
+    V3 p0, e1, e2;
+    mesh_face_operands<false>(g, p0, e1, e2);
+    const V3 h = cross(d, e2);
+    const double a = dot(e1, h);
+    if (a > -eps && a < eps) return false;
+    const double inv = 1.0 / a;
+    const V3 s = o - p0;
+    const double u = inv * dot(s, h);
+    if (u < 0.0 || u > 1.0) return false;
+    const V3 q = cross(s, e1);
+    const double v = inv * dot(d, q);
+    if (v < 0.0 || u + v > 1.0) return false;
+    const double t = inv * dot(e2, q);
+    X = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    return true;
+}
+
+__device__ __forceinline__ int mesh_grid_faces(const XrtMesh &m, V3 o, V3 d, V3 &X) {
+    // parameter range of the ray inside the z slab
+    double t0 = (m.fgrid_z_min - o.z) / d.z, t1 = (m.fgrid_z_max - o.z) / d.z;
+    bool wide = !(d.z != 0.0) || !(t0 == t0) || !(t1 == t1) || isinf(t0) || isinf(t1);
+    int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0;
+    if (!wide) {
+        const double xa = fma(t0, d.x, o.x), xb = fma(t1, d.x, o.x), ya = fma(t0, d.y, o.y), yb = fma(t1, d.y, o.y);
+        const double dx = 1.0 / m.fgrid_inv_dx, dy = 1.0 / m.fgrid_inv_dy;
+        // one cell of slack on each side: rounding of the slab end points, faces registered with a padded box
+        const double fx0 = floor((fmin(xa, xb) - m.fgrid_x0) * m.fgrid_inv_dx - 1e-6), fx1 = floor((fmax(xa, xb) - m.fgrid_x0) * m.fgrid_inv_dx + 1e-6);
+        const double fy0 = floor((fmin(ya, yb) - m.fgrid_y0) * m.fgrid_inv_dy - 1e-6), fy1 = floor((fmax(ya, yb) - m.fgrid_y0) * m.fgrid_inv_dy + 1e-6);
+        (void)dx; (void)dy;
+        if (fx1 < 0.0 || fy1 < 0.0 || fx0 >= (double)m.fgrid_nx || fy0 >= (double)m.fgrid_ny) return -1;   // track misses the footprint
+        cx0 = (int)fmax(fx0, 0.0); cx1 = (int)fmin(fx1, (double)(m.fgrid_nx - 1));
+        cy0 = (int)fmax(fy0, 0.0); cy1 = (int)fmin(fy1, (double)(m.fgrid_ny - 1));
+        wide = (cx1 - cx0 + 1) * (cy1 - cy0 + 1) > 16;
+    }
+    int hit = -1;
+    if (wide) {
+        for (int f = 0; f < m.n_faces; ++f) {
+            V3 P;
+            if (mesh_test_face_mt(m.face_geom + 9 * (size_t)f, o, d, P)) { hit = f; X = P; }
+        }
+        return hit;
+    }
+    for (int cy = cy0; cy <= cy1; ++cy) {
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            const int c = cy * m.fgrid_nx + cx;
+            const int b = __ldg(m.fgrid_start + c), e = __ldg(m.fgrid_start + c + 1);
+            for (int k = b; k < e; ++k) {
+                const int f = __ldg(m.fgrid_items + k);
+                if (f <= hit) continue;          // a lower face cannot win; also skips faces met in an earlier cell
+                V3 P;
+                if (mesh_test_face_mt(m.face_geom + 9 * (size_t)f, o, d, P)) { hit = f; X = P; }
+            }
+        }
+    }
+    return hit;
+}
+
 // step 2: exact nearest vertex through the uniform xy grid -- rings of cells around the query
 // cell until no unvisited cell can hold a closer vertex (the xy distance to the ring bounds
 // the 3-D distance from below).
@@ -347,8 +412,10 @@ static __device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o,
     const double *geom;
     const int n1 = mesh_stage1_faces(op, geom);
     int face;
-    if (!(op.flags & XRT_F_MESH_REFINE)) {
-        face = staged ? mesh_all_faces<true>(staged, n1, o, d, X) : mesh_all_faces<false>(geom, n1, o, d, X);
+    if (!(op.flags & XRT_F_MESH_REFINE) || (op.flags & XRT_F_MESH_LOSSLESS)) {
+        if (m.fgrid_start) face = mesh_grid_faces(m, o, d, X);
+        else if (op.flags & XRT_F_MESH_REFINE) face = mesh_all_faces<false>(m.face_geom, m.n_faces, o, d, X);
+        else face = staged ? mesh_all_faces<true>(staged, n1, o, d, X) : mesh_all_faces<false>(geom, n1, o, d, X);
     } else {
         V3 Xc = nan3();
         if (resume_Xc) {        // coarse step already done (mesh_coarse_hit): a coarse face was hit at *resume_Xc

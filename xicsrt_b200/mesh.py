@@ -399,6 +399,44 @@ def lookup_grids(points_xy, tri_simplices, cells_per_axis=None):
             'nb_start': nstart, 'nb_items': nitems}
 
 
+def face_grid(points, faces, cells_per_axis=None):
+    """
+    Uniform xy grid over the mesh footprint with, per cell, the faces whose (slightly grown) xy bounding box touches the
+    cell, plus the z range of the mesh: a ray can only hit a face inside the cells its xy track crosses while it is
+    within that z range, so the full Moeller-Trumbore loop over every face (_ShapeMesh.py:289-348) can be restricted
+    to those lists without changing its result.
+    """
+    pts = np.asarray(points, dtype=np.float64)
+    faces = np.asarray(faces)
+    lo, hi = pts[:, 0:2].min(axis=0), pts[:, 0:2].max(axis=0)
+    if cells_per_axis is None:
+        cells_per_axis = int(np.clip(np.sqrt(len(faces) / 2.0), 2, 1024))
+    nx = ny = cells_per_axis
+    span = np.maximum(hi - lo, 1e-300)
+    inv = np.array([nx, ny]) / span
+
+    def cell_xy(xy):
+        c = np.floor((xy - lo) * inv).astype(np.int64)
+        c[:, 0] = np.clip(c[:, 0], 0, nx - 1)
+        c[:, 1] = np.clip(c[:, 1], 0, ny - 1)
+        return c
+    fp = pts[faces][:, :, 0:2]
+    pad = 1e-9 * span
+    c_lo, c_hi = cell_xy(fp.min(axis=1) - pad), cell_xy(fp.max(axis=1) + pad)
+    items, cells = [], []
+    wmax = int((c_hi - c_lo).max()) + 1
+    for dx in range(wmax):
+        for dy in range(wmax):
+            cx, cy = c_lo[:, 0] + dx, c_lo[:, 1] + dy
+            ok = (cx <= c_hi[:, 0]) & (cy <= c_hi[:, 1])
+            items.append(np.flatnonzero(ok))
+            cells.append((cy * nx + cx)[ok])
+    start, fitems = _cell_lists(nx, ny, (np.concatenate(items), np.concatenate(cells)))
+    zpad = 1e-9 * max(float(pts[:, 2].max() - pts[:, 2].min()), float(span.max()))
+    return {'nx': nx, 'ny': ny, 'x0': float(lo[0]), 'y0': float(lo[1]), 'inv_dx': float(inv[0]), 'inv_dy': float(inv[1]),
+            'start': start, 'items': fitems, 'z_min': float(pts[:, 2].min() - zpad), 'z_max': float(pts[:, 2].max() + zpad)}
+
+
 def face_geometry(points, faces):
     """Moeller-Trumbore operands per face: p0, p1 - p0, p2 - p0 (_ShapeMesh.py:301-316)."""
     p0, p1, p2 = points[faces[:, 0]], points[faces[:, 1]], points[faces[:, 2]]
@@ -461,6 +499,10 @@ def device_tables(param):
             tr[:, 0:6] = t['tri_transform'].reshape(-1, 6)[t['grid']['tri_items']]
             tr[:, 6] = t['grid']['tri_items']
             t['grid']['tri_rec'] = tr
+    lossless = bool(param.get('mesh_lossless'))
+    if (not refine or lossless) and len(t['faces']) > 64:
+        t['face_grid'] = face_grid(t['points'], t['faces'])
+    t['lossless'] = lossless
     if refine:
         # the <= 8 candidate faces of every vertex as consecutive 128-byte records (area < 0: no face), so that the
         # candidate loop needs no index hop and can fetch the next record while it tests the current one
@@ -491,6 +533,15 @@ def fill_mesh(param, keep):
     m.vertex_faces = keep.arr(t['vertex_faces'], np.int32, C.c_int32)
     m.point_faces = keep.arr(t['point_faces'], np.int32, C.c_int32)
     m.point_faces_mask = keep.arr(t['point_faces_mask'], np.uint8, C.c_uint8)
+    if t.get('lossless'):
+        flags |= L.F_MESH_LOSSLESS
+    if 'face_grid' in t:
+        fg = t['face_grid']
+        m.fgrid_nx, m.fgrid_ny = fg['nx'], fg['ny']
+        m.fgrid_x0, m.fgrid_y0, m.fgrid_inv_dx, m.fgrid_inv_dy = fg['x0'], fg['y0'], fg['inv_dx'], fg['inv_dy']
+        m.fgrid_z_min, m.fgrid_z_max = fg['z_min'], fg['z_max']
+        m.fgrid_start = keep.arr(fg['start'], np.int32, C.c_int32)
+        m.fgrid_items = keep.arr(fg['items'], np.int32, C.c_int32)
     if 'coarse_points' in t:
         flags |= L.F_MESH_REFINE
         m.n_coarse_points, m.n_coarse_faces = len(t['coarse_points']), len(t['coarse_faces'])

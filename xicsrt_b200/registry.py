@@ -47,7 +47,11 @@ def _d_shape(shape):
     mesh = {'mesh_points': None, 'mesh_normals': None, 'mesh_faces': None,
             'mesh_coarse_points': None, 'mesh_coarse_normals': None,
             'mesh_coarse_faces': None, 'mesh_interpolate': None,
-            'mesh_refine': None}  # _ShapeMesh.py:96-109
+            'mesh_refine': None,  # _ShapeMesh.py:96-109
+            # not in the reference: find the fine face by the full Moeller-Trumbore test (accelerated by a face grid)
+            # instead of the lossy coarse -> nearest-vertex pre-selection the reference documents in
+            # _ShapeMesh.py:52-79 and TODO:3-8; results are those of mesh_refine=False
+            'mesh_lossless': False}
     if shape == 'mesh':
         return mesh
     if shape == 'mesh_sphere':
