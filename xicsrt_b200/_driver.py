@@ -362,23 +362,31 @@ def gather_rows(torch, rays, mask, n_found):
     table = [[int(v) for v in t.cpu()] for t in table]
     if rank != 0:
         if n:
-            dist.send(rays.contiguous(), dst=0)
-            dist.send(mask.contiguous(), dst=0)
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, rays.contiguous(), 0),
+                                               dist.P2POp(dist.isend, mask.contiguous(), 0)]):
+                req.wait()
         return rays, mask, n_found
     tot_found = sum(t[0] for t in table)
     tot = tot_found + sum(t[1] for t in table)
     out_rays = torch.empty((n_elem, 7, max(tot, 1)), dtype=rays.dtype, device=rays.device)
     out_mask = torch.empty((n_elem, max(tot, 1)), dtype=mask.dtype, device=rays.device)
+    # all receives are posted at once (one batched NCCL group), then the row ranges are copied into place
+    parts, ops = {0: (rays, mask)}, []
+    for r in range(1, world):
+        nf, nl = table[r]
+        if nf + nl:
+            parts[r] = (torch.empty((n_elem, 7, nf + nl), dtype=rays.dtype, device=rays.device),
+                        torch.empty((n_elem, nf + nl), dtype=mask.dtype, device=rays.device))
+            ops += [dist.P2POp(dist.irecv, parts[r][0], r), dist.P2POp(dist.irecv, parts[r][1], r)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     f_at, l_at = 0, tot_found
     for r in range(world):
         nf, nl = table[r]
-        if r == 0:
-            part_rays, part_mask = rays, mask
-        elif nf + nl:
-            part_rays = torch.empty((n_elem, 7, nf + nl), dtype=rays.dtype, device=rays.device)
-            part_mask = torch.empty((n_elem, nf + nl), dtype=mask.dtype, device=rays.device)
-            dist.recv(part_rays, src=r)
-            dist.recv(part_mask, src=r)
+        if r not in parts:
+            continue
+        part_rays, part_mask = parts[r]
         for e in range(n_elem):
             if nf:
                 src, dst = rows_views(part_rays, part_mask, e, 0, nf), rows_views(out_rays[:, :, :tot], out_mask[:, :tot], e, f_at, f_at + nf)
