@@ -410,6 +410,24 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
                     K.err = (float)((mode == CULL_BUNDLES ? 0.0 : dev) + 1e-9 +
                                     (mode == CULL_POINT ? 2e-5 * std::fmax(1.0, ll_max / r2) : 0.0));
                     K.moving = (src.velocity_c[0] != 0.0 || src.velocity_c[1] != 0.0 || src.velocity_c[2] != 0.0) ? 1 : 0;
+                    // second stage: crystal bounds (a ray outside |x| < hx, |y| < hy is lost at the crystal whatever else
+                    // the optic checks) and the second pre-test level with the rocking-curve uniform
+                    const uint32_t xy = XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE;
+                    K.bounds_xy = ((o.flags & xy) == xy) ? 1 : 0;
+                    K.convex = (o.flags & XRT_F_CONVEX) ? 1 : 0;
+                    K.gauss = o.rocking_type == XRT_ROCK_GAUSS ? 1 : 0;
+                    for (int i = 0; i < 3; ++i) {
+                        K.Ob[i] = (float)(src.origin[i] - o.origin[i]);
+                        K.ox[i] = (float)o.orient[i];
+                        K.oy[i] = (float)o.orient[3 + i];
+                        K.Oc[i] = o.origin[i];
+                    }
+                    K.hx = (float)o.half_size[0];
+                    K.hy = (float)o.half_size[1];
+                    K.lg_refl = (float)std::log2(o.reflectivity);
+                    K.two_sigma2 = (float)o.rock_two_sigma2;
+                    // (a step curve has no second level; the bounds test alone does not pay for the re-pack: measured)
+                    K.stage2 = (K.gauss && std::getenv("XRT_NO_STAGE2") == nullptr) ? 1 : 0;
                     s->cull_mode = mode;
                     d.kn32[0] = 1.0f;       // reported to the caller: the broad phase is in use
                 }

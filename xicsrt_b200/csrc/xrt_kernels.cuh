@@ -908,6 +908,17 @@ struct Cull32Par {
     float err_sig;         // 2e-3 |inv_two_d|: approximate-deviate term of err per unit sigma (bundles)
     int32_t moving;        // Doppler shift present
     int32_t normal_line;   // XRT_WAVE_NORMAL (else constant)
+    // second stage (rays the first stage could not reject, re-packed): crystal bounds and the rocking-curve uniform
+    int32_t stage2;        // enabled
+    int32_t bounds_xy;     // the crystal checks |x| < hx, |y| < hy (and nothing else that the stage does not know)
+    int32_t convex;        // sphere root: tca - thc instead of tca + thc
+    int32_t gauss;         // Gaussian rocking curve: second pre-test level with the ray's uniform
+    float Ob[3];           // source origin - crystal origin                      (not bundles)
+    float ox[3], oy[3];    // crystal x and y axes
+    float hx, hy;          // half sizes
+    float lg_refl;         // log2(reflectivity)
+    float two_sigma2;      // 2 sigma^2 of the rocking curve
+    double Oc[3];          // crystal origin in FP64 (bundles)
     double C[3], T[3];     // sphere centre and target in FP64 (bundles: per-ray differences formed in FP64 once)
 };
 
@@ -926,11 +937,20 @@ struct Cull32Out {
 #define XRT_CULL_BLOCKS 6
 #endif
 
+// what the second stage needs of a ray
+struct Cull32Full {
+    float dx, dy, dz, tca, thc;      // direction, sphere chord
+    float px, py, pz;                // ray origin - crystal origin
+    float gap, c2, err;              // Bragg pre-test quantities
+    bool usable;
+};
+
 // true = provably lost at the crystal
-template <int SRC>
+template <int SRC, bool FULL = false>
 __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
-                                           uint32_t lo, uint32_t hi) {
+                                           uint32_t lo, uint32_t hi, Cull32Full *full = nullptr) {
     const uint4 r = philox4x32_10(make_uint4(lo, hi, SITE_CONE, stream), pk);
+    float Px = K.Ob[0], Py = K.Ob[1], Pz = K.Ob[2];
 
     float one_m_cos = K.one_m_cos, sig = K.sig, err = K.err;
     float Lx = K.Lb[0], Ly = K.Lb[1], Lz = K.Lb[2];
@@ -957,6 +977,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         sig = (float)__ldg(&bd->wave_sigma);
         err = fmaf(K.err_sig, fabsf(sig), K.err);
         vx = (float)__ldg(&bd->velocity_c[0]); vy = (float)__ldg(&bd->velocity_c[1]); vz = (float)__ldg(&bd->velocity_c[2]);
+        if constexpr (FULL) { Px = (float)(ox - K.Oc[0]); Py = (float)(oy - K.Oc[1]); Pz = (float)(oz - K.Oc[2]); }
     }
 
     // ---- origin offset in world coordinates (the exact path: u01_42x3 of one block, off_k = ext_k (u_k - 1/2))
@@ -971,6 +992,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         const float wz = o0 * K.R[2] + o1 * K.R[5] + o2 * K.R[8];
         Lx -= wx; Ly -= wy; Lz -= wz;
         Tx -= wx; Ty -= wy; Tz -= wz;
+        if constexpr (FULL) { Px += wx; Py += wy; Pz += wz; }
     }
 
     // ---- local cone vector.  1 - a from the top 32 bits of the polar uniform (their complement): its RELATIVE
@@ -988,13 +1010,18 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
 
     // ---- direction and sphere chord
     float tca, ll, vd = 0.0f;
+    float dx = 0.0f, dy = 0.0f, dz = 0.0f;
     if constexpr (SRC == CULL_POINT) {
         // fixed basis and fixed origin: L . D = l . (basis L), v . D = l . (basis v); |L|^2 is a constant
         tca = lx * K.m[0] + ly * K.m[1] + z * K.m[2];
         ll = K.ll;
         if (K.moving) vd = lx * K.mv[0] + ly * K.mv[1] + z * K.mv[2];
+        if constexpr (FULL) {
+            dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
+            dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
+            dz = lx * K.basis[2] + ly * K.basis[5] + z * K.basis[8];
+        }
     } else {
-        float dx, dy, dz;
         if constexpr (SRC == CULL_BOX) {
             dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
             dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
@@ -1036,17 +1063,79 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
     const float gap = fabsf(sB - sI);
     const float diff = gap - err;
     const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
+    if constexpr (FULL) {
+        full->dx = dx; full->dy = dy; full->dz = dz; full->tca = tca; full->thc = thc;
+        full->px = Px; full->py = Py; full->pz = Pz;
+        full->gap = gap; full->c2 = c2; full->err = err; full->usable = usable;
+    }
     return usable & (diff > 0.0f) & (diff * diff > K.t2 * c2);
+}
+
+// Second stage for one ray that survived the first: the same single-precision ray once more (now with its direction
+// and chord), then
+//   bounds   X = O + t D in the crystal's frame; a ray farther outside |x| < hx, |y| < hy than the rounding of the
+//            chord arithmetic allows (4e-7 of the lengths that cancel in t = tca +- thc) is lost at the crystal;
+//   level 2  with the ray's rocking-curve uniform u (words z, w of the SITE_WAVE block, the block the exact path reads):
+//            reflected => dtheta^2 <= 2 sigma^2 ln(reflectivity / u); the first stage's lower bound on |dtheta| beyond
+//            that means lost (bragg_cull_uniform in single precision, u truncated to 23 bits -- downwards, which only
+//            widens the limit).
+// true = provably lost at the crystal.
+template <int SRC>
+__device__ __forceinline__ bool cull32_stage2(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
+                                              uint32_t lo, uint32_t hi) {
+    Cull32Full f;
+    if (cull32_ray<SRC, true>(K, src, pk, stream, lo, hi, &f)) return true;
+    bool lost = false;
+    if (K.bounds_xy) {
+        const float t = K.convex ? f.tca - f.thc : f.tca + f.thc;
+        const float X = fmaf(t, f.dx, f.px), Y = fmaf(t, f.dy, f.py), Z = fmaf(t, f.dz, f.pz);
+        const float xl = X * K.ox[0] + Y * K.ox[1] + Z * K.ox[2];
+        const float yl = X * K.oy[0] + Y * K.oy[1] + Z * K.oy[2];
+        const float slack = fmaf(4e-7f, fabsf(f.tca) + fabsf(f.thc) + fabsf(f.px) + fabsf(f.py) + fabsf(f.pz), 1e-7f);
+        lost = (fabsf(xl) > K.hx + slack) | (fabsf(yl) > K.hy + slack);       // NaN (sphere missed): not lost here
+    }
+    if (K.gauss && f.usable) {
+        const uint4 b = philox4x32_10(make_uint4(lo, hi, SITE_WAVE, stream), pk);
+        const float u = __uint_as_float(0x3f800000u | (b.z >> 9)) - 1.0f;
+        const float lim = 0.6931471805599453f * (K.lg_refl - lg2_approx(u));
+        const float bound = fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * K.two_sigma2;
+        const float diff = f.gap - f.err;
+        lost |= (diff > 0.0f) & (diff * diff > bound * f.c2) & (lim == lim);
+    }
+    return lost;
 }
 
 // groups of 32 consecutive ids per pass (independent chains): one for the bundle lookup, whose loads already overlap
 template <int SRC> __host__ __device__ constexpr int cull_unroll() { return SRC == CULL_BUNDLES ? 1 : XRT_CULL_UNROLL; }
 
 // cull_unroll groups of 32 consecutive ids: test, then append the survivors to the region's list
+// stage 2 for `cnt` offsets popped from the warp's queue; survivors are appended to the region's list
+template <int SRC, bool HIST>
+__device__ __forceinline__ void cull32_drain(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint64_t stream_id,
+                                             const XrtOutputs &out, unsigned lane, unsigned lt_mask, uint64_t id_first,
+                                             uint32_t off_first, const uint32_t *q, int first, int cnt, uint32_t *dst, uint32_t &kept) {
+    const bool active = (int)lane < cnt;
+    const uint32_t off = active ? q[first + lane] : q[first];
+    __syncwarp();
+    const uint64_t id = id_first + off;
+    const bool pass = active && !cull32_stage2<SRC>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32));
+    if constexpr (HIST) {
+        if (out.lost_count || out.lost_bits) {
+            PhiloxDraws dr;
+            dr.init(pk, stream_id, id, 0);
+            emit_lost<true>(out, lane, lt_mask, dr, active && !pass, id);
+        }
+    }
+    const unsigned m = __ballot_sync(kFull, pass);
+    if (pass) dst[kept + __popc(m & lt_mask)] = off_first + off;
+    kept += __popc(m);
+}
+
 template <int SRC, bool HIST, bool CHECK>
 __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint64_t stream_id,
                                             const XrtOutputs &out, unsigned lane, unsigned lt_mask, uint64_t id_first,
-                                            uint32_t off_first, uint32_t g, uint32_t n_here, uint32_t *dst, uint32_t &kept) {
+                                            uint32_t off_first, uint32_t g, uint32_t n_here, uint32_t *dst, uint32_t &kept,
+                                            uint32_t *q, int &nq) {
     constexpr int U = cull_unroll<SRC>();
     bool valid[U], pass[U];
     uint32_t off[U];
@@ -1068,17 +1157,28 @@ __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceD
             }
         }
         const unsigned m = __ballot_sync(kFull, pass[j]);
-        if (pass[j]) dst[kept + __popc(m & lt_mask)] = off_first + off[j];
-        kept += __popc(m);
+        if (K.stage2) {
+            if (pass[j]) q[nq + __popc(m & lt_mask)] = off[j];
+            nq += __popc(m);
+            __syncwarp();
+            if (nq >= 32) {         // at most 63 queued: one full pop keeps the queue below 32 + the next push
+                nq -= 32;
+                cull32_drain<SRC, HIST>(K, src, pk, stream_id, out, lane, lt_mask, id_first, off_first, q, nq, 32, dst, kept);
+            }
+        } else {
+            if (pass[j]) dst[kept + __popc(m & lt_mask)] = off_first + off[j];
+            kept += __popc(m);
+        }
     }
 }
 
-// resident blocks per SM: the bundle lookup (64-bit search, FP64 differences) needs more registers than the rest
+// resident blocks per SM: the bundle lookup (64-bit search, FP64 differences) and the lost-sample emission of
+// history-on launches need more registers than the rest
 #ifndef XRT_CULL_BLOCKS_BUNDLES
 #define XRT_CULL_BLOCKS_BUNDLES 4
 #endif
 template <int SRC, bool HIST>
-__global__ void __launch_bounds__(kBlock, (SRC == CULL_BUNDLES ? XRT_CULL_BLOCKS_BUNDLES : XRT_CULL_BLOCKS))
+__global__ void __launch_bounds__(kBlock, ((SRC == CULL_BUNDLES || HIST) ? XRT_CULL_BLOCKS_BUNDLES : XRT_CULL_BLOCKS))
 k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceDesc src, const __grid_constant__ PhiloxKeys pk,
          const uint64_t stream_id, const uint64_t ray_begin, const uint64_t ray_count, const Cull32Out lst,
          const XrtOutputs out) {
@@ -1088,6 +1188,9 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
     const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     constexpr uint32_t kPass = 32u * cull_unroll<SRC>();
     unsigned long long n_src = 0;
+    __shared__ uint32_t s_q2[kBlock / 32][64];          // per warp: offsets waiting for the second stage
+    uint32_t *q = s_q2[threadIdx.x >> 5];
+    int nq = 0;
     // Regions are claimed from a global counter: with a static share per warp the scheduler's oldest-first policy lets
     // the old warps of an SM finish early and the SM runs its last third at half occupancy (ncu: 49 % achieved of 75 %).
     if (blockIdx.x == 0 && threadIdx.x == 0) *lst.next_reset = 0u;
@@ -1105,9 +1208,13 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
         n_src += n_here;
         uint32_t g = 0;
         for (; g + kPass <= n_here; g += kPass)
-            cull32_pass<SRC, HIST, false>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept);
+            cull32_pass<SRC, HIST, false>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept, q, nq);
         if (g < n_here)
-            cull32_pass<SRC, HIST, true>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept);
+            cull32_pass<SRC, HIST, true>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept, q, nq);
+        if (nq > 0) {               // the queue holds offsets of this region only: drain it before the next one
+            cull32_drain<SRC, HIST>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, q, 0, nq, dst, kept);
+            nq = 0;
+        }
         if (lane == 0) lst.counts[reg] = kept;
     }
     // rays out of the source: one atomic per block
