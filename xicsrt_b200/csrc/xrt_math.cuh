@@ -90,10 +90,13 @@ __host__ __device__ inline void philox_round_keys(uint64_t seed, uint64_t stream
     }
 }
 
+#ifndef XRT_PHILOX_ROUNDS
+#define XRT_PHILOX_ROUNDS 10
+#endif
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &K) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < XRT_PHILOX_ROUNDS; ++r) {
         uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
         uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
         c = make_uint4(hi1 ^ c.y ^ K.rk[2 * r], lo1, hi0 ^ c.w ^ K.rk[2 * r + 1], lo0);
