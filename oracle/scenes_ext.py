@@ -152,6 +152,8 @@ EXTRA = {
     'mesh_torus_norefine': lambda: mesh_torus(n=5000, seed=39, mesh_size=(41, 41), mesh_refine=False),
     # product option mesh_lossless: a refining mesh traced with the full test; same rays as the scene above
     'mesh_torus_lossless': lambda: mesh_torus(n=5000, seed=39, mesh_size=(41, 41), mesh_lossless=True),
+    # refinement without interpolation: flat normals of the fine face that was hit (_ShapeMesh.py:428-432)
+    'mesh_torus_flat_normals': lambda: mesh_torus(n=5000, seed=40, mesh_size=(17, 23), mesh_interpolate=False),
     'mesh_torus_convex': lambda: mesh_torus(seed=37, convex=[True, False], mesh_size=(15, 15)),
     'mesh_sphere': mesh_sphere,
     'mesh_cylinder': mesh_cylinder,

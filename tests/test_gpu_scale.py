@@ -169,6 +169,59 @@ def test_work_skipping_stages_change_no_result_at_bench_scale(torch, name, monke
             assert torch.equal(found1, found0), f'{name} seed {seed}: found-id set differs with {env}'
 
 
+N_MESH = max(N_SCALE // 10, 1000)
+
+
+def _mesh_geometries():
+    import bench
+    g = {}
+    g['config4'] = bench.workload_config('config4', N_MESH)                    # point source: dot-product pre-selection
+    c = bench.workload_config('config4', N_MESH)
+    c['sources']['source'].update({'xsize': 5e-3, 'ysize': 5e-3, 'zsize': 5e-3})
+    g['config4_box_source'] = c                                               # staged face operands
+    c = bench.workload_config('config4', N_MESH)
+    c['optics']['crystal'].update({'check_bragg': True, 'rocking_fwhm': 2e-3, 'mesh_size': (24, 31),
+                                   'mesh_coarse_size': (4, 5)})
+    g['config4_bragg_24x31'] = c
+    c = bench.workload_config('config4', N_MESH)
+    c['optics']['crystal'].update({'trace_local': True, 'mesh_interpolate': False})
+    g['config4_local_flat_normals'] = c
+    return g
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('name', ['config4', 'config4_box_source', 'config4_bragg_24x31', 'config4_local_flat_normals'])
+def test_sorted_mesh_path_changes_no_result(torch, name, monkeypatch):
+    """The sorted mesh path (k_mesh_coarse -> counting sort by hit location -> k_trace in sorted mode) only changes the
+    order in which rays are refined: same counters, images and found-id sets as the single-kernel path at 1e8 rays."""
+    from xicsrt_b200 import _driver, config as xconfig
+    cfg = _mesh_geometries()[name]
+    cfg['general']['keep_history'] = False
+    results = []
+    for env in ({}, {'XRT_NO_MESH_SORT': '1'}):
+        monkeypatch.delenv('XRT_NO_MESH_SORT', raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        per_seed = []
+        for seed in SEEDS[:2]:
+            tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(copy.deepcopy(cfg))), seed=seed)
+            tracer.trace(1)
+            packed_off = tracer.packed.clone()
+            found, lost = tracer.select_ids(1, 64)
+            assert torch.equal(tracer.packed, packed_off), f'{name}: history-on launch counts differ from history-off'
+            per_seed.append((packed_off, found.clone(), lost.clone()))
+            tracer.close()
+        results.append(per_seed)
+    for s, seed in enumerate(SEEDS[:2]):
+        packed0, found0, lost0 = results[0][s]
+        packed1, found1, lost1 = results[1][s]
+        assert int(packed0[0]) == N_MESH
+        assert int(found0.numel()) == int(packed0[2]) > N_MESH // 1000
+        assert torch.equal(packed1, packed0), f'{name} seed {seed}: counters / images differ without the sort'
+        assert torch.equal(found1, found0), f'{name} seed {seed}: found-id set differs without the sort'
+        assert torch.equal(torch.sort(lost1)[0], torch.sort(lost0)[0]), f'{name} seed {seed}: lost sample differs'
+
+
 def _local_xy(res, elem):
     from xicsrt_b200 import elements
     from oracle import vecs

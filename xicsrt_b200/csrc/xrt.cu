@@ -10,6 +10,7 @@
 #include <new>
 #include <vector>
 
+#define XRT_MESHSORT_HOST_KERNELS
 #include "xrt_variants.h"
 #include "xrt_plasma.cuh"
 #include "xrt_select.cuh"
@@ -65,6 +66,16 @@ struct XrtScene {
     uint64_t list_ids_cap = 0, list_counts_cap = 0;
     unsigned int *list_next = nullptr;   // [2] region counters of k_cull32, used alternately (each launch resets the other)
     int list_phase = 0;
+    // sorted mesh path (xrt_meshsort.cuh): applies when the first optic is a refining mesh (see scene_build)
+    int mesh_sort = 0;
+    int mesh_bins = 0, mesh_tile = 0, mesh_tiles_x = 0, mesh_sub = 1;
+    uint32_t *ms_entries = nullptr, *ms_sorted = nullptr, *ms_counts = nullptr, *ms_total = nullptr;
+    uint16_t *ms_bins = nullptr;
+    unsigned int *ms_hist = nullptr, *ms_cursor = nullptr;
+    uint64_t ms_cap = 0, ms_counts_cap = 0;
+    const double *coarse_geom_dev = nullptr;   // of the mesh uploaded last (upload_mesh)
+    int32_t coarse_faces = 0;
+    MeshDirGrid dirgrid = {};                  // direction grid of a point source in front of the mesh (mask = nullptr: none)
 };
 
 static thread_local char g_err[512] = "";
@@ -158,6 +169,8 @@ static int upload_mesh(XrtScene *s, const XrtMesh *host, const XrtMesh **dev) {
         UP(m.fgrid_start, have ? fcells + 1 : 0);
         UP(m.fgrid_items, n_f);
     }
+    s->coarse_geom_dev = m.coarse_geom;
+    s->coarse_faces = m.n_coarse_faces;
     const XrtMesh *d = nullptr;
     int rc = upload(s, &m, 1, &d);
     if (rc != XRT_OK) return rc;
@@ -203,6 +216,9 @@ extern "C" int xrt_scene_destroy(XrtScene *s) {
     if (s->list_ids) cudaFreeAsync(s->list_ids, (cudaStream_t)0);
     if (s->list_counts) cudaFreeAsync(s->list_counts, (cudaStream_t)0);
     if (s->list_next) cudaFreeAsync(s->list_next, (cudaStream_t)0);
+    // ms_cursor and ms_total live inside the ms_hist allocation
+    for (void *p : {(void *)s->ms_entries, (void *)s->ms_sorted, (void *)s->ms_counts, (void *)s->ms_bins, (void *)s->ms_hist})
+        if (p) cudaFreeAsync(p, (cudaStream_t)0);
     delete s;
     return XRT_OK;
 }
@@ -285,6 +301,23 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
             if ((m.flags & XRT_F_MESH_INTERP) && (m.mesh->n_tri <= 0 || !m.mesh->ct_coef || !m.mesh->tri_transform ||
                                                   !m.mesh->grid_start))
                 return fail(XRT_EINVAL, "optic %d: mesh interpolation needs the Clough-Tocher tables", k);
+            if (k == 0 && (m.flags & XRT_F_MESH_REFINE) && !(m.flags & XRT_F_MESH_LOSSLESS) &&
+                m.mesh->n_coarse_faces <= (1 << kMeshFaceBits) && m.mesh->grid_nx > 0 && m.mesh->grid_ny > 0) {
+                // bins of the sorted path: tiles of the vertex grid, 3 x 3 cells unless that gives too many bins
+                // bins of the sorted path: the cells of the vertex grid, each cut in sub x sub (rays of one bin share the
+                // nearest vertex and the triangle: warp-uniform table reads), or tiles of tile x tile cells when the
+                // grid has more cells than bins allowed
+                int sub = 2, tile = 1;
+                if (const char *v = std::getenv("XRT_MESH_SUB")) sub = std::atoi(v) > 0 ? std::atoi(v) : 2;       // measurement knobs
+                if (const char *v = std::getenv("XRT_MESH_TILE")) tile = std::atoi(v) > 0 ? std::atoi(v) : 1;
+                const long gx = m.mesh->grid_nx, gy = m.mesh->grid_ny;
+                while (sub > 1 && gx * sub * gy * sub > kMeshMaxBins) --sub;
+                while (((gx * sub + tile - 1) / tile) * ((gy * sub + tile - 1) / tile) > kMeshMaxBins) ++tile;
+                s->mesh_sub = sub;
+                s->mesh_tile = tile;
+                s->mesh_tiles_x = (int)((gx * sub + tile - 1) / tile);
+                s->mesh_bins = s->mesh_tiles_x * (int)((gy * sub + tile - 1) / tile);
+            }
             int rc = upload_mesh(s, m.mesh, &m.mesh);
             if (rc != XRT_OK) return rc;
         } else {
@@ -317,6 +350,38 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
     // the lean variant has no wavelength plane in its queue: a source with a Doppler shift takes the lean
     // extended-source variant
     if (s->features == 0 && !s->lazy_wavelength) s->features = FT_SRCLEAN;
+    // sorted mesh path: the conditions under which k_trace splits stage A at the coarse mesh (mesh_staged)
+    s->mesh_sort = (s->mesh_bins > 0 && s->split == 0 && d.optics[0].shape == XRT_SHAPE_MESH && s->lazy_wavelength &&
+                    src.kind != XRT_SRC_BUNDLES && src.cone != XRT_CONE_ISOTROPIC_XY &&
+                    (s->features == FT_MESHLEAN || s->features == FT_FULL)) ? 1 : 0;
+    if (s->mesh_sort && src.kind == XRT_SRC_FIXED_AXIS && src.cone == XRT_CONE_ISOTROPIC && src.spatial == XRT_SPATIAL_UNIFORM &&
+        src.extent[0] == 0.0 && src.extent[1] == 0.0 && src.extent[2] == 0.0 && src.cone_par[0] > 0.2 &&
+        src.cone_par[0] < 1.0 && s->coarse_geom_dev && !getenv("XRT_NO_MESH_DIRGRID")) {
+        // direction grid over the cone (xrt_meshsort.cuh): cone frame and source point in the mesh's tracing frame
+        const XrtOpticDesc &o = d.optics[0];
+        const bool local = (o.flags & XRT_F_TRACE_LOCAL) != 0;
+        auto rot = [&](const double *v, double *out) {
+            for (int i = 0; i < 3; ++i)
+                out[i] = local ? o.orient[3 * i] * v[0] + o.orient[3 * i + 1] * v[1] + o.orient[3 * i + 2] * v[2] : v[i];
+        };
+        MeshDirGrid &G = s->dirgrid;
+        rot(src.axis_basis + 0, G.ex);
+        rot(src.axis_basis + 3, G.ey);
+        rot(src.axis_basis + 6, G.ez);
+        const double cs = src.cone_par[0];
+        G.half = std::sqrt(1.0 - cs * cs) / cs * (1.0 + 1e-9);
+        G.inv_h = kDirGrid / (2.0 * G.half);
+        double rel[3] = {src.origin[0] - (local ? o.origin[0] : 0.0), src.origin[1] - (local ? o.origin[1] : 0.0),
+                         src.origin[2] - (local ? o.origin[2] : 0.0)}, ot[3];
+        rot(rel, ot);
+        void *p = nullptr;
+        CU(cudaMallocAsync(&p, kDirGrid * kDirGrid * sizeof(uint32_t), (cudaStream_t)0));
+        s->allocs.push_back(p);
+        G.mask = (const uint32_t *)p;
+        k_mesh_dirgrid<<<(kDirGrid * kDirGrid + kBlock - 1) / kBlock, kBlock, 0, (cudaStream_t)0>>>(
+            s->coarse_geom_dev, s->coarse_faces, V3{ot[0], ot[1], ot[2]}, G, (uint32_t *)p);
+        CU(cudaGetLastError());
+    }
     s->known = 0;
     if (d.n_optics > 0) {
         const XrtOpticDesc &o = d.optics[s->split];
@@ -583,6 +648,54 @@ static int ensure_list(XrtScene *s, uint64_t n_ids, uint64_t n_regions, cudaStre
     return XRT_OK;
 }
 
+static uint64_t mesh_sort_min_rays() {
+    if (const char *v = std::getenv("XRT_MESH_SORT_MIN_RAYS")) return (uint64_t)std::strtoull(v, nullptr, 10);
+    return 1ull << 21;
+}
+
+static int ensure_mesh_sort(XrtScene *s, uint64_t n_ids, uint64_t n_regions, cudaStream_t st) {
+    if (!s->list_next) {
+        void *p = nullptr;
+        CU(cudaMallocAsync(&p, 2 * sizeof(unsigned int), st));
+        CU(cudaMemsetAsync(p, 0, 2 * sizeof(unsigned int), st));
+        s->list_next = (unsigned int *)p;
+        s->list_phase = 0;
+    }
+    if (!s->ms_hist) {
+        void *p = nullptr;
+        CU(cudaMallocAsync(&p, (2 * (size_t)kMeshMaxBins + 1) * sizeof(unsigned int), st));
+        CU(cudaMemsetAsync(p, 0, (2 * (size_t)kMeshMaxBins + 1) * sizeof(unsigned int), st));
+        s->ms_hist = (unsigned int *)p;
+        s->ms_cursor = s->ms_hist + kMeshMaxBins;
+        s->ms_total = (uint32_t *)(s->ms_hist + 2 * kMeshMaxBins);
+    }
+    if (s->ms_cap < n_ids) {
+        for (void *p : {(void *)s->ms_entries, (void *)s->ms_sorted, (void *)s->ms_bins})
+            if (p) CU(cudaFreeAsync(p, st));
+        s->ms_entries = s->ms_sorted = nullptr;
+        s->ms_bins = nullptr;
+        s->ms_cap = 0;
+        void *p = nullptr;
+        CU(cudaMallocAsync(&p, n_ids * sizeof(uint32_t), st));
+        s->ms_entries = (uint32_t *)p;
+        CU(cudaMallocAsync(&p, n_ids * sizeof(uint32_t), st));
+        s->ms_sorted = (uint32_t *)p;
+        CU(cudaMallocAsync(&p, n_ids * sizeof(uint16_t), st));
+        s->ms_bins = (uint16_t *)p;
+        s->ms_cap = n_ids;
+    }
+    if (s->ms_counts_cap < n_regions) {
+        if (s->ms_counts) CU(cudaFreeAsync(s->ms_counts, st));
+        s->ms_counts = nullptr;
+        s->ms_counts_cap = 0;
+        void *p = nullptr;
+        CU(cudaMallocAsync(&p, n_regions * sizeof(uint32_t), st));
+        s->ms_counts = (uint32_t *)p;
+        s->ms_counts_cap = n_regions;
+    }
+    return XRT_OK;
+}
+
 extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_t ray_begin, uint64_t ray_count,
                          const XrtOutputs *out, void *stream) {
     if (!s || !out) return fail(XRT_EINVAL, "null argument");
@@ -611,8 +724,10 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     const uint64_t cap_blocks = (uint64_t)s->sm_count * (uint64_t)bps;
 
     const bool two_kernels = s->cull_mode >= 0 && ray_count >= cull_min_rays();
-    // a launch covers at most 2^30 ids (32-bit offsets in the id list, 4 GB of list at most)
-    const uint64_t max_launch = two_kernels ? (1ull << 30) : ~0ull;
+    const bool mesh_sorted = !two_kernels && s->mesh_sort && ray_count >= mesh_sort_min_rays() && !getenv("XRT_NO_MESH_SORT");
+    // a launch covers at most 2^30 ids (32-bit offsets in the id list, 4 GB of list at most); 2^27 on the sorted mesh
+    // path (27-bit offsets beside the face tag)
+    const uint64_t max_launch = two_kernels ? (1ull << 30) : (mesh_sorted ? kMeshMaxLaunch : ~0ull);
     for (uint64_t done = 0; done < ray_count; done += max_launch) {
         const uint64_t n = ray_count - done < max_launch ? ray_count - done : max_launch;
         const uint64_t begin = ray_begin + done;
@@ -641,6 +756,45 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
             ck<<<(int)(want < ccap ? want : ccap), kBlock, 0, st>>>(s->cull, s->dev.source, pk, stream_id, begin, n, lst, *out);
             CU(cudaGetLastError());
             list = {s->list_ids, s->list_counts, n_regions, cap};
+        } else if (mesh_sorted) {
+            // regions of consecutive ids for k_mesh_coarse, as for the broad phase
+            const uint64_t n_groups = (n + 31) / 32;
+            uint64_t gpr = (n_groups + (uint64_t)s->sm_count * 384 - 1) / ((uint64_t)s->sm_count * 384);
+            if (gpr < 32) gpr = 32;
+            const uint32_t cap = (uint32_t)(gpr * 32);
+            const uint32_t n_regions = (uint32_t)((n + cap - 1) / cap);
+            rc = ensure_mesh_sort(s, (uint64_t)n_regions * cap, n_regions, st);
+            if (rc != XRT_OK) return rc;
+            size_t csmem = 0;
+            MeshCoarseKernel mk = s->features == FT_MESHLEAN ? mesh_coarse_kernel_mesh(hist, &csmem) : mesh_coarse_kernel_full(hist, &csmem);
+            int cbps = 0;
+            CU(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cbps, mk, kBlock, csmem));
+            if (cbps < 1) return fail(XRT_ECUDA, "coarse-mesh kernel does not fit on an SM");
+            const uint64_t cwant = ((uint64_t)n_regions + kBlock / 32 - 1) / (kBlock / 32);
+            const uint64_t ccap = (uint64_t)s->sm_count * (uint64_t)cbps;
+            MeshSortOut lst = {s->ms_entries, s->ms_bins, s->ms_counts, n_regions, cap, s->list_next + s->list_phase,
+                               s->list_next + (s->list_phase ^ 1), s->ms_hist, s->mesh_bins, s->mesh_tile, s->mesh_tiles_x, s->mesh_sub, s->dirgrid};
+            s->list_phase ^= 1;
+            mk<<<(int)(cwant < ccap ? cwant : ccap), kBlock, csmem, st>>>(s->dev, pk, stream_id, begin, n, lst, *out);
+            CU(cudaGetLastError());
+            k_mesh_scan<<<1, kBlock, 0, st>>>(s->ms_hist, s->ms_cursor, s->ms_total, s->mesh_bins);
+            CU(cudaGetLastError());
+            const uint64_t sgrid = (uint64_t)s->sm_count * 8;
+            CU(cudaFuncSetAttribute(k_mesh_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMeshMaxBins * sizeof(unsigned int))));
+            k_mesh_scatter<<<(int)(n_regions < sgrid ? n_regions : sgrid), kBlock, 2 * (size_t)s->mesh_bins * sizeof(unsigned int), st>>>(
+                s->ms_entries, s->ms_bins, s->ms_counts, n_regions, cap, s->ms_cursor, s->ms_sorted, s->mesh_bins);
+            CU(cudaGetLastError());
+            // the number of hits is known on the device only: one resident wave of the refinement kernel reads *total
+            MeshRefineKernel rk = s->features == FT_MESHLEAN ? mesh_refine_kernel_mesh(hist) : mesh_refine_kernel_full(hist);
+            int rbps = 0;
+            // 4 kB of static shared memory per block: a small carve-out, the rest of the SM's 256 kB is L1
+            CU(cudaFuncSetAttribute(rk, cudaFuncAttributePreferredSharedMemoryCarveout, 12));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rbps, rk, kBlock, 0));
+            if (rbps < 1) return fail(XRT_ECUDA, "mesh refinement kernel does not fit on an SM");
+            rk<<<s->sm_count * rbps, kBlock, 0, st>>>(s->dev, pk, stream_id, begin, s->ms_sorted, s->ms_total, *out, lazy_bits);
+            CU(cudaGetLastError());
+            continue;
         } else {
             const uint64_t n_groups = (n + 31) / 32;
             if (n_groups > 0xffffffffull) return fail(XRT_EINVAL, "ray_count too large for one launch");

@@ -1226,6 +1226,10 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
     if (threadIdx.x == 0 && s_src && out.counts) atomicAdd((unsigned long long *)out.counts, s_src);
 }
 
+}  // namespace xrt
+#include "xrt_meshsort.cuh"
+namespace xrt {
+
 // ---------------------------------------------------------------------------
 // recording kernel: history of every element, optional counters / images
 

@@ -391,15 +391,42 @@ __device__ __forceinline__ int mesh_stage1_faces(const XrtOpticDesc &op, const d
 // shared-memory copy of the step-1 face operands.
 // The coarse step alone (step 1 of a refining mesh): true = some coarse face is hit, Xc = the hit point.
 // The fused kernel runs it for every ray, re-packs the ~half that hit and resumes mesh_intersect with Xc.
-__device__ __forceinline__ bool mesh_coarse_hit(const XrtOpticDesc &op, V3 o, V3 d, V3 &Xc, const double *staged = nullptr,
+// Returns the coarse face that was hit (the last one in face order) or -1.
+__device__ __forceinline__ int mesh_coarse_face(const XrtOpticDesc &op, V3 o, V3 d, V3 &Xc, const double *staged = nullptr,
                                                 bool point_constants = false) {
     const double *geom;
     const int n1 = mesh_stage1_faces(op, geom);
     Xc = nan3();
-    int face;
-    if (staged && point_constants) face = mesh_all_faces_point(staged, geom, n1, o, d, Xc);
-    else face = staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
-    return face >= 0;
+    if (staged && point_constants) return mesh_all_faces_point(staged, geom, n1, o, d, Xc);
+    return staged ? mesh_all_faces<true>(staged, n1, o, d, Xc) : mesh_all_faces<false>(geom, n1, o, d, Xc);
+}
+
+__device__ __forceinline__ bool mesh_coarse_hit(const XrtOpticDesc &op, V3 o, V3 d, V3 &Xc, const double *staged = nullptr,
+                                                bool point_constants = false) {
+    return mesh_coarse_face(op, o, d, Xc, staged, point_constants) >= 0;
+}
+
+// The point where the ray meets the plane of one step-1 face: the arithmetic of the hit branch of mesh_all_faces for
+// a face that is known to be hit (sorted mesh path: k_mesh_coarse found the face, k_trace needs the point again).
+__device__ __forceinline__ V3 mesh_face_point(const double *__restrict__ g, V3 o, V3 d) {
+    V3 p0, e1, e2;
+    mesh_face_operands<false>(g, p0, e1, e2);
+    const V3 h = cross(d, e2);
+    const double inv = 1.0 / dot(e1, h);
+    const V3 s = o - p0;
+    const V3 q = cross(s, e1);
+    const double t = inv * dot(e2, q);
+    return v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+}
+
+// Spatial bin of a coarse hit point: the cells of the vertex grid (the cell arithmetic of mesh_nearest_vertex) cut in
+// sub x sub, grouped in tiles of tile x tile, row-major.  Rays of one bin read the same few kB of the refinement tables.
+__device__ __forceinline__ int mesh_bin_of(const XrtMesh &m, V3 q, int sub, int tile, int tiles_x) {
+    int cx = (int)floor((q.x - m.grid_x0) * m.grid_inv_dx * (double)sub);
+    int cy = (int)floor((q.y - m.grid_y0) * m.grid_inv_dy * (double)sub);
+    cx = min(max(cx, 0), m.grid_nx * sub - 1);
+    cy = min(max(cy, 0), m.grid_ny * sub - 1);
+    return (cy / tile) * tiles_x + cx / tile;
 }
 
 // Not inlined: the fused kernel reaches it from four places (optics before / at / after the split optic, stage A2)

@@ -39,6 +39,16 @@ XRT_DECLARE_VARIANT(full)
 
 CullKernel cull_kernel(int src_mode, bool hist);
 
+// sorted mesh path: the coarse-mesh kernel of the two feature sets that hold mesh optics
+typedef void (*MeshCoarseKernel)(const XrtSceneDesc, const PhiloxKeys, const uint64_t, const uint64_t, const uint64_t,
+                                 const MeshSortOut, const XrtOutputs);
+typedef void (*MeshRefineKernel)(const XrtSceneDesc, const PhiloxKeys, const uint64_t, const uint64_t, const uint32_t *,
+                                 const uint32_t *, const XrtOutputs, const int);
+MeshRefineKernel mesh_refine_kernel_mesh(bool hist);
+MeshRefineKernel mesh_refine_kernel_full(bool hist);
+MeshCoarseKernel mesh_coarse_kernel_mesh(bool hist, size_t *smem);
+MeshCoarseKernel mesh_coarse_kernel_full(bool hist, size_t *smem);
+
 // ---- helpers for the v_*.cu files
 template <uint32_t FT, uint32_t KN = 0>
 static void record_launch_ft(int mode, const RecordLaunch &a) {

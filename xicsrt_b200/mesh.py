@@ -375,13 +375,15 @@ def lookup_grids(points_xy, tri_simplices, cells_per_axis=None):
     c_lo = cell_xy(tp.min(axis=1) - pad)
     c_hi = cell_xy(tp.max(axis=1) + pad)
     items, cells = [], []
-    wmax = int((c_hi - c_lo).max()) + 1
+    wmax = int((c_hi - c_lo).max()) + 1 if len(tri_simplices) else 0     # no triangulation: mesh_refine alone
     for dx in range(wmax):
         for dy in range(wmax):
             cx, cy = c_lo[:, 0] + dx, c_lo[:, 1] + dy
             ok = (cx <= c_hi[:, 0]) & (cy <= c_hi[:, 1])
             items.append(np.flatnonzero(ok))
             cells.append((cy * nx + cx)[ok])
+    if not items:
+        items, cells = [np.zeros(0, dtype=np.int64)], [np.zeros(0, dtype=np.int64)]
     tstart, titems = _cell_lists(nx, ny, (np.concatenate(items), np.concatenate(cells)))
     # vertices of the 3 x 3 block of cells around each cell, cell-ordered: the nearest-vertex query reads one
     # contiguous list instead of walking nine cells
