@@ -597,6 +597,23 @@ extern "C" int xrt_launch_info(XrtScene *s, int32_t *grid, int32_t *block, int32
 
 extern "C" int xrt_launch_info_cull(XrtScene *s, int32_t *mode, int32_t *grid, int32_t *regs, int32_t *blocks_per_sm) {
     if (!s) return fail(XRT_EINVAL, "null scene");
+    if (s->cull_mode < 0 && s->mesh_sort && !getenv("XRT_NO_MESH_SORT")) {
+        // sorted mesh path: mode 4 = k_mesh_coarse in front of k_mesh_refine; with bins = the number of spatial bins
+        size_t csmem = 0;
+        MeshCoarseKernel mk = s->features == FT_MESHLEAN ? mesh_coarse_kernel_mesh(false, &csmem) : mesh_coarse_kernel_full(false, &csmem);
+        MeshRefineKernel rk = s->features == FT_MESHLEAN ? mesh_refine_kernel_mesh(false) : mesh_refine_kernel_full(false);
+        cudaFuncAttributes fa, fr;
+        CU(cudaFuncGetAttributes(&fa, mk));
+        CU(cudaFuncGetAttributes(&fr, rk));
+        int bps = 0;
+        CU(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, mk, kBlock, csmem));
+        if (mode) *mode = 4;
+        if (grid) *grid = s->sm_count * bps;
+        if (regs) *regs = fa.numRegs | (fr.numRegs << 16);     // refinement kernel's registers in the high half
+        if (blocks_per_sm) *blocks_per_sm = bps | (s->mesh_bins << 8);
+        return XRT_OK;
+    }
     if (mode) *mode = s->cull_mode;
     if (s->cull_mode < 0) {
         if (grid) *grid = 0;
@@ -780,9 +797,9 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
             CU(cudaGetLastError());
             k_mesh_scan<<<1, kBlock, 0, st>>>(s->ms_hist, s->ms_cursor, s->ms_total, s->mesh_bins);
             CU(cudaGetLastError());
-            const uint64_t sgrid = (uint64_t)s->sm_count * 8;
+            const uint64_t sgrid = (uint64_t)s->sm_count * 8, n_batches = (n_regions + kScatterBatch - 1) / kScatterBatch;
             CU(cudaFuncSetAttribute(k_mesh_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMeshMaxBins * sizeof(unsigned int))));
-            k_mesh_scatter<<<(int)(n_regions < sgrid ? n_regions : sgrid), kBlock, 2 * (size_t)s->mesh_bins * sizeof(unsigned int), st>>>(
+            k_mesh_scatter<<<(int)(n_batches < sgrid ? n_batches : sgrid), kBlock, 2 * (size_t)s->mesh_bins * sizeof(unsigned int), st>>>(
                 s->ms_entries, s->ms_bins, s->ms_counts, n_regions, cap, s->ms_cursor, s->ms_sorted, s->mesh_bins);
             CU(cudaGetLastError());
             // the number of hits is known on the device only: one resident wave of the refinement kernel reads *total

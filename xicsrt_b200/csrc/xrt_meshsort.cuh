@@ -278,19 +278,26 @@ __global__ void __launch_bounds__(kBlock) k_mesh_scan(unsigned int *hist, unsign
     if (threadIdx.x == kBlock - 1) *total = s_part[kBlock - 1];
 }
 
-// one region per block and pass: ranks inside the region by shared-memory atomics, one global atomic per bin
+// kScatterBatch consecutive regions per block and pass: ranks inside the batch by shared-memory atomics, one global
+// atomic per bin that occurs in it
+constexpr uint32_t kScatterBatch = 16;
 __global__ void __launch_bounds__(kBlock) k_mesh_scatter(const uint32_t *__restrict__ entries, const uint16_t *__restrict__ bins,
                                                          const uint32_t *__restrict__ counts, const uint32_t n_regions,
                                                          const uint32_t cap, unsigned int *cursor, uint32_t *__restrict__ sorted,
                                                          const int n_bins) {
-    extern __shared__ unsigned int s_sc[];      // count / fill per bin, then the region's base per bin
+    extern __shared__ unsigned int s_sc[];      // count / fill per bin, then the batch's base per bin
     unsigned int *s_cnt = s_sc, *s_base = s_sc + n_bins;
-    for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+    const uint32_t n_batches = (n_regions + kScatterBatch - 1) / kScatterBatch;
+    for (uint32_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        const uint32_t r0 = batch * kScatterBatch;
+        const uint32_t r1 = r0 + kScatterBatch < n_regions ? r0 + kScatterBatch : n_regions;
         for (int i = threadIdx.x; i < n_bins; i += kBlock) s_cnt[i] = 0u;
         __syncthreads();
-        const uint32_t n = counts[reg];
-        const uint64_t first = (uint64_t)reg * cap;
-        for (uint32_t i = threadIdx.x; i < n; i += kBlock) atomicAdd(&s_cnt[bins[first + i]], 1u);
+        for (uint32_t reg = r0; reg < r1; ++reg) {
+            const uint32_t n = counts[reg];
+            const uint64_t first = (uint64_t)reg * cap;
+            for (uint32_t i = threadIdx.x; i < n; i += kBlock) atomicAdd(&s_cnt[bins[first + i]], 1u);
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < n_bins; i += kBlock) {
             const unsigned int cn = s_cnt[i];
@@ -298,14 +305,17 @@ __global__ void __launch_bounds__(kBlock) k_mesh_scatter(const uint32_t *__restr
             s_cnt[i] = 0u;
         }
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
-            const unsigned int b = bins[first + i];
-            sorted[s_base[b] + atomicAdd(&s_cnt[b], 1u)] = entries[first + i];
+        for (uint32_t reg = r0; reg < r1; ++reg) {
+            const uint32_t n = counts[reg];
+            const uint64_t first = (uint64_t)reg * cap;
+            for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
+                const unsigned int b = bins[first + i];
+                sorted[s_base[b] + atomicAdd(&s_cnt[b], 1u)] = entries[first + i];
+            }
         }
         __syncthreads();
     }
 }
-
 #endif  // XRT_MESHSORT_HOST_KERNELS
 
 #ifndef XRT_REFINE_BLOCKS

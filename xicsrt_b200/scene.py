@@ -418,9 +418,13 @@ class DeviceScene:
         m = C.c_int32()
         L.check(self.lib.xrt_launch_info_cull(self.handle, C.byref(m), C.byref(g), C.byref(r), C.byref(p)))
         # FP32 broad phase in front of the fused kernel: None when it does not apply to this scene
-        info['broad_phase'] = None if m.value < 0 else {
+        info['broad_phase'] = None if m.value < 0 or m.value > 3 else {
             'source_kind': ('point', 'box', 'focused', 'bundles')[m.value], 'grid': g.value, 'registers': r.value,
             'blocks_per_sm': p.value}
+        # sorted mesh path (csrc/xrt_meshsort.cuh) instead of the fused kernel for launches above 2^21 rays
+        info['mesh_sort'] = None if m.value != 4 else {
+            'coarse': {'grid': g.value, 'registers': r.value & 0xffff, 'blocks_per_sm': p.value & 0xff},
+            'refine_registers': r.value >> 16, 'bins': p.value >> 8}
         return info
 
 
