@@ -440,7 +440,7 @@ int xrt_launch_info(XrtScene *scene, int32_t *grid, int32_t *block, int32_t *reg
    mode = 4: the scene takes the sorted mesh path instead (k_mesh_coarse -> counting sort by hit location ->
    k_mesh_refine, csrc/xrt_meshsort.cuh): grid / low 16 bits of regs / low 8 bits of blocks_per_sm describe
    k_mesh_coarse, the high 16 bits of regs are the registers of k_mesh_refine and blocks_per_sm >> 8 is the
-   number of spatial bins. */
+   number of spatial bins.  mode = 5: the broad phase of a mosaic crystal's crystallite scan (k_mosaic32). */
 int xrt_launch_info_cull(XrtScene *scene, int32_t *mode, int32_t *grid, int32_t *regs, int32_t *blocks_per_sm);
 
 #ifdef __cplusplus

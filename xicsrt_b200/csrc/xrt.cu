@@ -61,6 +61,9 @@ struct XrtScene {
     // FP32 broad phase (k_cull32): -1 = does not apply to this scene, else CULL_*
     int cull_mode = -1;
     Cull32Par cull;
+    // FP32 broad phase of a mosaic crystal's crystallite scan (k_mosaic32): -1 = does not apply, else CULL_*
+    int mosaic32_mode = -1;
+    Mosaic32Par mosaic32;
     uint32_t *list_ids = nullptr;   // id list between k_cull32 and k_trace (stream-ordered allocation, grown on demand)
     uint32_t *list_counts = nullptr;
     uint64_t list_ids_cap = 0, list_counts_cap = 0;
@@ -401,6 +404,92 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         const bool rock_ok = (o.rocking_type == XRT_ROCK_GAUSS && o.rock_inv_two_sigma2 > 0.0 && std::isfinite(o.rock_inv_two_sigma2)) ||
                              (o.rocking_type == XRT_ROCK_STEP && o.rocking_fwhm >= 0.0 && std::isfinite(o.rocking_fwhm));
         const bool wave_ok = !s->lazy_wavelength || src.wave == XRT_WAVE_NORMAL || src.wave == XRT_WAVE_CONST;
+        // parameters of the FP32 broad phases (k_cull32 for a Bragg crystal, k_mosaic32 for a mosaic crystal): first optic,
+        // isotropic cone from a point / uniform box / plasma voxel, constant or normal line.  Returns the CULL_* source
+        // kind, or -1 when the phase does not apply; fills s->cull.
+        auto fill_cull32 = [&](double t2) -> int {
+            const bool line_ok = src.wave == XRT_WAVE_NORMAL || src.wave == XRT_WAVE_CONST;
+            if (!(s->split == 0 && line_ok && src.cone == XRT_CONE_ISOTROPIC && src.spatial == XRT_SPATIAL_UNIFORM &&
+                  src.n_sightlines == 0 && std::fabs(src.wave_par[0] * o.inv_two_d) >= 0.1 &&
+                  std::getenv("XRT_NO_BROAD32") == nullptr))
+                return -1;
+            Cull32Par &K = s->cull;
+            std::memset(&K, 0, sizeof(K));
+            const double r2 = o.radius * o.radius;
+            const bool point = (s->known & KN_POINT_SOURCE) != 0;
+            const int mode = src.kind == XRT_SRC_BUNDLES ? CULL_BUNDLES
+                           : src.kind == XRT_SRC_FOCUSED ? CULL_FOCUSED : (point ? CULL_POINT : CULL_BOX);
+            // farthest source point from the centre of curvature (box corners); bundles are tested per ray
+            double ll_max = 0.0;
+            for (int c8 = 0; c8 < 8; ++c8) {
+                double p[3];
+                for (int a = 0; a < 3; ++a) {
+                    p[a] = src.origin[a];
+                    for (int e = 0; e < 3; ++e)
+                        p[a] += (((c8 >> e) & 1) ? 0.5 : -0.5) * src.extent[e] * src.orient[3 * e + a];
+                }
+                const double dx = o.center[0] - p[0], dy = o.center[1] - p[1], dz = o.center[2] - p[2];
+                ll_max = std::fmax(ll_max, dx * dx + dy * dy + dz * dz);
+            }
+            if (mode == CULL_BUNDLES || ll_max <= 4.0 * r2) {
+                K.one_m_cos = (float)(1.0 - src.cone_par[0]);
+                for (int i = 0; i < 9; ++i) K.basis[i] = (float)src.axis_basis[i];
+                for (int i = 0; i < 9; ++i) K.R[i] = (float)src.orient[i];
+                for (int i = 0; i < 3; ++i) {
+                    K.Lb[i] = (float)(o.center[i] - src.origin[i]);
+                    K.Tb[i] = (float)(src.target[i] - src.origin[i]);
+                    K.ext[i] = (float)src.extent[i];
+                    K.xz[i] = (float)(src.orient[i] + src.orient[6 + i]);
+                    K.vel[i] = (float)src.velocity_c[i];
+                    K.C[i] = o.center[i];
+                    K.T[i] = src.target[i];
+                }
+                for (int i = 0; i < 3; ++i) {      // point source: basis rows dotted with C - O and with v / c
+                    double mi = 0.0, mvi = 0.0;
+                    for (int a = 0; a < 3; ++a) {
+                        mi += src.axis_basis[3 * i + a] * (o.center[a] - src.origin[a]);
+                        mvi += src.axis_basis[3 * i + a] * src.velocity_c[a];
+                    }
+                    K.m[i] = (float)mi;
+                    K.mv[i] = (float)mvi;
+                }
+                K.ll = (float)ll_max;              // point source: the one value of |C - O|^2
+                K.r2 = (float)r2;
+                K.inv_r2 = (float)(1.0 / r2);
+                K.inv_r = (float)(1.0 / o.radius);
+                K.lam0 = (float)src.wave_par[0];
+                K.normal_line = src.wave == XRT_WAVE_NORMAL ? 1 : 0;
+                K.sig = K.normal_line ? (float)src.wave_par[1] : 0.0f;
+                K.inv_two_d = (float)o.inv_two_d;
+                K.t2 = (float)t2;
+                // approximate-deviate term: 2e-3 sigma / 2d (per bundle for a plasma); rounding of the exact path 1e-9
+                const double dev = K.normal_line ? 2e-3 * std::fabs(src.wave_par[1]) * std::fabs(o.inv_two_d) : 0.0;
+                K.err_sig = K.normal_line ? (float)(2e-3 * std::fabs(o.inv_two_d)) : 0.0f;
+                K.err = (float)((mode == CULL_BUNDLES ? 0.0 : dev) + 1e-9 +
+                                (mode == CULL_POINT ? 2e-5 * std::fmax(1.0, ll_max / r2) : 0.0));
+                K.moving = (src.velocity_c[0] != 0.0 || src.velocity_c[1] != 0.0 || src.velocity_c[2] != 0.0) ? 1 : 0;
+                // second stage: crystal bounds (a ray outside |x| < hx, |y| < hy is lost at the crystal whatever else
+                // the optic checks) and the second pre-test level with the rocking-curve uniform
+                const uint32_t xy = XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE;
+                K.bounds_xy = ((o.flags & xy) == xy) ? 1 : 0;
+                K.convex = (o.flags & XRT_F_CONVEX) ? 1 : 0;
+                K.gauss = o.rocking_type == XRT_ROCK_GAUSS ? 1 : 0;
+                for (int i = 0; i < 3; ++i) {
+                    K.Ob[i] = (float)(src.origin[i] - o.origin[i]);
+                    K.ox[i] = (float)o.orient[i];
+                    K.oy[i] = (float)o.orient[3 + i];
+                    K.Oc[i] = o.origin[i];
+                }
+                K.hx = (float)o.half_size[0];
+                K.hy = (float)o.half_size[1];
+                K.lg_refl = (float)std::log2(o.reflectivity);
+                K.two_sigma2 = (float)o.rock_two_sigma2;
+                // (a step curve has no second level; the bounds test alone does not pay for the re-pack: measured)
+                K.stage2 = (K.gauss && std::getenv("XRT_NO_STAGE2") == nullptr) ? 1 : 0;
+                return mode;
+            }
+            return -1;
+        };
         if (o.shape == XRT_SHAPE_SPHERE && o.interact == XRT_INTERACT_CRYSTAL && (o.flags & XRT_F_CHECK_BRAGG) &&
             !(o.flags & XRT_F_TRACE_LOCAL) && rock_ok && wave_ok && o.radius > 0.0 && std::isfinite(o.inv_two_d) &&
             !(s->features & FT_MESH) && std::getenv("XRT_NO_CULL") == nullptr) {
@@ -416,86 +505,10 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
             // |C - O| ~ R; the margin is 2e-5, scaled with |C - O|^2 / R^2 (per ray where the origin varies), and
             // the phase is left off for a source farther than 2 R from the centre of curvature and for Bragg angles
             // below 6 degrees, where thc -> sI amplifies the error of thc^2 by 1 / (2 sI).
-            const bool line_ok = src.wave == XRT_WAVE_NORMAL || src.wave == XRT_WAVE_CONST;
-            if (s->split == 0 && line_ok && src.cone == XRT_CONE_ISOTROPIC && src.spatial == XRT_SPATIAL_UNIFORM &&
-                src.n_sightlines == 0 && std::fabs(src.wave_par[0] * o.inv_two_d) >= 0.1 &&
-                std::getenv("XRT_NO_BROAD32") == nullptr) {
-                Cull32Par &K = s->cull;
-                std::memset(&K, 0, sizeof(K));
-                const double r2 = o.radius * o.radius;
-                const bool point = (s->known & KN_POINT_SOURCE) != 0;
-                const int mode = src.kind == XRT_SRC_BUNDLES ? CULL_BUNDLES
-                               : src.kind == XRT_SRC_FOCUSED ? CULL_FOCUSED : (point ? CULL_POINT : CULL_BOX);
-                // farthest source point from the centre of curvature (box corners); bundles are tested per ray
-                double ll_max = 0.0;
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    double p[3];
-                    for (int a = 0; a < 3; ++a) {
-                        p[a] = src.origin[a];
-                        for (int e = 0; e < 3; ++e)
-                            p[a] += (((c8 >> e) & 1) ? 0.5 : -0.5) * src.extent[e] * src.orient[3 * e + a];
-                    }
-                    const double dx = o.center[0] - p[0], dy = o.center[1] - p[1], dz = o.center[2] - p[2];
-                    ll_max = std::fmax(ll_max, dx * dx + dy * dy + dz * dz);
-                }
-                if (mode == CULL_BUNDLES || ll_max <= 4.0 * r2) {
-                    K.one_m_cos = (float)(1.0 - src.cone_par[0]);
-                    for (int i = 0; i < 9; ++i) K.basis[i] = (float)src.axis_basis[i];
-                    for (int i = 0; i < 9; ++i) K.R[i] = (float)src.orient[i];
-                    for (int i = 0; i < 3; ++i) {
-                        K.Lb[i] = (float)(o.center[i] - src.origin[i]);
-                        K.Tb[i] = (float)(src.target[i] - src.origin[i]);
-                        K.ext[i] = (float)src.extent[i];
-                        K.xz[i] = (float)(src.orient[i] + src.orient[6 + i]);
-                        K.vel[i] = (float)src.velocity_c[i];
-                        K.C[i] = o.center[i];
-                        K.T[i] = src.target[i];
-                    }
-                    for (int i = 0; i < 3; ++i) {      // point source: basis rows dotted with C - O and with v / c
-                        double mi = 0.0, mvi = 0.0;
-                        for (int a = 0; a < 3; ++a) {
-                            mi += src.axis_basis[3 * i + a] * (o.center[a] - src.origin[a]);
-                            mvi += src.axis_basis[3 * i + a] * src.velocity_c[a];
-                        }
-                        K.m[i] = (float)mi;
-                        K.mv[i] = (float)mvi;
-                    }
-                    K.ll = (float)ll_max;              // point source: the one value of |C - O|^2
-                    K.r2 = (float)r2;
-                    K.inv_r2 = (float)(1.0 / r2);
-                    K.inv_r = (float)(1.0 / o.radius);
-                    K.lam0 = (float)src.wave_par[0];
-                    K.normal_line = src.wave == XRT_WAVE_NORMAL ? 1 : 0;
-                    K.sig = K.normal_line ? (float)src.wave_par[1] : 0.0f;
-                    K.inv_two_d = (float)o.inv_two_d;
-                    K.t2 = (float)w.cull_t2;
-                    // approximate-deviate term: 2e-3 sigma / 2d (per bundle for a plasma); rounding of the exact path 1e-9
-                    const double dev = K.normal_line ? 2e-3 * std::fabs(src.wave_par[1]) * std::fabs(o.inv_two_d) : 0.0;
-                    K.err_sig = K.normal_line ? (float)(2e-3 * std::fabs(o.inv_two_d)) : 0.0f;
-                    K.err = (float)((mode == CULL_BUNDLES ? 0.0 : dev) + 1e-9 +
-                                    (mode == CULL_POINT ? 2e-5 * std::fmax(1.0, ll_max / r2) : 0.0));
-                    K.moving = (src.velocity_c[0] != 0.0 || src.velocity_c[1] != 0.0 || src.velocity_c[2] != 0.0) ? 1 : 0;
-                    // second stage: crystal bounds (a ray outside |x| < hx, |y| < hy is lost at the crystal whatever else
-                    // the optic checks) and the second pre-test level with the rocking-curve uniform
-                    const uint32_t xy = XRT_F_CHECK_SIZE | XRT_F_HAS_XSIZE | XRT_F_HAS_YSIZE;
-                    K.bounds_xy = ((o.flags & xy) == xy) ? 1 : 0;
-                    K.convex = (o.flags & XRT_F_CONVEX) ? 1 : 0;
-                    K.gauss = o.rocking_type == XRT_ROCK_GAUSS ? 1 : 0;
-                    for (int i = 0; i < 3; ++i) {
-                        K.Ob[i] = (float)(src.origin[i] - o.origin[i]);
-                        K.ox[i] = (float)o.orient[i];
-                        K.oy[i] = (float)o.orient[3 + i];
-                        K.Oc[i] = o.origin[i];
-                    }
-                    K.hx = (float)o.half_size[0];
-                    K.hy = (float)o.half_size[1];
-                    K.lg_refl = (float)std::log2(o.reflectivity);
-                    K.two_sigma2 = (float)o.rock_two_sigma2;
-                    // (a step curve has no second level; the bounds test alone does not pay for the re-pack: measured)
-                    K.stage2 = (K.gauss && std::getenv("XRT_NO_STAGE2") == nullptr) ? 1 : 0;
-                    s->cull_mode = mode;
-                    d.kn32[0] = 1.0f;       // reported to the caller: the broad phase is in use
-                }
+            const int mode32 = fill_cull32(w.cull_t2);
+            if (mode32 >= 0) {
+                s->cull_mode = mode32;
+                d.kn32[0] = 1.0f;       // reported to the caller: the broad phase is in use
             }
             // (mosaic crystals: below)
             // eager normal line (plasma bundles, Doppler shift) with no optic before the crystal: defer the exact deviate
@@ -505,7 +518,7 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
         // Analytic shape traced in global coordinates, Bragg test on, Gaussian or step rocking curve; the layer index
         // travels in the top byte of the queue's id word.
         if (o.interact == XRT_INTERACT_MOSAIC && (o.flags & XRT_F_CHECK_BRAGG) && rock_ok && !(o.flags & XRT_F_TRACE_LOCAL) &&
-            o.shape != XRT_SHAPE_MESH && o.mosaic_depth >= 1 && o.mosaic_depth <= 255 && std::isfinite(o.inv_two_d) &&
+            o.shape != XRT_SHAPE_MESH && o.mosaic_depth >= 1 && o.mosaic_depth <= 127 && std::isfinite(o.inv_two_d) &&
             std::isfinite(o.mosaic_sin_sigma) && std::getenv("XRT_NO_CULL") == nullptr) {
             XrtOpticDesc &w = d.optics[s->split];
             const double edge = o.rocking_type == XRT_ROCK_GAUSS ? std::sqrt(40.0 / o.rock_inv_two_sigma2) : 0.5 * o.rocking_fwhm;
@@ -513,11 +526,26 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
             w.mosaic_t2 = t * t;
             w.mosaic_err = 2e-6;
             w.mosaic_scan = 1;
+            // FP32 broad phase of the crystallite scan (k_mosaic32): concave or convex sphere as first optic, the
+            // source conditions of k_cull32 (no plasma bundles), lean mosaic feature set, no cutoff prefilter, wavelength
+            // not needed before the crystal
+            if (o.shape == XRT_SHAPE_SPHERE && s->features == FT_MOSAICLEAN && o.mosaic_depth <= (1 << kMosaicTagBits) &&
+                !(o.flags & XRT_F_MOSAIC_CUTOFF) && s->lazy_wavelength && wave_ok && o.radius > 0.0 &&
+                src.kind != XRT_SRC_BUNDLES && std::getenv("XRT_NO_MOSAIC32") == nullptr && fill_cull32(0.0) >= 0) {
+                s->mosaic32_mode = fill_cull32(0.0);
+                Mosaic32Par &M = s->mosaic32;
+                M.sin_sigma = (float)o.mosaic_sin_sigma;
+                M.err = (float)w.mosaic_err;
+                M.t2 = (float)w.mosaic_t2;
+                M.two_sigma2 = (float)o.rock_two_sigma2;
+                M.lg_refl = (float)std::log2(o.reflectivity);
+                M.depth = o.mosaic_depth;
+                M.gauss = o.rocking_type == XRT_ROCK_GAUSS ? 1 : 0;
+            }
         }
     }
     return XRT_OK;
 }
-
 extern "C" int xrt_scene_create(const XrtSceneDesc *desc, XrtScene **scene) {
     if (!desc || !scene) return fail(XRT_EINVAL, "null argument");
     *scene = nullptr;
@@ -612,6 +640,19 @@ extern "C" int xrt_launch_info_cull(XrtScene *s, int32_t *mode, int32_t *grid, i
         if (grid) *grid = s->sm_count * bps;
         if (regs) *regs = fa.numRegs | (fr.numRegs << 16);     // refinement kernel's registers in the high half
         if (blocks_per_sm) *blocks_per_sm = bps | (s->mesh_bins << 8);
+        return XRT_OK;
+    }
+    if (s->cull_mode < 0 && s->mosaic32_mode >= 0) {
+        // mode 5: the mosaic broad phase k_mosaic32 in front of k_trace
+        Mosaic32Kernel mk = mosaic32_kernel(s->mosaic32_mode, false);
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, mk));
+        int bps = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, mk, kBlock, 0));
+        if (mode) *mode = 5;
+        if (grid) *grid = s->sm_count * bps;
+        if (regs) *regs = fa.numRegs;
+        if (blocks_per_sm) *blocks_per_sm = bps;
         return XRT_OK;
     }
     if (mode) *mode = s->cull_mode;
@@ -740,11 +781,12 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
     const int lazy_bits = s->lazy_wavelength | (s->need_wavelength << 1) | (s->defer_wavelength << 2);
     const uint64_t cap_blocks = (uint64_t)s->sm_count * (uint64_t)bps;
 
-    const bool two_kernels = s->cull_mode >= 0 && ray_count >= cull_min_rays();
+    const bool mosaic32 = s->mosaic32_mode >= 0 && ray_count >= cull_min_rays();
+    const bool two_kernels = (s->cull_mode >= 0 && ray_count >= cull_min_rays()) || mosaic32;
     const bool mesh_sorted = !two_kernels && s->mesh_sort && ray_count >= mesh_sort_min_rays() && !getenv("XRT_NO_MESH_SORT");
     // a launch covers at most 2^30 ids (32-bit offsets in the id list, 4 GB of list at most); 2^27 on the sorted mesh
     // path (27-bit offsets beside the face tag)
-    const uint64_t max_launch = two_kernels ? (1ull << 30) : (mesh_sorted ? kMeshMaxLaunch : ~0ull);
+    const uint64_t max_launch = mosaic32 ? (1ull << (32 - kMosaicTagBits)) : two_kernels ? (1ull << 30) : (mesh_sorted ? kMeshMaxLaunch : ~0ull);
     for (uint64_t done = 0; done < ray_count; done += max_launch) {
         const uint64_t n = ray_count - done < max_launch ? ray_count - done : max_launch;
         const uint64_t begin = ray_begin + done;
@@ -755,11 +797,30 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
             const uint64_t n_groups = (n + 31) / 32;
             uint64_t gpr = (n_groups + (uint64_t)s->sm_count * 384 - 1) / ((uint64_t)s->sm_count * 384);
             if (gpr < 32) gpr = 32;
+            if (mosaic32 && gpr < 128) gpr = 128;   // the scan of a region is drained at its end: long regions
             gpr = (gpr + 3) & ~3ull;            // a multiple of the broad phase's groups per pass: only the last region is ragged
             const uint32_t cap = (uint32_t)(gpr * 32);
             const uint32_t n_regions = (uint32_t)((n + cap - 1) / cap);
             rc = ensure_list(s, (uint64_t)n_regions * cap, n_regions, st);
             if (rc != XRT_OK) return rc;
+            if (mosaic32) {
+                Mosaic32Kernel mk = mosaic32_kernel(s->mosaic32_mode, hist);
+                int mbps = 0;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mbps, mk, kBlock, 0));
+                if (mbps < 1) return fail(XRT_ECUDA, "mosaic broad-phase kernel does not fit on an SM");
+                const uint64_t mwant = ((uint64_t)n_regions + kBlock / 32 - 1) / (kBlock / 32);
+                const uint64_t mcap = (uint64_t)s->sm_count * (uint64_t)mbps;
+                Cull32Out lst = {s->list_ids, s->list_counts, n_regions, cap, s->list_next + s->list_phase,
+                                 s->list_next + (s->list_phase ^ 1)};
+                s->list_phase ^= 1;
+                mk<<<(int)(mwant < mcap ? mwant : mcap), kBlock, 0, st>>>(s->cull, s->mosaic32, s->dev.source, pk, stream_id, begin, n, lst, *out);
+                CU(cudaGetLastError());
+                list = {s->list_ids, s->list_counts, n_regions, cap, (uint32_t)kMosaicTagBits};
+                const uint64_t want = ((uint64_t)list.n_regions + kBlock / 32 - 1) / (kBlock / 32);
+                kern<<<(int)(want < cap_blocks ? want : cap_blocks), kBlock, smem, st>>>(s->dev, pk, stream_id, begin, n, *out, list, s->split, lazy_bits);
+                CU(cudaGetLastError());
+                continue;
+            }
             CullKernel ck = cull_kernel(s->cull_mode, hist);
             int cbps = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cbps, ck, kBlock, 0));
@@ -772,7 +833,7 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
             s->list_phase ^= 1;
             ck<<<(int)(want < ccap ? want : ccap), kBlock, 0, st>>>(s->cull, s->dev.source, pk, stream_id, begin, n, lst, *out);
             CU(cudaGetLastError());
-            list = {s->list_ids, s->list_counts, n_regions, cap};
+            list = {s->list_ids, s->list_counts, n_regions, cap, 0u};
         } else if (mesh_sorted) {
             // regions of consecutive ids for k_mesh_coarse, as for the broad phase
             const uint64_t n_groups = (n + 31) / 32;
@@ -815,7 +876,7 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
         } else {
             const uint64_t n_groups = (n + 31) / 32;
             if (n_groups > 0xffffffffull) return fail(XRT_EINVAL, "ray_count too large for one launch");
-            list = {nullptr, nullptr, (uint32_t)n_groups, 32u};
+            list = {nullptr, nullptr, (uint32_t)n_groups, 32u, 0u};
         }
         const uint64_t want = ((uint64_t)list.n_regions + kBlock / 32 - 1) / (kBlock / 32);
         const int grid = (int)(want < cap_blocks ? want : cap_blocks);

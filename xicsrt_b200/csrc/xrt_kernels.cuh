@@ -46,10 +46,13 @@ constexpr unsigned kFull = 0xffffffffu;
 // region).  List mode: region r holds counts[r] surviving id offsets of its range at ids[r * cap ...], written by
 // k_cull32.  Warp w takes regions w, w + n_warps, ... in both modes: no atomics, and the order in which a warp
 // meets its rays does not depend on scheduling.
+// tag_bits > 0: a list entry is (id offset << tag_bits) | tag; the mosaic broad phase passes the first crystallite
+// layer it could not reject this way.
 struct IdList {
     const uint32_t *ids;
     const uint32_t *counts;
     uint32_t n_regions, cap;
+    uint32_t tag_bits;
 };
 
 // U groups of <= 32 ids are fetched one pass ahead of their use, so that the list loads (L2 / DRAM latency) overlap the
@@ -58,7 +61,7 @@ template <int U>
 struct IdCursor {
     const uint32_t *ids, *counts;
     uint64_t base, n_rays;
-    uint32_t reg, n_regions, cap, pos, cnt, step;
+    uint32_t reg, n_regions, cap, pos, cnt, step, tag_bits;
     uint64_t pbase[U];    // pending ids of this lane: region base + poff (the sum is formed when the id is handed out, so
     uint32_t poff[U];     // that the list load stays in flight until then)
     bool pvalid[U];
@@ -103,7 +106,7 @@ struct IdCursor {
     }
     __device__ __forceinline__ void init(const IdList &L, uint64_t ray_begin, uint64_t ray_count, uint32_t warp_global,
                                          uint32_t n_warps, unsigned lane) {
-        ids = L.ids; counts = L.counts; n_regions = L.n_regions; cap = L.cap;
+        ids = L.ids; counts = L.counts; n_regions = L.n_regions; cap = L.cap; tag_bits = L.tag_bits;
         base = ray_begin; n_rays = ray_count;
         reg = warp_global; step = n_warps; pos = 0;
         load();
@@ -114,6 +117,16 @@ struct IdCursor {
     __device__ __forceinline__ void take(unsigned lane, uint64_t (&id)[U], bool (&valid)[U]) {
 #pragma unroll
         for (int j = 0; j < U; ++j) { id[j] = pbase[j] + poff[j]; valid[j] = pvalid[j]; }
+        fetch(lane);
+    }
+    // tagged entries: id and tag
+    __device__ __forceinline__ void take(unsigned lane, uint64_t (&id)[U], bool (&valid)[U], uint32_t (&tag)[U]) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            id[j] = pbase[j] + (poff[j] >> tag_bits);
+            tag[j] = poff[j] & ((1u << tag_bits) - 1u);
+            valid[j] = pvalid[j];
+        }
         fetch(lane);
     }
 };
@@ -372,6 +385,39 @@ __device__ __forceinline__ void stage_b(const XrtSceneDesc &sc, const XrtOpticDe
 // are re-packed with new rays.  While the queues drain at the end of the launch the batch runs to completion.
 constexpr int kMinScan = XRT_MIN_SCAN;
 constexpr uint64_t kIdMask = (1ull << 56) - 1ull;
+// queue word of a mosaic ray: id (56 bits) | layer (7 bits) | resumed (1 bit: the ray has been in stage S before, its
+// wavelength travels with it)
+constexpr uint64_t kResumed = 1ull << 63;
+
+// FP32 pre-test of one crystallite layer (b = the layer's Philox block): true = the layer provably does not reflect
+// the ray.  dr0, dr1, dn = D.r_0, D.r_1, D.n for the unit direction D and the basis (r_0, r_1, n) of mosaic_normal;
+// sB = sin(theta_B); err = margin for everything that is not exact here.
+struct MosaicPre {
+    float s32, t2, two_sigma2, lg_refl;
+    bool gauss;
+};
+__device__ __forceinline__ bool mosaic_pretest(const uint4 b, const MosaicPre &M, float dr0, float dr1, float dn, float sB, float err) {
+    const uint32_t na = ~b.x;
+    const float omu = fmaf((float)na, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // 1 - u1
+    const float rr = sqrt_approx(-1.3862943611198906f * lg2_approx(omu));                 // sqrt(-2 ln(1 - u1))
+    const float ang = 6.283185307179586f * (__uint_as_float(0x3f800000u | ((b.y & 0xffffffu) >> 1)) - 1.5f);
+    const float x = -M.s32 * rr * __cosf(ang), y = -M.s32 * rr * __sinf(ang);
+    const float t = fmaf(x, dr0, fmaf(y, dr1, dn));
+    const float sI = fabsf(t) * rsqrt_approx(fmaf(x, x, fmaf(y, y, 1.0f)));
+    const float gap = fabsf(sB - sI);
+    const float diff = gap - err;
+    const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
+    bool rej = (diff > 0.0f) & (diff * diff > M.t2 * c2);
+    if (M.gauss) {
+        const float u = __uint_as_float(0x3f800000u | (b.z >> 9)) - 1.0f;          // top 23 bits: u32 <= u
+        const float lim = 0.6931471805599453f * (M.lg_refl - lg2_approx(u));       // >= ln(reflectivity / u)
+        const float bound = fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * M.two_sigma2;
+        rej |= (diff > 0.0f) & (diff * diff > bound * c2) & (lim == lim);
+    }
+    // 1 - u1 below 2^-16 (|z| > 4.7): its 32-bit truncation is not precise enough for the radius, the layer is
+    // decided exactly (1.5e-5 of the layers)
+    return rej & (na >= 65536u);
+}
 
 template <uint32_t FT, uint32_t KN, bool HIST>
 __device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOpticDesc &ops, const XrtOutputs &out,
@@ -386,11 +432,13 @@ __device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOp
     r.w = 1.0;
     uint64_t id = 0;
     int layer = 0;
+    bool fresh = false;
     if (active) {
         const double *p = q1 + n1 + c.lane;
         const uint64_t word = (uint64_t)__double_as_longlong(p[0]);
         id = word & kIdMask;
-        layer = (int)(word >> 56);
+        layer = (int)((word >> 56) & 0x7fu);
+        fresh = (word & kResumed) == 0;
         r.o = v3(p[1 * P], p[2 * P], p[3 * P]);
         r.d = v3(p[4 * P], p[5 * P], p[6 * P]);
         r.w = p[7 * P];
@@ -401,8 +449,9 @@ __device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOp
     const uint32_t flags = flags_of<KN>(ops);
     const V3 n = analytic_normal<FT, KN>(ops, r.o);
     bool scanning = active;
-    if (active && layer == 0) {
-        // first visit: the wavelength (lazy / deferred, as stage B) and the optional prefilter on the nominal normal
+    if (active && fresh) {
+        // first visit (at the layer the broad phase k_mosaic32 found, else layer 0): the wavelength (lazy / deferred, as
+        // stage B) and the optional prefilter on the nominal normal
         if (lazy && need_wave) {
             SrcLocal L;
             source_local<0, KN>(sc.source, id, L);
@@ -427,10 +476,13 @@ __device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOp
         dn = (float)(dot(r.d, n) * il);
         sB = (float)(r.w * ops.inv_two_d);
     }
-    const float s32 = (float)ops.mosaic_sin_sigma, err = (float)ops.mosaic_err, t2 = (float)ops.mosaic_t2;
-    const bool gauss = ops.rocking_type != XRT_ROCK_STEP;
-    const float two_sigma2 = (float)ops.rock_two_sigma2;
-    const float lg_refl = lg2_approx((float)ops.reflectivity);
+    const float err = (float)ops.mosaic_err;
+    MosaicPre MP;
+    MP.s32 = (float)ops.mosaic_sin_sigma;
+    MP.t2 = (float)ops.mosaic_t2;
+    MP.gauss = ops.rocking_type != XRT_ROCK_STEP;
+    MP.two_sigma2 = (float)ops.rock_two_sigma2;
+    MP.lg_refl = lg2_approx((float)ops.reflectivity);
     const int depth = ops.mosaic_depth;
     const int min_scan = drain ? 1 : kMinScan;
     bool cand = false, reflected = false;
@@ -438,27 +490,7 @@ __device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOp
 
     // FP32 pre-test of one layer: true = the layer provably does not reflect the ray
     auto pretest = [&](int lay) -> bool {
-        const uint4 b = dr.raw(site_optic(split, lay, 1));
-        const uint32_t na = ~b.x;
-        const float omu = fmaf((float)na, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // 1 - u1
-        const float rr = sqrt_approx(-1.3862943611198906f * lg2_approx(omu));                 // sqrt(-2 ln(1 - u1))
-        const float ang = 6.283185307179586f * (__uint_as_float(0x3f800000u | ((b.y & 0xffffffu) >> 1)) - 1.5f);
-        const float x = -s32 * rr * __cosf(ang), y = -s32 * rr * __sinf(ang);
-        const float t = fmaf(x, dr0, fmaf(y, dr1, dn));
-        const float sI = fabsf(t) * rsqrt_approx(fmaf(x, x, fmaf(y, y, 1.0f)));
-        const float gap = fabsf(sB - sI);
-        const float diff = gap - err;
-        const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
-        bool rej = (diff > 0.0f) & (diff * diff > t2 * c2);
-        if (gauss) {
-            const float u = __uint_as_float(0x3f800000u | (b.z >> 9)) - 1.0f;          // top 23 bits: u32 <= u
-            const float lim = 0.6931471805599453f * (lg_refl - lg2_approx(u));        // >= ln(reflectivity / u)
-            const float bound = fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * two_sigma2;
-            rej |= (diff > 0.0f) & (diff * diff > bound * c2) & (lim == lim);
-        }
-        // 1 - u1 below 2^-16 (|z| > 4.7): its 32-bit truncation is not precise enough for the radius, the layer is
-        // decided exactly (1.5e-5 of the layers)
-        return rej & (na >= 65536u);
+        return mosaic_pretest(dr.raw(site_optic(split, lay, 1)), MP, dr0, dr1, dn, sB, err);
     };
 
     for (;;) {
@@ -511,7 +543,7 @@ __device__ __forceinline__ void stage_mosaic(const XrtSceneDesc &sc, const XrtOp
     const unsigned ms = __ballot_sync(kFull, scanning);
     if (scanning) {
         double *p = q1 + n1 + __popc(ms & c.lt_mask);
-        p[0] = __longlong_as_double((long long)(id | ((uint64_t)layer << 56)));
+        p[0] = __longlong_as_double((long long)(id | ((uint64_t)layer << 56) | kResumed));
         p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
         p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
         p[7 * P] = r.w;
@@ -766,7 +798,11 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
         } else {
             uint64_t id1[1];
             bool valid1[1];
-            if constexpr (!SPECTRO) cur.take(c.lane, id1, valid1);
+            uint32_t tag1[1] = {0u};
+            if constexpr (!SPECTRO) {
+                if constexpr ((FT & FT_MOSAIC) != 0) cur.take(c.lane, id1, valid1, tag1);
+                else cur.take(c.lane, id1, valid1);
+            }
             const uint64_t id = id1[0];
             const bool valid = valid1[0];
             PhiloxDraws dr;
@@ -847,7 +883,8 @@ k_trace(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxK
             const unsigned m = __ballot_sync(kFull, cand);
             if (cand) {
                 double *p = q1 + n1 + __popc(m & c.lt_mask);
-                p[0] = __longlong_as_double((long long)id);
+                // mosaic variants: the layer at which stage S starts (k_mosaic32 rejected the layers before it)
+                p[0] = __longlong_as_double((long long)(id | ((uint64_t)tag1[0] << 56)));
                 p[1 * P] = r.o.x; p[2 * P] = r.o.y; p[3 * P] = r.o.z;
                 p[4 * P] = r.d.x; p[5 * P] = r.d.y; p[6 * P] = r.d.z;
                 if constexpr (FT != 0) p[7 * P] = r.w;
@@ -942,6 +979,8 @@ struct Cull32Full {
     float dx, dy, dz, tca, thc;      // direction, sphere chord
     float px, py, pz;                // ray origin - crystal origin
     float gap, c2, err;              // Bragg pre-test quantities
+    float lx, ly, lz;                // sphere centre - ray origin
+    float sB;                        // sin(theta_B) of the ray's (approximate) wavelength
     bool usable;
 };
 
@@ -1067,6 +1106,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         full->dx = dx; full->dy = dy; full->dz = dz; full->tca = tca; full->thc = thc;
         full->px = Px; full->py = Py; full->pz = Pz;
         full->gap = gap; full->c2 = c2; full->err = err; full->usable = usable;
+        full->lx = Lx; full->ly = Ly; full->lz = Lz; full->sB = sB;
     }
     return usable & (diff > 0.0f) & (diff * diff > K.t2 * c2);
 }
@@ -1229,6 +1269,190 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
 }  // namespace xrt
 #include "xrt_meshsort.cuh"
 namespace xrt {
+
+// ---------------------------------------------------------------------------
+// FP32 broad phase of a spherical MOSAIC crystal as first optic (k_mosaic32)
+//
+// A HOPG-like crystal reflects a ray at the first of its mosaic_depth crystallite layers that satisfies Bragg's law
+// with its own random normal; ~97 % of the (ray, layer) pairs fail by many rocking-curve widths.  Stage S of k_trace
+// rejects them with an FP32 pre-test per layer (mosaic_pretest), but it does so inside the FP64 kernel: 128
+// registers, 16 warps per SM, 140 kB of code.  This kernel runs the same scan for every ray of the launch in a small
+// single-precision kernel of its own, with the ray generated in FP32 from its Philox blocks (cull32_ray):
+//
+//   feed   32 consecutive ids: direction, sphere chord, intersection point, crystal bounds (a ray farther outside
+//          than the rounding allows is lost at the crystal), the frame (n, r_0, r_1) of mosaic_normal at the point and
+//          the three dot products of the pre-test -> per-warp queue (offset, dr0, dr1, dn, sB, err)
+//   scan   every lane owns one queued ray and tests two layers per iteration; a lane whose ray is finished (first
+//          layer that cannot be rejected found, or all layers rejected = lost) takes the next ray from the queue, so
+//          the scan runs with nearly all lanes busy
+//
+// A ray with a candidate layer leaves as (id offset << 5 | layer) in the region's list; k_trace starts its exact FP64
+// scan at that layer.  Rays the single-precision geometry cannot judge (sphere missed or nearly so, deviate outside
+// the range of normal_approx, NaN) leave with layer 0.  Every FP32 quantity is within ~1e-6 of its FP64 value; the
+// margin err carries 2e-5 (x |C - O|^2 / R^2) + the approximate-deviate term + stage S's own 2e-6, so a layer rejected
+// here is rejected by the exact test as well and results are identical with the phase off (tests/test_gpu_scale.py).
+
+struct Mosaic32Par {
+    float sin_sigma, err, t2, two_sigma2, lg_refl;
+    int32_t depth, gauss;
+};
+
+#ifndef XRT_MOSAIC32_BLOCKS
+#define XRT_MOSAIC32_BLOCKS 4
+#endif
+constexpr int kMosaicTagBits = 5;          // layer index in a list entry: mosaic_depth <= 32
+
+template <int SRC, bool HIST>
+__global__ void __launch_bounds__(kBlock, XRT_MOSAIC32_BLOCKS)
+k_mosaic32(const __grid_constant__ Cull32Par K, const __grid_constant__ Mosaic32Par M, const __grid_constant__ XrtSourceDesc src,
+           const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id, const uint64_t ray_begin, const uint64_t ray_count,
+           const Cull32Out lst, const XrtOutputs out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr int kQ = 64;
+    __shared__ uint32_t s_off[kBlock / 32][kQ];
+    __shared__ float s_par[kBlock / 32][5][kQ];
+    uint32_t *q_off = s_off[threadIdx.x >> 5];
+    float(*q_par)[kQ] = s_par[threadIdx.x >> 5];
+    MosaicPre MP;
+    MP.s32 = M.sin_sigma;
+    MP.t2 = M.t2;
+    MP.two_sigma2 = M.two_sigma2;
+    MP.lg_refl = M.lg_refl;
+    MP.gauss = M.gauss != 0;
+    const int depth = M.depth;
+    const uint32_t stream = (uint32_t)stream_id;
+    unsigned long long n_src = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *lst.next_reset = 0u;
+    for (;;) {
+        uint32_t reg = 0;
+        if (lane == 0) reg = atomicAdd(lst.next, 1u);
+        reg = __shfl_sync(kFull, reg, 0);
+        if (reg >= lst.n_regions) break;
+        const uint64_t first = (uint64_t)reg * lst.cap;
+        const uint64_t left = ray_count - first;
+        const uint32_t n_here = left < (uint64_t)lst.cap ? (uint32_t)left : lst.cap;
+        const uint64_t id_first = ray_begin + first;
+        const uint32_t off_first = (uint32_t)first;
+        uint32_t *dst = lst.ids + first;
+        uint32_t kept = 0;
+        n_src += n_here;
+        int nq = 0;
+        uint32_t g = 0;
+        // the ray this lane is scanning
+        bool busy = false;
+        uint32_t off = 0;
+        int layer = 0;
+        float dr0 = 0.0f, dr1 = 0.0f, dn = 0.0f, sB = 0.0f, err = 0.0f;
+        for (;;) {
+            if (g < n_here && nq < 32) {
+                // ---- feed: 32 consecutive ids
+                const uint32_t o1 = g + lane;
+                const bool valid = o1 < n_here;
+                const uint64_t id = id_first + (valid ? o1 : 0u);
+                Cull32Full f;
+                cull32_ray<SRC, true>(K, src, pk, stream, (uint32_t)id, (uint32_t)(id >> 32), &f);
+                const float t = K.convex ? f.tca - f.thc : f.tca + f.thc;
+                // frame of mosaic_normal at the intersection point: n = (C - X) / R with C - X = L - t D
+                const float nx = (f.lx - t * f.dx) * K.inv_r, ny = (f.ly - t * f.dy) * K.inv_r, nz = (f.lz - t * f.dz) * K.inv_r;
+                float ax = ny, ay = nz - nx, az = -ny;                                          // r_0 ~ n x x + n x z
+                const float a2 = ax * ax + ay * ay + az * az;
+                // t is NaN when the chord is (sphere missed in FP32); a nearly degenerate frame (n along x + z) would
+                // amplify the rounding of n
+                const bool judged = f.usable && (t == t) && a2 > 0.01f;
+                bool outside = false;
+                if (K.bounds_xy) {
+                    const float X = fmaf(t, f.dx, f.px), Y = fmaf(t, f.dy, f.py), Z = fmaf(t, f.dz, f.pz);
+                    const float xl = X * K.ox[0] + Y * K.ox[1] + Z * K.ox[2];
+                    const float yl = X * K.oy[0] + Y * K.oy[1] + Z * K.oy[2];
+                    const float slack = fmaf(4e-7f, fabsf(f.tca) + fabsf(f.thc) + fabsf(f.px) + fabsf(f.py) + fabsf(f.pz), 1e-7f);
+                    outside = (fabsf(xl) > K.hx + slack) | (fabsf(yl) > K.hy + slack);
+                }
+                const bool lost = valid && judged && outside;
+                const bool scan = valid && judged && !outside;
+                const bool pass0 = valid && !judged;             // left to k_trace, from layer 0
+                if constexpr (HIST) {
+                    if (out.lost_count || out.lost_bits) {
+                        PhiloxDraws dr;
+                        dr.init(pk, stream_id, id, 0);
+                        emit_lost<true>(out, lane, lt_mask, dr, lost, id);
+                    }
+                }
+                const unsigned mp = __ballot_sync(kFull, pass0);
+                if (pass0) dst[kept + __popc(mp & lt_mask)] = (off_first + o1) << kMosaicTagBits;
+                kept += __popc(mp);
+                const unsigned ms = __ballot_sync(kFull, scan);
+                if (scan) {
+                    const float ia = rsqrt_approx(a2);
+                    ax *= ia; ay *= ia; az *= ia;
+                    float bx = ny * az - nz * ay, by = nz * ax - nx * az, bz = nx * ay - ny * ax;   // r_1 ~ n x r_0
+                    const float ib = rsqrt_approx(bx * bx + by * by + bz * bz);
+                    const int slot = nq + __popc(ms & lt_mask);
+                    q_off[slot] = o1;
+                    q_par[0][slot] = f.dx * ax + f.dy * ay + f.dz * az;
+                    q_par[1][slot] = (f.dx * bx + f.dy * by + f.dz * bz) * ib;
+                    q_par[2][slot] = f.dx * nx + f.dy * ny + f.dz * nz;
+                    q_par[3][slot] = f.sB;
+                    q_par[4][slot] = f.err + M.err;
+                }
+                nq += __popc(ms);
+                g += 32u;
+                __syncwarp();
+            }
+            // ---- refill: idle lanes take the last entries of the queue
+            {
+                const unsigned mi = __ballot_sync(kFull, !busy);
+                const int r = __popc(mi & lt_mask);
+                if (!busy && r < nq) {
+                    const int slot = nq - 1 - r;
+                    off = q_off[slot];
+                    dr0 = q_par[0][slot]; dr1 = q_par[1][slot]; dn = q_par[2][slot]; sB = q_par[3][slot]; err = q_par[4][slot];
+                    layer = 0;
+                    busy = true;
+                }
+                const int taken = __popc(mi);
+                nq -= taken < nq ? taken : nq;
+                __syncwarp();
+            }
+            if (!__ballot_sync(kFull, busy)) {
+                if (g >= n_here) break;          // region done: nothing queued, nothing being scanned
+                continue;
+            }
+            // ---- scan: two layers (independent chains; the second is wasted only when the first is a candidate)
+            bool found = false, gone = false;
+            if (busy) {
+                const uint64_t id = id_first + off;
+                const uint32_t lo = (uint32_t)id, hi = (uint32_t)(id >> 32);
+                const uint4 b0 = philox4x32_10(make_uint4(lo, hi, site_optic(0, layer, 1), stream), pk);
+                const uint4 b1 = philox4x32_10(make_uint4(lo, hi, site_optic(0, layer + 1, 1), stream), pk);
+                const bool rej0 = mosaic_pretest(b0, MP, dr0, dr1, dn, sB, err);
+                const bool rej1 = mosaic_pretest(b1, MP, dr0, dr1, dn, sB, err);
+                if (!rej0) found = true;
+                else if (layer + 1 >= depth) gone = true;
+                else if (!rej1) { layer += 1; found = true; }
+                else { layer += 2; gone = layer >= depth; }
+            }
+            if constexpr (HIST) {
+                if (out.lost_count || out.lost_bits) {
+                    PhiloxDraws dr;
+                    dr.init(pk, stream_id, id_first + off, 0);
+                    emit_lost<true>(out, lane, lt_mask, dr, gone, id_first + off);
+                }
+            }
+            const unsigned mf = __ballot_sync(kFull, found);
+            if (found) dst[kept + __popc(mf & lt_mask)] = ((off_first + off) << kMosaicTagBits) | (uint32_t)layer;
+            kept += __popc(mf);
+            if (found || gone) busy = false;
+        }
+        if (lane == 0) lst.counts[reg] = kept;
+    }
+    __shared__ unsigned long long s_src;
+    if (threadIdx.x == 0) s_src = 0ull;
+    __syncthreads();
+    if (lane == 0 && n_src) atomicAdd(&s_src, n_src);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_src && out.counts) atomicAdd((unsigned long long *)out.counts, s_src);
+}
 
 // ---------------------------------------------------------------------------
 // recording kernel: history of every element, optional counters / images

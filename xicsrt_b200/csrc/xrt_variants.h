@@ -39,6 +39,10 @@ XRT_DECLARE_VARIANT(full)
 
 CullKernel cull_kernel(int src_mode, bool hist);
 
+typedef void (*Mosaic32Kernel)(const Cull32Par, const Mosaic32Par, const XrtSourceDesc, const PhiloxKeys, const uint64_t,
+                               const uint64_t, const uint64_t, const Cull32Out, const XrtOutputs);
+Mosaic32Kernel mosaic32_kernel(int src_mode, bool hist);
+
 // sorted mesh path: the coarse-mesh kernel of the two feature sets that hold mesh optics
 typedef void (*MeshCoarseKernel)(const XrtSceneDesc, const PhiloxKeys, const uint64_t, const uint64_t, const uint64_t,
                                  const MeshSortOut, const XrtOutputs);

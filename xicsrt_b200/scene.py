@@ -425,6 +425,8 @@ class DeviceScene:
         info['mesh_sort'] = None if m.value != 4 else {
             'coarse': {'grid': g.value, 'registers': r.value & 0xffff, 'blocks_per_sm': p.value & 0xff},
             'refine_registers': r.value >> 16, 'bins': p.value >> 8}
+        # FP32 broad phase of a mosaic crystal's crystallite scan (k_mosaic32) in front of the fused kernel
+        info['mosaic_broad_phase'] = None if m.value != 5 else {'grid': g.value, 'registers': r.value, 'blocks_per_sm': p.value}
         return info
 
 
