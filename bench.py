@@ -601,8 +601,8 @@ def run_gpu_arm(args):
         roof['kernel_ms_per_step'] = 1e3 * t_kernel / args.steps
         try:
             prof = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
-            roof['traffic'] = prof['k_trace']['dram_bytes_per_launch']
-            roof['executed_ncu'] = prof['k_trace'].get('executed')
+            roof['traffic'] = prof['step']['dram_bytes_per_launch']
+            roof['executed_ncu'] = prof['step'].get('executed')
         except (OSError, KeyError, ValueError):
             pass
     hist_line = None
