@@ -102,8 +102,8 @@ typedef struct XrtMesh {
     const double *face_normals;  /* [n_faces][3]                                         */
     const double *face_geom;     /* [n_faces][9]: p0, p1 - p0, p2 - p0 (Moeller-Trumbore) */
     const double *face_area;     /* [n_faces]: |(p0 - p1) x (p0 - p2)| (area-sum inside test) */
-    const double *face_rec;      /* [n_faces][16]: p0, e1, e2, unit normal, area, pad -- one
-                                    128-byte record per face for the candidate-face test  */
+    const double *face_rec;      /* [n_faces][16]: p0, e1 x n, e2 x n, unit normal n, area, (index), (e1 x e2).n, pad --
+                                    one 128-byte record per face for the candidate-face test  */
     int32_t n_coarse_points, n_coarse_faces;   /* 0 when there is no coarse mesh         */
     const double *coarse_points;
     const int32_t *coarse_faces;
@@ -114,8 +114,8 @@ typedef struct XrtMesh {
     /* Clough-Tocher interpolation of z and the normal over the xy Delaunay triangulation */
     int32_t n_tri;               /* 0 when mesh_interpolate is off                       */
     int32_t pad0;
-    const double *ct_coef;       /* [n_tri][4][19] Bezier control coefficients of the cubic
-                                    macro element, fields z, nx, ny, nz                  */
+    const double *ct_coef;       /* [n_tri][19][4] Bezier control coefficients of the cubic
+                                    macro element, the fields z, nx, ny, nz side by side */
     const double *tri_transform; /* [n_tri][3][2] barycentric transform (scipy layout:
                                     rows 0,1 = inverse edge matrix, row 2 = third vertex) */
     /* uniform xy grid over the mesh footprint                                           */

@@ -271,28 +271,31 @@ __device__ __forceinline__ int mesh_nearest_vertex(const XrtMesh &m, V3 q) {
 
 // step 3: the faces around vertex `vert`.  face_geom gives p0 and the two edges, face_area the
 // constant |(p0 - p1) x (p0 - p2)| of the reference's area-sum test.
-struct FaceRec { double2 g0, g1, g2, g3, g4, g5, g6; };
+struct FaceRec { double2 g0, g1, g2, g3, g4, g5, g6, g7; };
 
 __device__ __forceinline__ FaceRec load_face_rec(const double *rec) {
     const double2 *g = (const double2 *)rec;
     FaceRec r;
     r.g0 = __ldg(g); r.g1 = __ldg(g + 1); r.g2 = __ldg(g + 2); r.g3 = __ldg(g + 3); r.g4 = __ldg(g + 4);
-    r.g5 = __ldg(g + 5); r.g6 = __ldg(g + 6);
+    r.g5 = __ldg(g + 5); r.g6 = __ldg(g + 6); r.g7 = __ldg(g + 7);
     return r;
 }
 
-// one candidate face (_ShapeMesh.py:350-426): ray / plane point, inside test by the area sum, distance >= 0
+// one candidate face (_ShapeMesh.py:350-426): ray / plane point, inside test by the area sum, distance >= 0.
+// Record (xicsrt_b200/mesh.py:device_tables): p0, m1 = e1 x n, m2 = e2 x n, n, area, face index, A0 = (e1 x e2) . n.
 __device__ __forceinline__ bool mesh_test_face(const FaceRec &r, V3 o, V3 d, V3 &X) {
-    const V3 p0 = v3(r.g0.x, r.g0.y, r.g1.x), e1 = v3(r.g1.y, r.g2.x, r.g2.y), e2 = v3(r.g3.x, r.g3.y, r.g4.x);
+    const V3 p0 = v3(r.g0.x, r.g0.y, r.g1.x), m1 = v3(r.g1.y, r.g2.x, r.g2.y), m2 = v3(r.g3.x, r.g3.y, r.g4.x);
     const V3 n = v3(r.g4.y, r.g5.x, r.g5.y);
-    const double area = r.g6.x;
+    const double area = r.g6.x, A0 = r.g7.x;
     const double dist = dot(p0 - o, n) / dot(d, n);
     if (!(dist >= 0.0)) return false;
     const V3 P = v3(d.x * dist + o.x, d.y * dist + o.y, d.z * dist + o.z);
-    const V3 a = P - p0, b = a - e1, c = a - e2;
-    // P lies in the face plane, so b x c, c x a and a x b are parallel to the unit normal n:
-    // their lengths are |(.) . n| -- the reference's three norms without a square root
-    const double diff = fabs(dot(cross(b, c), n)) + fabs(dot(cross(c, a), n)) + fabs(dot(cross(a, b), n)) - area;
+    const V3 a = P - p0;
+    // The reference sums the areas |b x c|, |c x a|, |a x b| of the three sub-triangles (b = a - e1, c = a - e2).  P lies
+    // in the face plane, so each cross product is parallel to the unit normal and its length is |(.) . n|; with
+    // (a x e) . n = a . (e x n):  (a x b) . n = -a . m1,  (c x a) . n = a . m2,  (b x c) . n = A0 + a . m1 - a . m2.
+    const double s1 = dot(a, m1), s2 = dot(a, m2);
+    const double diff = fabs(A0 + s1 - s2) + fabs(s2) + fabs(s1) - area;
     if (diff < 1e-10) {
         X = P;
         return true;
@@ -365,18 +368,30 @@ __device__ __forceinline__ int mesh_find_triangle(const XrtMesh &m, double x, do
     return -1;
 }
 
-// the cubic of one field: coefficient order of xicsrt_b200/mesh.py CT_NAMES
+// Clough-Tocher cubic of the four fields (z, nx, ny, nz) at once.  Coefficient order of xicsrt_b200/mesh.py CT_NAMES:
 //  0 c3000  1 c0300  2 c0030  3 c0003  4 c2100  5 c2010  6 c2001  7 c1200  8 c0210  9 c0201
 // 10 c1020 11 c0120 12 c0021 13 c1002 14 c0102 15 c0012 16 c1101 17 c1011 18 c0111
-__device__ __forceinline__ double ct_cubic(const double *__restrict__ c, double b1, double b2, double b3, double b4) {
+// Table layout [n_tri][19][4]: the 19 monomials (with their factors 1, 3, 6) are formed once and each multiplies the four
+// field coefficients that sit side by side (two 16-byte loads).
+__device__ __forceinline__ void ct_cubic4(const double *__restrict__ c, double b1, double b2, double b3, double b4, double w[4]) {
     const double b11 = b1 * b1, b22 = b2 * b2, b33 = b3 * b3, b44 = b4 * b4;
-    double w = b11 * b1 * __ldg(c + 0) + b22 * b2 * __ldg(c + 1) + b33 * b3 * __ldg(c + 2) + b44 * b4 * __ldg(c + 3);
-    w += 3.0 * (b11 * (b2 * __ldg(c + 4) + b3 * __ldg(c + 5) + b4 * __ldg(c + 6))
-                + b22 * (b1 * __ldg(c + 7) + b3 * __ldg(c + 8) + b4 * __ldg(c + 9))
-                + b33 * (b1 * __ldg(c + 10) + b2 * __ldg(c + 11) + b4 * __ldg(c + 12))
-                + b44 * (b1 * __ldg(c + 13) + b2 * __ldg(c + 14) + b3 * __ldg(c + 15)));
-    w += 6.0 * (b1 * b2 * b4 * __ldg(c + 16) + b1 * b3 * b4 * __ldg(c + 17) + b2 * b3 * b4 * __ldg(c + 18));
-    return w;
+    const double t1 = 3.0 * b11, t2 = 3.0 * b22, t3 = 3.0 * b33, t4 = 3.0 * b44;
+    const double s14 = 6.0 * b1 * b4, s234 = 6.0 * b2 * b3 * b4;
+    const double mono[19] = {b11 * b1, b22 * b2, b33 * b3, b44 * b4,
+                             t1 * b2, t1 * b3, t1 * b4, t2 * b1, t2 * b3, t2 * b4,
+                             t3 * b1, t3 * b2, t3 * b4, t4 * b1, t4 * b2, t4 * b3,
+                             s14 * b2, s14 * b3, s234};
+    const double2 *c2 = (const double2 *)c;
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 19; ++i) {
+        const double2 ca = __ldg(c2 + 2 * i), cb = __ldg(c2 + 2 * i + 1);
+        w0 = fma(mono[i], ca.x, w0);
+        w1 = fma(mono[i], ca.y, w1);
+        w2 = fma(mono[i], cb.x, w2);
+        w3 = fma(mono[i], cb.y, w3);
+    }
+    w[0] = w0; w[1] = w1; w[2] = w2; w[3] = w3;
 }
 
 // number of faces step 1 walks (the coarse mesh when refining) and their operands
@@ -469,9 +484,10 @@ static __device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o,
         } else {
             const double mn = fmin(b0, fmin(b1, b2));
             const double e1 = b0 - mn, e2 = b1 - mn, e3 = b2 - mn, e4 = 3.0 * mn;
-            const double *c = m.ct_coef + (size_t)t * 76;
-            X.z = ct_cubic(c, e1, e2, e3, e4);
-            V3 nn = v3(ct_cubic(c + 19, e1, e2, e3, e4), ct_cubic(c + 38, e1, e2, e3, e4), ct_cubic(c + 57, e1, e2, e3, e4));
+            double w[4];
+            ct_cubic4(m.ct_coef + (size_t)t * 76, e1, e2, e3, e4, w);
+            X.z = w[0];
+            V3 nn = v3(w[1], w[2], w[3]);
             n = nn * rsqrt(dot(nn, nn));
         }
     } else {

@@ -462,8 +462,14 @@ def device_tables(param):
          'point_faces': np.ascontiguousarray(m['p_faces_idx'], dtype=np.int32),
          'point_faces_mask': np.ascontiguousarray(m['p_faces_mask'], dtype=np.uint8)}
     t['vertex_faces'] = np.ascontiguousarray(np.where(m['p_faces_mask'], m['p_faces_idx'], -1).T, dtype=np.int32)
+    # record of the candidate-face test (csrc/xrt_mesh.cuh:mesh_test_face): p0, m1 = e1 x n, m2 = e2 x n, unit normal n,
+    # area |e1 x e2|, (face index, filled per vertex), A0 = (e1 x e2) . n.  With a = P - p0 the three sub-triangle areas of
+    # the reference's inside test (_ShapeMesh.py:350-426) are |a . m1|, |a . m2| and |A0 + a . m1 - a . m2|.
     rec = np.zeros((len(t['faces']), 16))
-    rec[:, 0:9], rec[:, 9:12], rec[:, 12] = t['face_geom'], t['face_normals'], t['face_area']
+    e1, e2, nrm = t['face_geom'][:, 3:6], t['face_geom'][:, 6:9], t['face_normals']
+    rec[:, 0:3], rec[:, 3:6], rec[:, 6:9] = t['face_geom'][:, 0:3], np.cross(e1, nrm), np.cross(e2, nrm)
+    rec[:, 9:12], rec[:, 12] = nrm, t['face_area']
+    rec[:, 14] = np.einsum('ij,ij->i', np.cross(e1, e2), nrm)
     t['face_rec'] = rec
     refine = bool(param['mesh_refine'])
     if refine:
@@ -553,7 +559,8 @@ def fill_mesh(param, keep):
     if 'ct_coef' in t:
         flags |= L.F_MESH_INTERP
         m.n_tri = len(t['ct_coef'])
-        m.ct_coef = keep.f64(t['ct_coef'])
+        # device layout: coefficient-major, the four fields (z, nx, ny, nz) of one coefficient side by side
+        m.ct_coef = keep.f64(np.ascontiguousarray(np.transpose(t['ct_coef'], (0, 2, 1))))
         m.tri_transform = keep.f64(t['tri_transform'])
     if 'grid' in t:
         g = t['grid']
