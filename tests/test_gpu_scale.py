@@ -122,6 +122,19 @@ def _geometries():
     c['optics']['crystal'].pop('radius')
     c['optics']['crystal']['class_name'] = 'XicsrtOpticPlanarMosaicCrystal'
     g['config3_mosaic_planar'] = c
+    # the other source kinds of the mosaic broad phase (k_mosaic32<box>, <focused>), a lossy shallow crystal, and a run of
+    # more than 2^27 rays (three launches of the broad phase: 27-bit id offsets beside the layer tag)
+    c = bench.workload_config('config3', n3)
+    c['sources']['source'].update({'xsize': 2e-3, 'ysize': 1e-3, 'zsize': 3e-3})
+    g['config3_mosaic_box_source'] = c
+    c = bench.workload_config('config3', n3)
+    c['sources']['source'].update({'class_name': 'XicsrtSourceFocused', 'target': [0.0, 0.0, 0.80374151],
+                                   'xsize': 0.02, 'ysize': 0.02, 'zsize': 0.02, 'spread': float(np.radians(8.0))})
+    g['config3_mosaic_focused_source'] = c
+    c = bench.workload_config('config3', n3)
+    c['optics']['crystal'].update({'reflectivity': 0.55, 'mosaic_depth': 4, 'mosaic_spread': float(np.radians(0.8))})
+    g['config3_mosaic_lossy_depth4'] = c
+    g['config3_mosaic_3e8'] = bench.workload_config('config3', 3 * n3)
     return g
 
 
@@ -129,7 +142,13 @@ GEOMETRIES = ['config2', 'config2_reflectivity_0.37', 'config2_step_curve', 'bro
               'broad_phase_threshold_outside', 'sin_bragg_0.1002', 'sin_bragg_0.0998', 'planar_limit_r1e5',
               'planar_limit_r1e5_box_source', 'wide_cone_75deg', 'broad_line_narrow_curve', 'box_source_1mm',
               'focused_box_source_2cm', 'doppler_shifted_line', 'config5_plasma', 'config3_mosaic',
-              'config3_mosaic_cutoff_lossy', 'config3_mosaic_step_curve', 'config3_mosaic_planar']
+              'config3_mosaic_cutoff_lossy', 'config3_mosaic_step_curve', 'config3_mosaic_planar',
+              'config3_mosaic_box_source', 'config3_mosaic_focused_source', 'config3_mosaic_lossy_depth4',
+              'config3_mosaic_3e8']
+
+
+MOSAIC32_SCENES = {'config3_mosaic', 'config3_mosaic_step_curve', 'config3_mosaic_box_source', 'config3_mosaic_focused_source',
+                   'config3_mosaic_lossy_depth4', 'config3_mosaic_3e8'}
 
 
 @pytest.mark.timeout(900)
@@ -147,6 +166,10 @@ def test_work_skipping_stages_change_no_result_at_bench_scale(torch, name, monke
         per_seed = []
         for seed in SEEDS:
             tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(copy.deepcopy(cfg))), seed=seed)
+            if not env and name in MOSAIC32_SCENES:          # the plan under test is the one that runs
+                assert tracer.scene.launch_info()['mosaic_broad_phase'] is not None, name
+            if env and name in MOSAIC32_SCENES:
+                assert tracer.scene.launch_info()['mosaic_broad_phase'] is None, name
             tracer.trace(1)                                  # history off: the launch bench.py times
             packed_off = tracer.packed.clone()
             found, lost = tracer.select_ids(1, 64)           # history on: found / lost lists
@@ -156,7 +179,7 @@ def test_work_skipping_stages_change_no_result_at_bench_scale(torch, name, monke
         results.append(per_seed)
     for s, seed in enumerate(SEEDS):
         n0, packed0, found0 = results[0][s]
-        assert n0 >= 0.09 * N_SCALE
+        assert n0 >= 0.09 * N_SCALE or name.startswith('config3')
         n_src, n_det = int(packed0[0]), int(packed0[2])
         assert n_src == n0
         assert int(found0.numel()) == n_det
@@ -186,11 +209,13 @@ def _mesh_geometries():
     c = bench.workload_config('config4', N_MESH)
     c['optics']['crystal'].update({'trace_local': True, 'mesh_interpolate': False})
     g['config4_local_flat_normals'] = c
+    g['config4_3e8'] = bench.workload_config('config4', 3 * N_MESH)          # three launches of the sorted path (27-bit offsets)
     return g
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize('name', ['config4', 'config4_box_source', 'config4_bragg_24x31', 'config4_local_flat_normals'])
+@pytest.mark.parametrize('name', ['config4', 'config4_box_source', 'config4_bragg_24x31', 'config4_local_flat_normals',
+                                  'config4_3e8'])
 def test_sorted_mesh_path_changes_no_result(torch, name, monkeypatch):
     """The sorted mesh path (k_mesh_coarse -> counting sort by hit location -> k_trace in sorted mode) only changes the
     order in which rays are refined: same counters, images and found-id sets as the single-kernel path at 1e8 rays."""
@@ -205,6 +230,7 @@ def test_sorted_mesh_path_changes_no_result(torch, name, monkeypatch):
         per_seed = []
         for seed in SEEDS[:2]:
             tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(copy.deepcopy(cfg))), seed=seed)
+            assert (tracer.scene.launch_info()['mesh_sort'] is not None) == (not env), name
             tracer.trace(1)
             packed_off = tracer.packed.clone()
             found, lost = tracer.select_ids(1, 64)
@@ -215,7 +241,7 @@ def test_sorted_mesh_path_changes_no_result(torch, name, monkeypatch):
     for s, seed in enumerate(SEEDS[:2]):
         packed0, found0, lost0 = results[0][s]
         packed1, found1, lost1 = results[1][s]
-        assert int(packed0[0]) == N_MESH
+        assert int(packed0[0]) in (N_MESH, 3 * N_MESH)
         assert int(found0.numel()) == int(packed0[2]) > N_MESH // 1000
         assert torch.equal(packed1, packed0), f'{name} seed {seed}: counters / images differ without the sort'
         assert torch.equal(found1, found0), f'{name} seed {seed}: found-id set differs without the sort'
