@@ -428,6 +428,17 @@ def bounds_fraction(workload, seed=1):
     return mb['crystal'] / mb['source']
 
 
+def plan_kernels(info):
+    """The kernels of one step under the launch plan xrt_scene_create chose for the scene."""
+    if info.get('broad_phase'):
+        return 'k_cull32 + k_trace'
+    if info.get('mosaic_broad_phase'):
+        return 'k_mosaic32 + k_trace'
+    if info.get('mesh_sort'):
+        return 'k_mesh_coarse + k_mesh_scan + k_mesh_scatter + k_mesh_refine'
+    return 'k_trace'
+
+
 def roofline_for(workload, meta, rays_per_s_kernel, peak, tracer):
     f_reflect = meta['crystal'] / meta['source']
     extra = {}
@@ -478,6 +489,7 @@ def run_config(ctx, workload, rays_per_gpu, steps, warmup, peak, with_cpu):
             'detected_per_step': meta['detector'], 'launch': info}
     if ctx.rank == 0:
         line['roofline'] = roofline_for(workload, meta, (launched / ctx.world) * steps / t_kern, peak, tracer)
+        line['roofline']['kernel'] = plan_kernels(info)
         line['roofline']['kernel_ms_per_step'] = 1e3 * t_kern / steps
     tracer.close()
     e2e, _, _ = e2e_through_api(ctx, workload, total, max(2, steps // 2), 1)
@@ -597,7 +609,7 @@ def run_gpu_arm(args):
     roof = None
     if rank == 0:
         roof = roofline_for(headline_wl, meta, (launched / world) * args.steps / t_kernel, peak, tracer)
-        roof['kernel'] = 'k_cull32 + k_trace' if info.get('broad_phase') else 'k_trace'
+        roof['kernel'] = plan_kernels(info)
         roof['kernel_ms_per_step'] = 1e3 * t_kernel / args.steps
         try:
             prof = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))

@@ -34,6 +34,9 @@ namespace xrt {
 #ifndef XRT_MESH_BLOCKS
 #define XRT_MESH_BLOCKS 2      // resident blocks per SM of the mesh variants
 #endif
+#ifndef XRT_MOSAIC_BLOCKS
+#define XRT_MOSAIC_BLOCKS 2    // resident blocks per SM of the lean mosaic variant
+#endif
 #ifndef XRT_MIN_SCAN
 #define XRT_MIN_SCAN 8         // mosaic scan stage: lanes that must still be scanning for another scan iteration
 #endif
@@ -611,6 +614,7 @@ __device__ __forceinline__ bool spectro_stage_ab(const XrtSceneDesc &sc, const X
 // two independent chains) and for the lean extended-source variant (bundle lookup + focused cone basis); 3 otherwise.
 template <uint32_t FT, uint32_t KN> __host__ __device__ constexpr int trace_min_blocks() {
     if ((FT & FT_MESH) != 0) return XRT_MESH_BLOCKS;
+    if (FT == FT_MOSAICLEAN) return XRT_MOSAIC_BLOCKS;
     return (((FT & FT_MESH) != 0 || (FT & FT_MOSAIC) != 0 || FT == FT_SRCLEAN ||
              ((KN & KN_SPECTROMETER) == KN_SPECTROMETER && XRT_UNROLL > 1)) &&
             XRT_MIN_BLOCKS > 2) ? 2 : XRT_MIN_BLOCKS;

@@ -444,10 +444,12 @@ __device__ __forceinline__ int mesh_bin_of(const XrtMesh &m, V3 q, int sub, int 
     return (cy / tile) * tiles_x + cx / tile;
 }
 
-// Not inlined: the fused kernel reaches it from four places (optics before / at / after the split optic, stage A2)
-// and four inlined copies made the mesh variants 250 kB of code -- instruction-cache stalls of 4.5 cycles per issue.
-static __device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
-                                            const double *staged = nullptr, const V3 *resume_Xc = nullptr) {
+// mesh_intersect (below) is the out-of-line copy: the fused kernel reaches it from four places (optics before / at /
+// after the split optic, stage A2) and four inlined copies made the mesh variants 250 kB of code -- instruction-cache
+// stalls of 4.5 cycles per issue.  k_mesh_refine, which has one call site on its hot path, inlines it (no call, no
+// stack traffic for X and n, table loads scheduled with the caller's arithmetic).
+__device__ __forceinline__ bool mesh_intersect_inline(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
+                                                      const double *staged = nullptr, const V3 *resume_Xc = nullptr) {
     const XrtMesh &m = *op.mesh;
     X = nan3();
     n = nan3();
@@ -494,6 +496,11 @@ static __device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o,
         n = ld3(m.face_normals + 3 * face);
     }
     return true;
+}
+
+static __device__ __noinline__ bool mesh_intersect(const XrtOpticDesc &op, V3 o, V3 d, V3 &X, V3 &n,
+                                            const double *staged = nullptr, const V3 *resume_Xc = nullptr) {
+    return mesh_intersect_inline(op, o, d, X, n, staged, resume_Xc);
 }
 
 }  // namespace xrt

@@ -843,7 +843,7 @@ __device__ __forceinline__ void frame_to_external(const XrtOpticDesc &op, bool l
     }
 }
 
-template <uint32_t FT, bool WANT_NORMAL, uint32_t KN = 0>
+template <uint32_t FT, bool WANT_NORMAL, uint32_t KN = 0, bool INLINE_MESH = false>
 __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3 &n, const double *staged_mesh = nullptr,
                                               const V3 *mesh_resume = nullptr) {
     V3 o = r.o, d = r.d;
@@ -863,7 +863,8 @@ __device__ __forceinline__ int optic_geometry(const XrtOpticDesc &op, Ray &r, V3
     if constexpr ((FT & FT_MESH) != 0) {
         if (shape_of<KN>(op) == XRT_SHAPE_MESH) {
             analytic = false;
-            ok = mesh_intersect(op, o, d, X, n, staged_mesh, mesh_resume);
+            if constexpr (INLINE_MESH) ok = mesh_intersect_inline(op, o, d, X, n, staged_mesh, mesh_resume);
+            else ok = mesh_intersect(op, o, d, X, n, staged_mesh, mesh_resume);
         }
     }
     if (analytic) {
