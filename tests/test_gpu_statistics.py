@@ -241,16 +241,20 @@ def test_fused_kernel_equals_replay_kernel(torch, name):
 
 
 @pytest.mark.parametrize('name,kind', [('sphere', 'point'), ('sphere_step_box', 'focused'), ('plasma_toroidal', 'bundles'),
-                                       ('plasma_cubic_poisson', 'bundles'), ('mosaic_sphere', None), ('mosaic_sphere_cutoff', None),
-                                       ('mosaic_plane', None)])
+                                       ('plasma_cubic_poisson', 'bundles'), ('mosaic_sphere', 'mosaic32'), ('mosaic_sphere_cutoff', None),
+                                       ('mosaic_plane', None), ('mesh_torus', 'mesh_sort'), ('mesh_torus_41', 'mesh_sort'),
+                                       ('mesh_sphere', 'mesh_sort'), ('mesh_cylinder', 'mesh_sort'),
+                                       ('mesh_torus_flat_normals', 'mesh_sort')])
 def test_two_kernel_path_equals_replay_kernel(torch, name, kind, monkeypatch):
     """
-    The same comparison with the FP32 broad phase forced on for a small launch (XRT_CULL32_MIN_RAYS=0: k_cull32 writes
-    the id list, k_trace consumes it) for every source kind it is built for, and for the mosaic scan stage: counters,
-    images, found set and lost sample must equal what the straight replay kernel gives ray for ray.
+    The same comparison with the multi-kernel launch plans forced on for a small launch (XRT_CULL32_MIN_RAYS=0,
+    XRT_MESH_SORT_MIN_RAYS=0): k_cull32 for every source kind it is built for, the mosaic scan stage with and without its
+    broad phase k_mosaic32, and the sorted mesh path (k_mesh_coarse -> sort -> k_mesh_refine): counters, images, found
+    set and lost sample must equal what the straight replay kernel gives ray for ray.
     """
     from xicsrt_b200 import _driver, config as xconfig, elements
     monkeypatch.setenv('XRT_CULL32_MIN_RAYS', '0')
+    monkeypatch.setenv('XRT_MESH_SORT_MIN_RAYS', '0')
     cfg = scenes.get(name)
     if name.startswith('plasma'):
         cfg['sources']['source']['time_resolution'] *= 500
@@ -261,7 +265,11 @@ def test_two_kernel_path_equals_replay_kernel(torch, name, kind, monkeypatch):
     tracer = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), seed=1234)
     info = tracer.scene.launch_info()
     if kind is None:
-        assert info['broad_phase'] is None
+        assert info['broad_phase'] is None and info['mosaic_broad_phase'] is None and info['mesh_sort'] is None
+    elif kind == 'mosaic32':
+        assert info['mosaic_broad_phase'] is not None, info
+    elif kind == 'mesh_sort':
+        assert info['mesh_sort'] is not None, info
     else:
         assert info['broad_phase'] is not None and info['broad_phase']['source_kind'] == kind, info
     n = tracer.n_rays

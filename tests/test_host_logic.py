@@ -244,6 +244,87 @@ def test_fp32_broad_phase_error_budget():
         assert err + mufu < margin / 5, (name, err, mufu, margin)
 
 
+def test_fp32_mosaic_broad_phase_error_budget():
+    """
+    The mosaic broad phase (k_mosaic32 in csrc/xrt_kernels.cuh) rejects a crystallite layer when its single-precision
+    sin(theta_i) = |x D.r_0 + y D.r_1 + D.n| / sqrt(x^2 + y^2 + 1) is farther from sin(theta_B) than the rocking curve
+    allows; the frame (n, r_0, r_1) of mosaic_normal at the intersection point and the three dot products come from the
+    FP32 ray (n = (L - t D) / R, r_0 = unit(n_y, n_z - n_x, -n_y), r_1 = unit(n x r_0)).  The margin is that of
+    k_cull32, 2e-5 max(1, |C - O|^2 / R^2), plus stage S's 2e-6.  Restated here in numpy float32 for config 3 and two
+    stress variants: the error of sin(theta_i) must stay within a fifth of the margin for every crystallite offset.
+    """
+    import bench
+    from xicsrt_b200 import config as xconfig, scene as xscene
+    f32 = np.float32
+    rng = np.random.default_rng(23)
+    n = 300000
+    a = np.concatenate([rng.random(n), 1.0 - 10.0**rng.uniform(-12, -1, n // 4), 10.0**rng.uniform(-12, -1, n // 4)])
+    b = rng.random(len(a))
+    for name, mod in {'config3': {}, 'scaled': {'scale': 3.0}, 'off_rowland': {'origin': [0.01, -0.02, 0.15]}}.items():
+        cfg = bench.workload_config('config3', 1000)
+        if 'scale' in mod:
+            for o in cfg['optics'].values():
+                o['origin'] = [mod['scale'] * v for v in o['origin']]
+            cfg['optics']['crystal']['radius'] = mod['scale']
+        if 'origin' in mod:
+            cfg['sources']['source']['origin'] = mod['origin']
+        _, sname, sp, sf, optics = xscene.prepare(xconfig.get_config(xconfig.to_numpy(cfg)))
+        cp = optics['crystal']
+        basis = xscene.cone_basis(sp['direction'] if sp.get('direction') is not None else sp['zaxis'], sp['xaxis'], sp['zaxis'])
+        cs0 = np.cos(np.atleast_1d(sp['spread'])[0])
+        Lc = np.asarray(cp['center'], dtype=np.float64) - np.asarray(sp['origin'], dtype=np.float64)
+        R = float(cp['radius'])
+        sig = np.sin(float(cp['mosaic_spread']) / (2.0 * np.sqrt(2.0 * np.log(2.0)))) if 'mosaic_spread' in cp else 3e-3
+        # crystallite offsets: Gaussian with the mosaic width, plus far tails
+        xy = np.concatenate([rng.normal(0.0, sig, (len(a) // 2, 2)), rng.normal(0.0, 5 * sig, (len(a) - len(a) // 2, 2))])
+
+        def frame(d, t, L, inv_r, dt):
+            nrm = ((L - t[:, None] * d) * inv_r).astype(dt)
+            r0 = np.stack([nrm[:, 1], nrm[:, 2] - nrm[:, 0], -nrm[:, 1]], axis=1).astype(dt)
+            r0 = (r0 / np.sqrt((r0 * r0).sum(axis=1, dtype=dt))[:, None]).astype(dt)
+            r1 = np.cross(nrm, r0).astype(dt)
+            r1 = (r1 / np.sqrt((r1 * r1).sum(axis=1, dtype=dt))[:, None]).astype(dt)
+            return (d * r0).sum(axis=1, dtype=dt), (d * r1).sum(axis=1, dtype=dt), (d * nrm).sum(axis=1, dtype=dt), r0
+
+        # ---- FP64 (generate_geometry, hit_sphere, mosaic_normal)
+        z = cs0 + (1.0 - cs0) * a
+        rho = np.sqrt(1.0 - z * z)
+        d = (rho * np.cos(2 * np.pi * b))[:, None] * basis[0] + (rho * np.sin(2 * np.pi * b))[:, None] * basis[1] + z[:, None] * basis[2]
+        tca = d @ Lc
+        thc2 = R * R - (Lc @ Lc - tca * tca)
+        hit = thc2 > 0
+        t = tca + np.sqrt(np.where(hit, thc2, 1.0))
+        dr0, dr1, dn, r0_64 = frame(d, t, Lc[None, :], 1.0 / R, np.float64)
+        sI64 = np.abs(xy[:, 0] * dr0 + xy[:, 1] * dr1 + dn) / np.sqrt(xy[:, 0]**2 + xy[:, 1]**2 + 1.0)
+        # ---- FP32 (cull32_ray<point, FULL> + the frame of k_mosaic32)
+        na = np.floor((1.0 - a) * 2.0**32)
+        one_minus_a = ((na + 0.5) * 2.0**-32).astype(f32)
+        b24 = (np.floor(b * 2**23) / 2**23).astype(f32)
+        w = (f32(1.0 - cs0) * one_minus_a).astype(f32)
+        z32 = (f32(1) - w).astype(f32)
+        rho32 = np.sqrt((w * (f32(2) - w)).astype(f32)).astype(f32)
+        ang = (f32(6.283185307179586) * (b24 - f32(0.5))).astype(f32)
+        lx, ly = (-rho32 * np.cos(ang).astype(f32)).astype(f32), (-rho32 * np.sin(ang).astype(f32)).astype(f32)
+        b32 = basis.astype(f32)
+        d32 = (lx[:, None] * b32[0] + ly[:, None] * b32[1] + z32[:, None] * b32[2]).astype(f32)
+        m32 = (basis @ Lc).astype(f32)
+        tca32 = (lx * m32[0] + ly * m32[1] + z32 * m32[2]).astype(f32)
+        t2 = (f32(R * R) - (f32(Lc @ Lc) - tca32 * tca32).astype(f32)).astype(f32)
+        t32 = (tca32 + np.sqrt(np.where(t2 > 0, t2, f32(1))).astype(f32)).astype(f32)
+        dr0_32, dr1_32, dn_32, r0_32 = frame(d32, t32, Lc.astype(f32)[None, :], f32(1.0 / R), f32)
+        x32, y32 = xy[:, 0].astype(f32), xy[:, 1].astype(f32)
+        sI32 = (np.abs(x32 * dr0_32 + y32 * dr1_32 + dn_32) / np.sqrt(x32 * x32 + y32 * y32 + f32(1))).astype(f32)
+        # the kernel leaves rays with a nearly degenerate frame (|r_0 before normalisation|^2 <= 0.01) to the FP64 path
+        nrm64 = (Lc[None, :] - t[:, None] * d) / R
+        a2 = 2 * nrm64[:, 1]**2 + (nrm64[:, 2] - nrm64[:, 0])**2
+        both = hit & (t2 > 0) & (na >= 256) & (a2 > 0.01)
+        assert both.sum() > 0.5 * len(a)
+        err = np.abs(sI32.astype(np.float64) - sI64)[both].max()
+        mufu = 2.0**-21 * 2.0 * np.abs(Lc).sum() / R + 1e-6      # sin / cos / sqrt / rsqrt of the MUFU units
+        margin = 2e-5 * max(1.0, (Lc @ Lc) / (R * R)) + 2e-6
+        assert err + mufu < margin / 5, (name, err, mufu, margin)      # measured: 8-9 % of the margin
+
+
 def test_fp32_broad_phase_error_budget_extended_sources():
     """
     The same budget for the generalised broad phase (cull32_ray<CULL_BOX / CULL_FOCUSED / CULL_BUNDLES> in
