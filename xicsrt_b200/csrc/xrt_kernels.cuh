@@ -1058,7 +1058,6 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         // fixed basis and fixed origin: L . D = l . (basis L), v . D = l . (basis v); |L|^2 is a constant
         tca = lx * K.m[0] + ly * K.m[1] + z * K.m[2];
         ll = K.ll;
-        if (K.moving) vd = lx * K.mv[0] + ly * K.mv[1] + z * K.mv[2];
         if constexpr (FULL) {
             dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
             dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
@@ -1100,7 +1099,12 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         lam = fmaf(normal_approx(r.w, in_range), sig, lam);
         usable &= in_range;
     }
-    if (SRC == CULL_BUNDLES || K.moving) lam = fmaf(-lam, vd, lam);
+    if constexpr (SRC == CULL_POINT) {
+        // Doppler factor formed here, inside the one uniform branch that uses it (most scenes are at rest)
+        if (K.moving) lam = fmaf(-lam, lx * K.mv[0] + ly * K.mv[1] + z * K.mv[2], lam);
+    } else {
+        if (SRC == CULL_BUNDLES || K.moving) lam = fmaf(-lam, vd, lam);
+    }
     const float sB = lam * K.inv_two_d;
 
     const float gap = fabsf(sB - sI);
