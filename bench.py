@@ -654,6 +654,10 @@ def run_gpu_arm(args):
         extras['history'] = guarded(ctx, 'history e2e', hist_e2e)
         extras['target'] = guarded(ctx, 'config5 target', lambda: target_config5(ctx))
     extras['shard_parity'] = guarded(ctx, 'shard parity', lambda: shard_parity(ctx)) if world > 1 else None
+    if world > 1 and not single and not args.quick:
+        # the same check for the other launch plans (mosaic broad phase, sorted mesh path, plasma bundles)
+        extras['shard_parity_configs'] = {wl: guarded(ctx, 'shard parity ' + wl, lambda wl=wl: shard_parity(ctx, wl, 24_000_000))
+                                          for wl in ('config3', 'config4', 'config5')}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only)
     cpu = None
