@@ -18,6 +18,10 @@ def make(name, n):
                                          'xsize': 0.02, 'ysize': 0.02, 'zsize': 0.02})
     elif name == 'doppler':
         cfg['sources']['source']['velocity'] = [0.0, 0.0, 1e4]
+    elif name == 'plasma_mesh':       # the config 5 plasma in front of the config 4 mesh crystal (Bragg test on)
+        cfg = bench.workload_config('config5', n)
+        cfg['optics']['crystal'] = bench.workload_config('config4', n)['optics']['crystal']
+        cfg['optics']['crystal'].update({'check_bragg': True, 'rocking_fwhm': 2e-3})
     elif name == 'step':
         cfg['optics']['crystal']['rocking_type'] = 'step'
     elif name == 'nocull':
@@ -36,7 +40,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     args = ap.parse_args()
     for name in args.names:
-        n = int(args.rays if name not in ('config3', 'config4') else min(args.rays, 1e8))
+        n = int(args.rays if name not in ('config3', 'config4', 'plasma_mesh') else min(args.rays, 1e8))
         cfg = make(name, n)
         tr = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), 0)
         for it in range(2):

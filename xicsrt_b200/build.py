@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, 'libxrt.so')
 # one translation unit per compiled feature set (they build in parallel) + the host side
 SOURCES = ['xrt.cu', 'v_cull.cu', 'v_lean.cu', 'v_mid.cu', 'v_mosaic.cu', 'v_src.cu', 'v_mesh.cu', 'v_full.cu']
 HEADERS = ['xrt_math.cuh', 'xrt_fastmath.cuh', 'xrt_trace.cuh', 'xrt_mesh.cuh', 'xrt_plasma.cuh', 'xrt_kernels.cuh',
-           'xrt_variants.h', os.path.join('..', '..', 'include', 'xrt.h')]
+           'xrt_meshsort.cuh', 'xrt_select.cuh', 'xrt_variants.h', os.path.join('..', '..', 'include', 'xrt.h')]
 OBJ_DIR = os.path.join(os.path.dirname(HERE), 'build', 'obj')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -354,8 +354,10 @@ static int scene_build(XrtScene *s, const XrtSceneDesc *desc) {
     // extended-source variant
     if (s->features == 0 && !s->lazy_wavelength) s->features = FT_SRCLEAN;
     // sorted mesh path: the conditions under which k_trace splits stage A at the coarse mesh (mesh_staged)
-    s->mesh_sort = (s->mesh_bins > 0 && s->split == 0 && d.optics[0].shape == XRT_SHAPE_MESH && s->lazy_wavelength &&
-                    src.kind != XRT_SRC_BUNDLES && src.cone != XRT_CONE_ISOTROPIC_XY &&
+    // (any source kind, plasma bundles included: both kernels rebuild the ray from its id; a wavelength that depends on
+    // the source direction or the bundle is drawn with the ray in k_mesh_refine)
+    s->mesh_sort = (s->mesh_bins > 0 && s->split == 0 && d.optics[0].shape == XRT_SHAPE_MESH &&
+                    src.cone != XRT_CONE_ISOTROPIC_XY &&
                     (s->features == FT_MESHLEAN || s->features == FT_FULL)) ? 1 : 0;
     if (s->mesh_sort && src.kind == XRT_SRC_FIXED_AXIS && src.cone == XRT_CONE_ISOTROPIC && src.spatial == XRT_SPATIAL_UNIFORM &&
         src.extent[0] == 0.0 && src.extent[1] == 0.0 && src.extent[2] == 0.0 && src.cone_par[0] > 0.2 &&

@@ -98,7 +98,7 @@ k_mesh_coarse(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ P
     const double *geom;
     const int nf = mesh_stage1_faces(ops, geom);
     // the host enables this path for nf <= 32 (5-bit face tag), so the operands always fit the staging area
-    const bool mesh_point = src.extent[0] == 0.0 && src.extent[1] == 0.0 && src.extent[2] == 0.0 &&
+    const bool mesh_point = src.kind != XRT_SRC_BUNDLES && src.extent[0] == 0.0 && src.extent[1] == 0.0 && src.extent[2] == 0.0 &&
                             src.spatial == XRT_SPATIAL_UNIFORM && kPointRec * nf <= 9 * kStageFaces;
     if (mesh_point) {
         V3 o = v3(src.origin);
@@ -341,6 +341,7 @@ k_mesh_refine(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ P
     c.lt_mask = (1u << c.lane) - 1u;
     c.s_cnt = s_cnt;
     const XrtOpticDesc &ops = sc.optics[0];
+    const bool lazy = (lazy_rt & 1) != 0;
     const bool need_wave = (lazy_rt & 2) != 0;
     const int nopt = sc.n_optics;
     const uint32_t n = __ldg(total);
@@ -363,6 +364,9 @@ k_mesh_refine(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ P
             SrcLocal L;
             source_local<FT, 0>(sc.source, id, L);
             generate_geometry<FT, PhiloxDraws, 0, true>(sc.source, L, dr, r, s_sincos);
+            // a wavelength that depends on the direction at the source or on the bundle (Doppler shift, plasma) is drawn
+            // with the ray, as in stage A of k_trace
+            if (!lazy) r.w = generate_wavelength<PhiloxDraws, 0>(sc.source, L, dr, r.d);
             V3 o = r.o, d = r.d;
             if (optic_is_local<FT>(ops)) {
                 o = to_local(ops.orient, o - v3(ops.origin));
@@ -371,8 +375,8 @@ k_mesh_refine(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ P
             const V3 Xc = mesh_face_point(coarse_geom + 9 * face, o, d);
             V3 nrm = v3(0.0, 0.0, 1.0);
             if (optic_geometry<FT, true, 0, true>(ops, r, nrm, nullptr, &Xc) == HIT_INSIDE) {
-                // the wavelength is lazy on this path (drawn where it is first read; no Doppler shift)
-                if (need_wave) r.w = generate_wavelength<PhiloxDraws, 0, false>(sc.source, L, dr, r.d);
+                // a lazy wavelength is drawn where it is first read (no Doppler shift)
+                if (lazy && need_wave) r.w = generate_wavelength<PhiloxDraws, 0, false>(sc.source, L, dr, r.d);
                 optic_interact<FT, PhiloxDraws, 0>(ops, 0, dr, r, nrm);
                 if (r.alive && (ops.flags & XRT_F_IMAGE) && out.images) add_pixel(out, ops, r, c.lt_mask);
             }
