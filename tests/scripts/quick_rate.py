@@ -10,6 +10,12 @@ from xicsrt_b200 import _driver, config as xconfig
 def make(name, n):
     if name in ('config2', 'config3', 'config4', 'config5'):
         return bench.workload_config(name, n)
+    if name.startswith('scene:'):     # a parity scene of oracle/scenes.py at n rays, history off
+        from oracle import scenes
+        cfg = scenes.get(name[6:])
+        cfg['sources']['source']['intensity'] = n
+        cfg['general']['keep_history'] = False
+        return cfg
     cfg = bench.spectrometer(n)
     if name == 'box':
         cfg['sources']['source'].update({'xsize': 1e-3, 'ysize': 1e-3, 'zsize': 1e-3})
@@ -40,7 +46,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     args = ap.parse_args()
     for name in args.names:
-        n = int(args.rays if name not in ('config3', 'config4', 'plasma_mesh') else min(args.rays, 1e8))
+        n = int(args.rays if name not in ('config3', 'config4', 'plasma_mesh') and not name.startswith('scene:') else min(args.rays, 1e8))
         cfg = make(name, n)
         tr = _driver.Tracer(xconfig.get_config(xconfig.to_numpy(cfg)), 0)
         for it in range(2):
