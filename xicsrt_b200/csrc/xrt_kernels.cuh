@@ -985,11 +985,15 @@ struct Cull32Full {
     float gap, c2, err;              // Bragg pre-test quantities
     float lx, ly, lz;                // sphere centre - ray origin
     float sB;                        // sin(theta_B) of the ray's (approximate) wavelength
+    float cl[3];                     // local cone vector (point source: the direction is cl . basis, formed by whoever needs it)
     bool usable;
 };
+// what cull32_ray hands out besides its verdict: nothing; what the second stage needs (no direction for a point source,
+// whose first stage never forms it); everything (k_mosaic32)
+enum { CULL_OUT_NONE = 0, CULL_OUT_STAGE2 = 1, CULL_OUT_FULL = 2 };
 
 // true = provably lost at the crystal
-template <int SRC, bool FULL = false>
+template <int SRC, int OUT = CULL_OUT_NONE>
 __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
                                            uint32_t lo, uint32_t hi, Cull32Full *full = nullptr) {
     const uint4 r = philox4x32_10(make_uint4(lo, hi, SITE_CONE, stream), pk);
@@ -1020,7 +1024,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         sig = (float)__ldg(&bd->wave_sigma);
         err = fmaf(K.err_sig, fabsf(sig), K.err);
         vx = (float)__ldg(&bd->velocity_c[0]); vy = (float)__ldg(&bd->velocity_c[1]); vz = (float)__ldg(&bd->velocity_c[2]);
-        if constexpr (FULL) { Px = (float)(ox - K.Oc[0]); Py = (float)(oy - K.Oc[1]); Pz = (float)(oz - K.Oc[2]); }
+        if constexpr (OUT != CULL_OUT_NONE) { Px = (float)(ox - K.Oc[0]); Py = (float)(oy - K.Oc[1]); Pz = (float)(oz - K.Oc[2]); }
     }
 
     // ---- origin offset in world coordinates (the exact path: u01_42x3 of one block, off_k = ext_k (u_k - 1/2))
@@ -1035,7 +1039,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         const float wz = o0 * K.R[2] + o1 * K.R[5] + o2 * K.R[8];
         Lx -= wx; Ly -= wy; Lz -= wz;
         Tx -= wx; Ty -= wy; Tz -= wz;
-        if constexpr (FULL) { Px += wx; Py += wy; Pz += wz; }
+        if constexpr (OUT != CULL_OUT_NONE) { Px += wx; Py += wy; Pz += wz; }
     }
 
     // ---- local cone vector.  1 - a from the top 32 bits of the polar uniform (their complement): its RELATIVE
@@ -1058,7 +1062,7 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
         // fixed basis and fixed origin: L . D = l . (basis L), v . D = l . (basis v); |L|^2 is a constant
         tca = lx * K.m[0] + ly * K.m[1] + z * K.m[2];
         ll = K.ll;
-        if constexpr (FULL) {
+        if constexpr (OUT == CULL_OUT_FULL) {
             dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
             dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
             dz = lx * K.basis[2] + ly * K.basis[5] + z * K.basis[8];
@@ -1110,7 +1114,8 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
     const float gap = fabsf(sB - sI);
     const float diff = gap - err;
     const float c2 = fmaf(2.0f, gap, fmaf(-sI, sI, 1.0f));
-    if constexpr (FULL) {
+    if constexpr (OUT != CULL_OUT_NONE) {
+        full->cl[0] = lx; full->cl[1] = ly; full->cl[2] = z;
         full->dx = dx; full->dy = dy; full->dz = dz; full->tca = tca; full->thc = thc;
         full->px = Px; full->py = Py; full->pz = Pz;
         full->gap = gap; full->c2 = c2; full->err = err; full->usable = usable;
@@ -1119,36 +1124,83 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
     return usable & (diff > 0.0f) & (diff * diff > K.t2 * c2);
 }
 
-// Second stage for one ray that survived the first: the same single-precision ray once more (now with its direction
-// and chord), then
+// Second stage for one ray that survived the first, from the values the first stage left in the warp's queue (the ray
+// is not generated again):
 //   bounds   X = O + t D in the crystal's frame; a ray farther outside |x| < hx, |y| < hy than the rounding of the
 //            chord arithmetic allows (4e-7 of the lengths that cancel in t = tca +- thc) is lost at the crystal;
 //   level 2  with the ray's rocking-curve uniform u (words z, w of the SITE_WAVE block, the block the exact path reads):
 //            reflected => dtheta^2 <= 2 sigma^2 ln(reflectivity / u); the first stage's lower bound on |dtheta| beyond
 //            that means lost (bragg_cull_uniform in single precision, u truncated to 23 bits -- downwards, which only
 //            widens the limit).
-// true = provably lost at the crystal.
+// Queue record (planes of 64 entries per warp): offset | usable << 31; point source: local cone vector, tca, thc, gap,
+// c2 (its direction is cone vector . basis, origin and margin are constants); other sources: direction, tca, thc, gap,
+// c2, origin - crystal origin, margin.
+// Sources whose second stage is fed from the queue; for the others (per-ray focused basis, plasma bundles: more values,
+// and few rays survive the first stage at all) the queue holds the offset alone and the second stage generates the ray
+// again -- measured: hand-off +6.5 % for the point source, +2.5 % for the box, -2 % / -5 % for focused / bundles.
+template <int SRC> __host__ __device__ constexpr bool cull_handoff() { return SRC == CULL_POINT || SRC == CULL_BOX; }
+template <int SRC> __host__ __device__ constexpr int cull_planes() { return SRC == CULL_POINT ? 8 : (SRC == CULL_BOX ? 12 : 1); }
+constexpr int kCullQ = 64;
+
+template <int SRC>
+__device__ __forceinline__ void cull32_push(uint32_t *q, int slot, uint32_t off, const Cull32Full &f) {
+    q[slot] = off | (f.usable ? 0x80000000u : 0u);
+    if constexpr (!cull_handoff<SRC>()) return;
+    float *qf = (float *)q;
+    if constexpr (SRC == CULL_POINT) {
+        qf[1 * kCullQ + slot] = f.cl[0]; qf[2 * kCullQ + slot] = f.cl[1]; qf[3 * kCullQ + slot] = f.cl[2];
+    } else {
+        qf[1 * kCullQ + slot] = f.dx; qf[2 * kCullQ + slot] = f.dy; qf[3 * kCullQ + slot] = f.dz;
+        qf[8 * kCullQ + slot] = f.px; qf[9 * kCullQ + slot] = f.py; qf[10 * kCullQ + slot] = f.pz;
+        qf[11 * kCullQ + slot] = f.err;
+    }
+    qf[4 * kCullQ + slot] = f.tca; qf[5 * kCullQ + slot] = f.thc; qf[6 * kCullQ + slot] = f.gap; qf[7 * kCullQ + slot] = f.c2;
+}
+
+// true = provably lost at the crystal
 template <int SRC>
 __device__ __forceinline__ bool cull32_stage2(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
-                                              uint32_t lo, uint32_t hi) {
-    Cull32Full f;
-    if (cull32_ray<SRC, true>(K, src, pk, stream, lo, hi, &f)) return true;
+                                              uint32_t lo, uint32_t hi, const uint32_t *q, int slot, bool usable) {
+    const float *qf = (const float *)q;
+    float tca, thc, gap, c2, dx, dy, dz, px, py, pz, err;
+    if constexpr (!cull_handoff<SRC>()) {
+        Cull32Full f;
+        if (cull32_ray<SRC, CULL_OUT_FULL>(K, src, pk, stream, lo, hi, &f)) return true;
+        tca = f.tca; thc = f.thc; gap = f.gap; c2 = f.c2;
+        dx = f.dx; dy = f.dy; dz = f.dz; px = f.px; py = f.py; pz = f.pz; err = f.err;
+        usable = f.usable;
+    } else {
+        tca = qf[4 * kCullQ + slot]; thc = qf[5 * kCullQ + slot]; gap = qf[6 * kCullQ + slot]; c2 = qf[7 * kCullQ + slot];
+    }
+    if constexpr (!cull_handoff<SRC>()) {
+    } else if constexpr (SRC == CULL_POINT) {
+        const float lx = qf[1 * kCullQ + slot], ly = qf[2 * kCullQ + slot], z = qf[3 * kCullQ + slot];
+        dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
+        dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
+        dz = lx * K.basis[2] + ly * K.basis[5] + z * K.basis[8];
+        px = K.Ob[0]; py = K.Ob[1]; pz = K.Ob[2];
+        err = K.err;
+    } else {
+        dx = qf[1 * kCullQ + slot]; dy = qf[2 * kCullQ + slot]; dz = qf[3 * kCullQ + slot];
+        px = qf[8 * kCullQ + slot]; py = qf[9 * kCullQ + slot]; pz = qf[10 * kCullQ + slot];
+        err = qf[11 * kCullQ + slot];
+    }
     bool lost = false;
     if (K.bounds_xy) {
-        const float t = K.convex ? f.tca - f.thc : f.tca + f.thc;
-        const float X = fmaf(t, f.dx, f.px), Y = fmaf(t, f.dy, f.py), Z = fmaf(t, f.dz, f.pz);
+        const float t = K.convex ? tca - thc : tca + thc;
+        const float X = fmaf(t, dx, px), Y = fmaf(t, dy, py), Z = fmaf(t, dz, pz);
         const float xl = X * K.ox[0] + Y * K.ox[1] + Z * K.ox[2];
         const float yl = X * K.oy[0] + Y * K.oy[1] + Z * K.oy[2];
-        const float slack = fmaf(4e-7f, fabsf(f.tca) + fabsf(f.thc) + fabsf(f.px) + fabsf(f.py) + fabsf(f.pz), 1e-7f);
+        const float slack = fmaf(4e-7f, fabsf(tca) + fabsf(thc) + fabsf(px) + fabsf(py) + fabsf(pz), 1e-7f);
         lost = (fabsf(xl) > K.hx + slack) | (fabsf(yl) > K.hy + slack);       // NaN (sphere missed): not lost here
     }
-    if (K.gauss && f.usable) {
+    if (K.gauss && usable) {
         const uint4 b = philox4x32_10(make_uint4(lo, hi, SITE_WAVE, stream), pk);
         const float u = __uint_as_float(0x3f800000u | (b.z >> 9)) - 1.0f;
         const float lim = 0.6931471805599453f * (K.lg_refl - lg2_approx(u));
         const float bound = fmaf(fabsf(lim), 1e-3f, lim + 1e-3f) * K.two_sigma2;
-        const float diff = f.gap - f.err;
-        lost |= (diff > 0.0f) & (diff * diff > bound * f.c2) & (lim == lim);
+        const float diff = gap - err;
+        lost |= (diff > 0.0f) & (diff * diff > bound * c2) & (lim == lim);
     }
     return lost;
 }
@@ -1156,17 +1208,18 @@ __device__ __forceinline__ bool cull32_stage2(const Cull32Par &K, const XrtSourc
 // groups of 32 consecutive ids per pass (independent chains): one for the bundle lookup, whose loads already overlap
 template <int SRC> __host__ __device__ constexpr int cull_unroll() { return SRC == CULL_BUNDLES ? 1 : XRT_CULL_UNROLL; }
 
-// cull_unroll groups of 32 consecutive ids: test, then append the survivors to the region's list
-// stage 2 for `cnt` offsets popped from the warp's queue; survivors are appended to the region's list
+// stage 2 for `cnt` records popped from the warp's queue; survivors are appended to the region's list
 template <int SRC, bool HIST>
 __device__ __forceinline__ void cull32_drain(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint64_t stream_id,
                                              const XrtOutputs &out, unsigned lane, unsigned lt_mask, uint64_t id_first,
                                              uint32_t off_first, const uint32_t *q, int first, int cnt, uint32_t *dst, uint32_t &kept) {
     const bool active = (int)lane < cnt;
-    const uint32_t off = active ? q[first + lane] : q[first];
-    __syncwarp();
+    const int slot = active ? first + (int)lane : first;
+    const uint32_t word = q[slot];
+    const uint32_t off = word & 0x7fffffffu;
     const uint64_t id = id_first + off;
-    const bool pass = active && !cull32_stage2<SRC>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32));
+    const bool pass = active && !cull32_stage2<SRC>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32), q, slot, (word >> 31) != 0u);
+    __syncwarp();
     if constexpr (HIST) {
         if (out.lost_count || out.lost_bits) {
             PhiloxDraws dr;
@@ -1179,34 +1232,33 @@ __device__ __forceinline__ void cull32_drain(const Cull32Par &K, const XrtSource
     kept += __popc(m);
 }
 
+// cull_unroll groups of 32 consecutive ids: first stage; what it cannot reject goes to the second stage through the
+// warp's queue (K.stage2) or straight to the region's list
 template <int SRC, bool HIST, bool CHECK>
 __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint64_t stream_id,
                                             const XrtOutputs &out, unsigned lane, unsigned lt_mask, uint64_t id_first,
                                             uint32_t off_first, uint32_t g, uint32_t n_here, uint32_t *dst, uint32_t &kept,
                                             uint32_t *q, int &nq) {
     constexpr int U = cull_unroll<SRC>();
-    bool valid[U], pass[U];
-    uint32_t off[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-        off[j] = g + 32u * j + lane;
-        valid[j] = CHECK ? off[j] < n_here : true;
-        const uint64_t id = id_first + (valid[j] ? off[j] : 0u);      // lanes past the end re-test the region's first ray
-        pass[j] = !cull32_ray<SRC>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32));
-        if constexpr (CHECK) pass[j] = pass[j] && valid[j];
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
+        const uint32_t off = g + 32u * j + lane;
+        const bool valid = CHECK ? off < n_here : true;
+        const uint64_t id = id_first + (valid ? off : 0u);      // lanes past the end re-test the region's first ray
+        Cull32Full f;
+        f.usable = true;
+        bool pass = !cull32_ray<SRC, cull_handoff<SRC>() ? CULL_OUT_STAGE2 : CULL_OUT_NONE>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32), &f);
+        if constexpr (CHECK) pass = pass && valid;
         if constexpr (HIST) {
             if (out.lost_count || out.lost_bits) {
                 PhiloxDraws dr;
-                dr.init(pk, stream_id, id_first + off[j], 0);
-                emit_lost<true>(out, lane, lt_mask, dr, valid[j] && !pass[j], id_first + off[j]);
+                dr.init(pk, stream_id, id_first + off, 0);
+                emit_lost<true>(out, lane, lt_mask, dr, valid && !pass, id_first + off);
             }
         }
-        const unsigned m = __ballot_sync(kFull, pass[j]);
+        const unsigned m = __ballot_sync(kFull, pass);
         if (K.stage2) {
-            if (pass[j]) q[nq + __popc(m & lt_mask)] = off[j];
+            if (pass) cull32_push<SRC>(q, nq + __popc(m & lt_mask), off, f);
             nq += __popc(m);
             __syncwarp();
             if (nq >= 32) {         // at most 63 queued: one full pop keeps the queue below 32 + the next push
@@ -1214,7 +1266,7 @@ __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceD
                 cull32_drain<SRC, HIST>(K, src, pk, stream_id, out, lane, lt_mask, id_first, off_first, q, nq, 32, dst, kept);
             }
         } else {
-            if (pass[j]) dst[kept + __popc(m & lt_mask)] = off_first + off[j];
+            if (pass) dst[kept + __popc(m & lt_mask)] = off_first + off;
             kept += __popc(m);
         }
     }
@@ -1236,7 +1288,7 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
     const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     constexpr uint32_t kPass = 32u * cull_unroll<SRC>();
     unsigned long long n_src = 0;
-    __shared__ uint32_t s_q2[kBlock / 32][64];          // per warp: offsets waiting for the second stage
+    __shared__ uint32_t s_q2[kBlock / 32][cull_planes<SRC>() * kCullQ];     // per warp: records waiting for the second stage
     uint32_t *q = s_q2[threadIdx.x >> 5];
     int nq = 0;
     // Regions are claimed from a global counter: with a static share per warp the scheduler's oldest-first policy lets
@@ -1359,7 +1411,7 @@ k_mosaic32(const __grid_constant__ Cull32Par K, const __grid_constant__ Mosaic32
                 const bool valid = o1 < n_here;
                 const uint64_t id = id_first + (valid ? o1 : 0u);
                 Cull32Full f;
-                cull32_ray<SRC, true>(K, src, pk, stream, (uint32_t)id, (uint32_t)(id >> 32), &f);
+                cull32_ray<SRC, CULL_OUT_FULL>(K, src, pk, stream, (uint32_t)id, (uint32_t)(id >> 32), &f);
                 const float t = K.convex ? f.tca - f.thc : f.tca + f.thc;
                 // frame of mosaic_normal at the intersection point: n = (C - X) / R with C - X = L - t D
                 const float nx = (f.lx - t * f.dx) * K.inv_r, ny = (f.ly - t * f.dy) * K.inv_r, nz = (f.lz - t * f.dz) * K.inv_r;
