@@ -32,8 +32,9 @@ target    north_star target: config 5 at 1.25e9 rays per GPU (1e10 over 8 GPUs) 
 shard_parity  (N > 1, untimed) the reduced counters / images of one step equal a single-rank replay of the
           whole id range.
 cpu_baseline / --impl reference
-          the oracle port of the reference's NumPy path, run with multiprocessing over the
-          host cores (the reference's xicsrt_multiprocessing scheme: one run per task).
+          the unmodified reference (xicsrt.raytrace_mp from the offline install baseline/_ref, kind "reference")
+          over the host cores, one run per pool task; without that install the oracle port of the
+          reference's NumPy path under the same scheme (kind "port").
 """
 import argparse
 import json
@@ -203,19 +204,93 @@ def flops_config5(f_bounds, f_reflect):
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference NumPy path on the host cores
+# CPU arm on the host cores: the UNMODIFIED reference (xicsrt.raytrace_mp) when its offline install travelled with the
+# repository (baseline/_ref, git-ignored: `python __graft_entry__.py` installs it where /root/reference exists),
+# else the oracle port of the reference's NumPy path (same scheme: one run per pool task)
+
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+_REF = {}
+
+
+def reference_module():
+    """The reference package from baseline/_ref, or None (then the oracle port is timed)."""
+    if 'mod' not in _REF:
+        mod = None
+        if os.environ.get('XRT_BENCH_CPU_PORT') != '1' and os.path.isfile(os.path.join(REF_DIR, 'xicsrt', '__init__.py')):
+            sys.path.insert(0, REF_DIR)
+            try:
+                import logging
+                import xicsrt as mod
+                if os.path.realpath(os.path.dirname(mod.__file__)) != os.path.realpath(os.path.join(REF_DIR, 'xicsrt')):
+                    mod = None
+                else:
+                    logging.getLogger('xicsrt').setLevel(logging.WARNING)
+            except Exception as e:      # noqa: BLE001  (missing dependency of the reference on this box)
+                print(f'[bench] reference install in {REF_DIR} not importable ({e!r}): timing the oracle port', file=sys.stderr)
+                mod = None
+            finally:
+                sys.path.remove(REF_DIR)
+        _REF['mod'] = mod
+    return _REF['mod']
+
+
+def cpu_kind():
+    return 'reference' if reference_module() is not None else 'port'
+
+
+def cpu_what():
+    return ('the unmodified reference from baseline/_ref: xicsrt.raytrace_mp' if reference_module() is not None
+            else 'oracle port of the NumPy path; reference scheme xicsrt_multiprocessing')
+
+
+class _StdoutToStderr:
+    """The reference and its pool workers log to fd 1; the bench's stdout is one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def _warm_parent(ref, workload):
+    """The reference imports its object classes (and scipy) lazily inside the first raytrace of a process, ~1.7 s; its
+    pool forks a fresh set of workers per raytrace_mp call.  One tiny in-process run per workload lets the workers
+    inherit the imported modules, so the timed sample holds raytracing only."""
+    if ref is None or workload in _REF.setdefault('warm', set()):
+        return
+    _REF['warm'].add(workload)
+    cfg = workload_config(workload, 2000, seed=1, bundle_count=20) if workload == 'config5' \
+        else workload_config(workload, 2000, seed=1, history=False)
+    cfg['general']['print_results'] = False
+    with _StdoutToStderr():
+        ref.raytrace(cfg)
+
 
 def cpu_reference_step(rays_per_run, runs, processes, seed, workload='config2'):
-    import oracle
+    ref = reference_module()
+    _warm_parent(ref, workload)
     if workload == 'config5':
         # the reference builds one Python source object per bundle (0.5 ms each): 2000 bundles keep the sample bounded
         cfg = workload_config('config5', rays_per_run, seed=seed, bundle_count=2000)
     else:
         cfg = workload_config(workload, rays_per_run, seed=seed, history=False)
     cfg['general']['number_of_runs'] = runs
-    t0 = time.perf_counter()
-    res = oracle.raytrace_mp(cfg, processes=processes)
-    dt = time.perf_counter() - t0
+    cfg['general']['print_results'] = False
+    if ref is not None:
+        with _StdoutToStderr():
+            t0 = time.perf_counter()
+            res = ref.raytrace_mp(cfg, processes=processes)
+            dt = time.perf_counter() - t0
+    else:
+        import oracle
+        t0 = time.perf_counter()
+        res = oracle.raytrace_mp(cfg, processes=processes)
+        dt = time.perf_counter() - t0
     n = int(res['total']['meta']['source']['num_out'])
     return n, dt
 
@@ -228,9 +303,8 @@ def cpu_baseline_for(workload, procs):
         cpu_reference_step(200000, procs, procs, seed=7)          # warm the pool / imports
     n, dt = cpu_reference_step(per_run, runs, procs, seed=8, workload=workload)
     note = ' (2000 bundles instead of 1e5: the reference spends 0.5 ms of Python per bundle)' if workload == 'config5' else ''
-    return {'value': n / dt, 'unit': UNIT, 'cores': procs, 'kind': 'port',
-            'sample': f'{runs} runs x {per_run} rays over {procs} processes, {dt:.1f} s{note} '
-                      f'(oracle port of the NumPy path; reference scheme xicsrt_multiprocessing)'}
+    return {'value': n / dt, 'unit': UNIT, 'cores': procs, 'kind': cpu_kind(),
+            'sample': f'{runs} runs x {per_run} rays over {procs} processes, {dt:.1f} s{note} ({cpu_what()})'}
 
 
 def run_reference_arm(args):
@@ -249,13 +323,13 @@ def run_reference_arm(args):
         total_rays += n
         total_t += dt
     value = total_rays / total_t
-    sample = f'{runs} runs x {rays_per_run} rays per step over {procs} processes (oracle port of the NumPy path)'
+    sample = f'{runs} runs x {rays_per_run} rays per step over {procs} processes ({cpu_what()})'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_t / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'rays_per_step': runs * rays_per_run, 'history': False},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': cpu_kind(), 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
