@@ -1132,9 +1132,9 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
 //            reflected => dtheta^2 <= 2 sigma^2 ln(reflectivity / u); the first stage's lower bound on |dtheta| beyond
 //            that means lost (bragg_cull_uniform in single precision, u truncated to 23 bits -- downwards, which only
 //            widens the limit).
-// Queue record (planes of 64 entries per warp): offset | usable << 31; point source: local cone vector, tca, thc, gap,
-// c2 (its direction is cone vector . basis, origin and margin are constants); other sources: direction, tca, thc, gap,
-// c2, origin - crystal origin, margin.
+// Queue record (planes of 64 16-byte entries per warp): {offset | usable << 31, local cone vector}, {tca, thc, gap, c2}
+// for the point source (its direction is cone vector . basis, origin and margin are constants); {offset | usable << 31,
+// direction}, {tca, thc, gap, c2}, {origin - crystal origin, margin} for the box.
 // Sources whose second stage is fed from the queue; for the others (per-ray focused basis, plasma bundles: more values,
 // and few rays survive the first stage at all) the queue holds the offset alone and the second stage generates the ray
 // again -- measured: hand-off +6.5 % for the point source, +2.5 % for the box, -2 % / -5 % for focused / bundles.
@@ -1144,24 +1144,28 @@ constexpr int kCullQ = 64;
 
 template <int SRC>
 __device__ __forceinline__ void cull32_push(uint32_t *q, int slot, uint32_t off, const Cull32Full &f) {
-    q[slot] = off | (f.usable ? 0x80000000u : 0u);
-    if constexpr (!cull_handoff<SRC>()) return;
-    float *qf = (float *)q;
-    if constexpr (SRC == CULL_POINT) {
-        qf[1 * kCullQ + slot] = f.cl[0]; qf[2 * kCullQ + slot] = f.cl[1]; qf[3 * kCullQ + slot] = f.cl[2];
+    const uint32_t word = off | (f.usable ? 0x80000000u : 0u);
+    if constexpr (!cull_handoff<SRC>()) {
+        q[slot] = word;
     } else {
-        qf[1 * kCullQ + slot] = f.dx; qf[2 * kCullQ + slot] = f.dy; qf[3 * kCullQ + slot] = f.dz;
-        qf[8 * kCullQ + slot] = f.px; qf[9 * kCullQ + slot] = f.py; qf[10 * kCullQ + slot] = f.pz;
-        qf[11 * kCullQ + slot] = f.err;
+        // 16-byte records in planes of kCullQ: two (point) or three (box) STS.128 per ray instead of 8 / 12 STS.32 --
+        // consecutive slots are consecutive 16-byte words, so a quarter warp covers the 32 banks once
+        float4 *q4 = (float4 *)q;
+        if constexpr (SRC == CULL_POINT) {
+            q4[slot] = make_float4(__uint_as_float(word), f.cl[0], f.cl[1], f.cl[2]);
+        } else {
+            q4[slot] = make_float4(__uint_as_float(word), f.dx, f.dy, f.dz);
+            q4[2 * kCullQ + slot] = make_float4(f.px, f.py, f.pz, f.err);
+        }
+        q4[kCullQ + slot] = make_float4(f.tca, f.thc, f.gap, f.c2);
     }
-    qf[4 * kCullQ + slot] = f.tca; qf[5 * kCullQ + slot] = f.thc; qf[6 * kCullQ + slot] = f.gap; qf[7 * kCullQ + slot] = f.c2;
 }
 
 // true = provably lost at the crystal
 template <int SRC>
 __device__ __forceinline__ bool cull32_stage2(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
-                                              uint32_t lo, uint32_t hi, const uint32_t *q, int slot, bool usable) {
-    const float *qf = (const float *)q;
+                                              uint32_t lo, uint32_t hi, const uint32_t *q, int slot, const float4 &head, bool usable) {
+    const float4 *q4 = (const float4 *)q;
     float tca, thc, gap, c2, dx, dy, dz, px, py, pz, err;
     if constexpr (!cull_handoff<SRC>()) {
         Cull32Full f;
@@ -1170,20 +1174,21 @@ __device__ __forceinline__ bool cull32_stage2(const Cull32Par &K, const XrtSourc
         dx = f.dx; dy = f.dy; dz = f.dz; px = f.px; py = f.py; pz = f.pz; err = f.err;
         usable = f.usable;
     } else {
-        tca = qf[4 * kCullQ + slot]; thc = qf[5 * kCullQ + slot]; gap = qf[6 * kCullQ + slot]; c2 = qf[7 * kCullQ + slot];
+        const float4 b = q4[kCullQ + slot];
+        tca = b.x; thc = b.y; gap = b.z; c2 = b.w;
     }
     if constexpr (!cull_handoff<SRC>()) {
     } else if constexpr (SRC == CULL_POINT) {
-        const float lx = qf[1 * kCullQ + slot], ly = qf[2 * kCullQ + slot], z = qf[3 * kCullQ + slot];
+        const float lx = head.y, ly = head.z, z = head.w;
         dx = lx * K.basis[0] + ly * K.basis[3] + z * K.basis[6];
         dy = lx * K.basis[1] + ly * K.basis[4] + z * K.basis[7];
         dz = lx * K.basis[2] + ly * K.basis[5] + z * K.basis[8];
         px = K.Ob[0]; py = K.Ob[1]; pz = K.Ob[2];
         err = K.err;
     } else {
-        dx = qf[1 * kCullQ + slot]; dy = qf[2 * kCullQ + slot]; dz = qf[3 * kCullQ + slot];
-        px = qf[8 * kCullQ + slot]; py = qf[9 * kCullQ + slot]; pz = qf[10 * kCullQ + slot];
-        err = qf[11 * kCullQ + slot];
+        const float4 c = q4[2 * kCullQ + slot];
+        dx = head.y; dy = head.z; dz = head.w;
+        px = c.x; py = c.y; pz = c.z; err = c.w;
     }
     bool lost = false;
     if (K.bounds_xy) {
@@ -1215,10 +1220,17 @@ __device__ __forceinline__ void cull32_drain(const Cull32Par &K, const XrtSource
                                              uint32_t off_first, const uint32_t *q, int first, int cnt, uint32_t *dst, uint32_t &kept) {
     const bool active = (int)lane < cnt;
     const int slot = active ? first + (int)lane : first;
-    const uint32_t word = q[slot];
+    float4 head = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    uint32_t word;
+    if constexpr (cull_handoff<SRC>()) {
+        head = ((const float4 *)q)[slot];
+        word = __float_as_uint(head.x);
+    } else {
+        word = q[slot];
+    }
     const uint32_t off = word & 0x7fffffffu;
     const uint64_t id = id_first + off;
-    const bool pass = active && !cull32_stage2<SRC>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32), q, slot, (word >> 31) != 0u);
+    const bool pass = active && !cull32_stage2<SRC>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32), q, slot, head, (word >> 31) != 0u);
     __syncwarp();
     if constexpr (HIST) {
         if (out.lost_count || out.lost_bits) {
@@ -1288,7 +1300,7 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
     const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     constexpr uint32_t kPass = 32u * cull_unroll<SRC>();
     unsigned long long n_src = 0;
-    __shared__ uint32_t s_q2[kBlock / 32][cull_planes<SRC>() * kCullQ];     // per warp: records waiting for the second stage
+    __shared__ __align__(16) uint32_t s_q2[kBlock / 32][cull_planes<SRC>() * kCullQ];     // per warp: records waiting for the second stage
     uint32_t *q = s_q2[threadIdx.x >> 5];
     int nq = 0;
     // Regions are claimed from a global counter: with a static share per warp the scheduler's oldest-first policy lets
