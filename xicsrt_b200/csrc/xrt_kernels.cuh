@@ -993,9 +993,51 @@ struct Cull32Full {
 enum { CULL_OUT_NONE = 0, CULL_OUT_STAGE2 = 1, CULL_OUT_FULL = 2 };
 
 // true = provably lost at the crystal
+// first bundle b with bundle_end[b] > id (the search of source_local), bracketed by the hint table
+__device__ __forceinline__ uint64_t cull32_bundle_of(const XrtSourceDesc &src, uint64_t id) {
+    uint64_t blo = 0, bhi = src.n_bundles - 1;
+    if (src.bundle_hint) {
+        const uint64_t j = id >> src.bundle_hint_shift;
+        blo = __ldg(src.bundle_hint + j);
+        bhi = __ldg(src.bundle_hint + j + 1);
+    }
+    while (blo < bhi) {
+        const uint64_t mid = (blo + bhi) >> 1;
+        if (__ldg(src.bundle_end + mid) > id) bhi = mid; else blo = mid + 1;
+    }
+    return blo;
+}
+
+// The per-ray values of a plasma bundle in single precision (differences formed in FP64 once), as the first stage uses
+// them: 4 x 16 bytes.  Ray ids are handed out bundle by bundle (inclusive prefix sum of the counts), so the 32 consecutive
+// ids of a pass nearly always share the bundle of the pass before: a warp keeps the record of its current bundle in
+// shared memory (k_cull32) and looks a bundle up only where a pass crosses a bundle boundary.
+struct Cull32Bundle { float4 a, b, c, d; };     // {L, 1 - cos}, {T, sigma}, {v / c, margin}, {origin - crystal origin, -}
+
+__device__ __forceinline__ Cull32Bundle cull32_bundle_record(const Cull32Par &K, const XrtBundle *bd) {
+    const double ox = __ldg(&bd->origin[0]), oy = __ldg(&bd->origin[1]), oz = __ldg(&bd->origin[2]);
+    Cull32Bundle r;
+    const float sig = (float)__ldg(&bd->wave_sigma);
+    r.a = make_float4((float)(K.C[0] - ox), (float)(K.C[1] - oy), (float)(K.C[2] - oz), (float)(1.0 - __ldg(&bd->cos_spread)));
+    r.b = make_float4((float)(K.T[0] - ox), (float)(K.T[1] - oy), (float)(K.T[2] - oz), sig);
+    r.c = make_float4((float)__ldg(&bd->velocity_c[0]), (float)__ldg(&bd->velocity_c[1]), (float)__ldg(&bd->velocity_c[2]),
+                      fmaf(K.err_sig, fabsf(sig), K.err));
+    r.d = make_float4((float)(ox - K.Oc[0]), (float)(oy - K.Oc[1]), (float)(oz - K.Oc[2]), 0.0f);
+    return r;
+}
+
+// out of line: runs where a pass of k_cull32 crosses a bundle boundary, and must not cost the passes that do not any
+// registers.  Returns the id at which the bundle of `id` ends.
+static __device__ __noinline__ uint64_t cull32_bundle_miss(const Cull32Par &K, const XrtSourceDesc &src, uint64_t id, Cull32Bundle *out) {
+    const uint64_t b = cull32_bundle_of(src, id);
+    *out = cull32_bundle_record(K, src.bundles + b);
+    return __ldg(src.bundle_end + b);
+}
+
 template <int SRC, int OUT = CULL_OUT_NONE>
 __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint32_t stream,
-                                           uint32_t lo, uint32_t hi, Cull32Full *full = nullptr) {
+                                           uint32_t lo, uint32_t hi, Cull32Full *full = nullptr,
+                                           const Cull32Bundle *cached = nullptr) {
     const uint4 r = philox4x32_10(make_uint4(lo, hi, SITE_CONE, stream), pk);
     float Px = K.Ob[0], Py = K.Ob[1], Pz = K.Ob[2];
 
@@ -1004,27 +1046,18 @@ __device__ __forceinline__ bool cull32_ray(const Cull32Par &K, const XrtSourceDe
     float Tx = K.Tb[0], Ty = K.Tb[1], Tz = K.Tb[2];
     float vx = K.vel[0], vy = K.vel[1], vz = K.vel[2];
     if constexpr (SRC == CULL_BUNDLES) {
-        // bundle of this ray: first b with bundle_end[b] > id (same search as source_local)
-        const uint64_t id = ((uint64_t)hi << 32) | lo;
-        uint64_t blo = 0, bhi = src.n_bundles - 1;
-        if (src.bundle_hint) {
-            const uint64_t j = id >> src.bundle_hint_shift;
-            blo = __ldg(src.bundle_hint + j);
-            bhi = __ldg(src.bundle_hint + j + 1);
+        // bundle of this ray: the warp's cached record (every id of the pass lies in that bundle), else a lookup
+        Cull32Bundle rec;
+        if (cached) {
+            rec = *cached;
+        } else {
+            const uint64_t id = ((uint64_t)hi << 32) | lo;
+            rec = cull32_bundle_record(K, src.bundles + cull32_bundle_of(src, id));
         }
-        while (blo < bhi) {
-            const uint64_t mid = (blo + bhi) >> 1;
-            if (__ldg(src.bundle_end + mid) > id) bhi = mid; else blo = mid + 1;
-        }
-        const XrtBundle *bd = src.bundles + blo;
-        const double ox = __ldg(&bd->origin[0]), oy = __ldg(&bd->origin[1]), oz = __ldg(&bd->origin[2]);
-        Lx = (float)(K.C[0] - ox); Ly = (float)(K.C[1] - oy); Lz = (float)(K.C[2] - oz);
-        Tx = (float)(K.T[0] - ox); Ty = (float)(K.T[1] - oy); Tz = (float)(K.T[2] - oz);
-        one_m_cos = (float)(1.0 - __ldg(&bd->cos_spread));
-        sig = (float)__ldg(&bd->wave_sigma);
-        err = fmaf(K.err_sig, fabsf(sig), K.err);
-        vx = (float)__ldg(&bd->velocity_c[0]); vy = (float)__ldg(&bd->velocity_c[1]); vz = (float)__ldg(&bd->velocity_c[2]);
-        if constexpr (OUT != CULL_OUT_NONE) { Px = (float)(ox - K.Oc[0]); Py = (float)(oy - K.Oc[1]); Pz = (float)(oz - K.Oc[2]); }
+        Lx = rec.a.x; Ly = rec.a.y; Lz = rec.a.z; one_m_cos = rec.a.w;
+        Tx = rec.b.x; Ty = rec.b.y; Tz = rec.b.z; sig = rec.b.w;
+        vx = rec.c.x; vy = rec.c.y; vz = rec.c.z; err = rec.c.w;
+        if constexpr (OUT != CULL_OUT_NONE) { Px = rec.d.x; Py = rec.d.y; Pz = rec.d.z; }
     }
 
     // ---- origin offset in world coordinates (the exact path: u01_42x3 of one block, off_k = ext_k (u_k - 1/2))
@@ -1244,13 +1277,32 @@ __device__ __forceinline__ void cull32_drain(const Cull32Par &K, const XrtSource
     kept += __popc(m);
 }
 
+// Lane 0 looks up the bundle of id_first + off and leaves its record in the warp's cache; returns the offset (from
+// id_first, saturated) at which that bundle ends.
+template <int SRC>
+__device__ __forceinline__ uint32_t cull32_bundle_cache(const Cull32Par &K, const XrtSourceDesc &src, uint64_t id_first,
+                                                        uint32_t off, unsigned lane, Cull32Bundle *bc) {
+    uint32_t end = 0;
+    if constexpr (SRC == CULL_BUNDLES) {
+        __syncwarp();
+        if (lane == 0) {
+            const uint64_t e = cull32_bundle_miss(K, src, id_first + off, bc);
+            // ids past the last bundle do not occur (ray_count is the total of the counts); e <= id can only mean that
+            end = e > id_first + off ? (uint32_t)min(e - id_first, (uint64_t)0xffffffffu) : 0u;
+        }
+        end = __shfl_sync(kFull, end, 0);
+        __syncwarp();                           // lane 0's stores before the other lanes' reads
+    }
+    return end;
+}
+
 // cull_unroll groups of 32 consecutive ids: first stage; what it cannot reject goes to the second stage through the
 // warp's queue (K.stage2) or straight to the region's list
 template <int SRC, bool HIST, bool CHECK>
 __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceDesc &src, const PhiloxKeys &pk, uint64_t stream_id,
                                             const XrtOutputs &out, unsigned lane, unsigned lt_mask, uint64_t id_first,
                                             uint32_t off_first, uint32_t g, uint32_t n_here, uint32_t *dst, uint32_t &kept,
-                                            uint32_t *q, int &nq) {
+                                            uint32_t *q, int &nq, Cull32Bundle *bc, uint32_t &bc_end) {
     constexpr int U = cull_unroll<SRC>();
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -1259,7 +1311,24 @@ __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceD
         const uint64_t id = id_first + (valid ? off : 0u);      // lanes past the end re-test the region's first ray
         Cull32Full f;
         f.usable = true;
-        bool pass = !cull32_ray<SRC, cull_handoff<SRC>() ? CULL_OUT_STAGE2 : CULL_OUT_NONE>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32), &f);
+        bool pass;
+        if constexpr (SRC == CULL_BUNDLES) {
+            // offsets below bc_end lie in the warp's cached bundle (the region is walked upwards)
+            // The warp's cached bundle covers the offsets below bc_end (the region is walked upwards).  A pass that crosses
+            // a bundle boundary (3 in 1000 at 1e4 rays per bundle) looks every lane's bundle up, leaves the record in the
+            // lane's own slot, and caches the bundle of the next pass's first id (if the region has one).
+            const Cull32Bundle *rec = bc;
+            const uint32_t next = g + 32u * j + 32u;
+            if (next > bc_end) {
+                Cull32Bundle *mine = bc + 1 + lane;
+                cull32_bundle_miss(K, src, id, mine);
+                rec = mine;
+                bc_end = next < n_here ? cull32_bundle_cache<SRC>(K, src, id_first, next, lane, bc) : 0u;
+            }
+            pass = !cull32_ray<SRC, CULL_OUT_NONE>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32), &f, rec);
+        } else {
+            pass = !cull32_ray<SRC, cull_handoff<SRC>() ? CULL_OUT_STAGE2 : CULL_OUT_NONE>(K, src, pk, (uint32_t)stream_id, (uint32_t)id, (uint32_t)(id >> 32), &f);
+        }
         if constexpr (CHECK) pass = pass && valid;
         if constexpr (HIST) {
             if (out.lost_count || out.lost_bits) {
@@ -1284,13 +1353,17 @@ __device__ __forceinline__ void cull32_pass(const Cull32Par &K, const XrtSourceD
     }
 }
 
-// resident blocks per SM: the bundle lookup (64-bit search, FP64 differences) and the lost-sample emission of
-// history-on launches need more registers than the rest
+// resident blocks per SM: the lost-sample emission of history-on launches needs more registers than the rest (4 x 64);
+// the plasma source with the warp's bundle record cached runs without spills at 80 registers, and 3 resident blocks of
+// that beat 4 blocks with 160 B of spills (9.3e10 against 8.8e10 rays/s on config 5; 8.4e10 before the cache)
+#ifndef XRT_CULL_BLOCKS_HIST
+#define XRT_CULL_BLOCKS_HIST 4
+#endif
 #ifndef XRT_CULL_BLOCKS_BUNDLES
-#define XRT_CULL_BLOCKS_BUNDLES 4
+#define XRT_CULL_BLOCKS_BUNDLES 3
 #endif
 template <int SRC, bool HIST>
-__global__ void __launch_bounds__(kBlock, ((SRC == CULL_BUNDLES || HIST) ? XRT_CULL_BLOCKS_BUNDLES : XRT_CULL_BLOCKS))
+__global__ void __launch_bounds__(kBlock, (SRC == CULL_BUNDLES ? XRT_CULL_BLOCKS_BUNDLES : (HIST ? XRT_CULL_BLOCKS_HIST : XRT_CULL_BLOCKS)))
 k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceDesc src, const __grid_constant__ PhiloxKeys pk,
          const uint64_t stream_id, const uint64_t ray_begin, const uint64_t ray_count, const Cull32Out lst,
          const XrtOutputs out) {
@@ -1299,13 +1372,20 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
     const uint32_t n_warps = gridDim.x * (kBlock / 32);
     const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     constexpr uint32_t kPass = 32u * cull_unroll<SRC>();
-    unsigned long long n_src = 0;
     __shared__ __align__(16) uint32_t s_q2[kBlock / 32][cull_planes<SRC>() * kCullQ];     // per warp: records waiting for the second stage
     uint32_t *q = s_q2[threadIdx.x >> 5];
     int nq = 0;
+    // per warp: record of its current bundle + one slot per lane for the passes that cross a bundle boundary
+    __shared__ Cull32Bundle s_bc[SRC == CULL_BUNDLES ? (kBlock / 32) * 33 : 1];
+    Cull32Bundle *bc = s_bc + (SRC == CULL_BUNDLES ? (threadIdx.x >> 5) * 33 : 0);
+    uint32_t bc_end = 0;
     // Regions are claimed from a global counter: with a static share per warp the scheduler's oldest-first policy lets
     // the old warps of an SM finish early and the SM runs its last third at half occupancy (ncu: 49 % achieved of 75 %).
-    if (blockIdx.x == 0 && threadIdx.x == 0) *lst.next_reset = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *lst.next_reset = 0u;
+        // rays out of the source: every region of the launch is claimed by exactly one warp
+        if (out.counts && ray_count) atomicAdd((unsigned long long *)out.counts, (unsigned long long)ray_count);
+    }
     (void)n_warps; (void)warp_global;
     for (;;) {
         uint32_t reg = 0;
@@ -1317,25 +1397,18 @@ k_cull32(const __grid_constant__ Cull32Par K, const __grid_constant__ XrtSourceD
         const uint32_t n_here = left < (uint64_t)lst.cap ? (uint32_t)left : lst.cap;
         uint32_t *dst = lst.ids + first;
         uint32_t kept = 0;
-        n_src += n_here;
         uint32_t g = 0;
+        bc_end = cull32_bundle_cache<SRC>(K, src, ray_begin + first, 0u, lane, bc);
         for (; g + kPass <= n_here; g += kPass)
-            cull32_pass<SRC, HIST, false>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept, q, nq);
+            cull32_pass<SRC, HIST, false>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept, q, nq, bc, bc_end);
         if (g < n_here)
-            cull32_pass<SRC, HIST, true>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept, q, nq);
+            cull32_pass<SRC, HIST, true>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, g, n_here, dst, kept, q, nq, bc, bc_end);
         if (nq > 0) {               // the queue holds offsets of this region only: drain it before the next one
             cull32_drain<SRC, HIST>(K, src, pk, stream_id, out, lane, lt_mask, ray_begin + first, (uint32_t)first, q, 0, nq, dst, kept);
             nq = 0;
         }
         if (lane == 0) lst.counts[reg] = kept;
     }
-    // rays out of the source: one atomic per block
-    __shared__ unsigned long long s_src;
-    if (threadIdx.x == 0) s_src = 0ull;
-    __syncthreads();
-    if (lane == 0 && n_src) atomicAdd(&s_src, n_src);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_src && out.counts) atomicAdd((unsigned long long *)out.counts, s_src);
 }
 
 }  // namespace xrt
