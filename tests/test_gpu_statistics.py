@@ -368,6 +368,59 @@ def _long_train(n_apertures):
     return cfg
 
 
+@pytest.mark.parametrize('name', ['sphere', 'mesh_torus', 'mosaic_sphere'])
+def test_scene_cache_changes_no_result(torch, name, monkeypatch):
+    """
+    raytrace() keeps the prepared scene of a call for the next call with the same elements (_driver._SCENES).  Calls
+    that hit the cache give what calls with the cache off give -- counters, images, histories, output config -- for new
+    seeds and a changed ray count (a different scene), and an output's config is the caller's own (no shared dicts).
+    """
+    import xicsrt_b200
+    from xicsrt_b200 import _driver
+
+    def run(seed, n, history):
+        cfg = scenes.get(name)
+        cfg['sources']['source']['intensity'] = n
+        cfg['general']['keep_history'] = history
+        cfg['general']['random_seed'] = seed
+        return xicsrt_b200.raytrace(cfg)
+
+    calls = [(3, 200000, False), (4, 200000, False), (4, 200000, True), (5, 150000, False), (3, 200000, False)]
+    monkeypatch.setenv('XRT_SCENE_CACHE', '0')
+    _driver.clear_scene_cache()
+    plain = [run(*c) for c in calls]
+    assert len(_driver._SCENES) == 0
+    monkeypatch.setenv('XRT_SCENE_CACHE', '2')
+    cached = [run(*c) for c in calls]
+    assert 1 <= len(_driver._SCENES) <= 2
+    for a, b, c in zip(plain, cached, calls):
+        assert a['total']['meta'] == b['total']['meta'], c
+        for k, img in a['total']['image'].items():
+            assert (img is None and b['total']['image'][k] is None) or np.array_equal(img, b['total']['image'][k]), (c, k)
+        for kind in ('found', 'lost'):
+            assert a[kind]['history'].keys() == b[kind]['history'].keys()
+            for elem, h in a[kind]['history'].items():
+                for field, arr in h.items():
+                    assert np.array_equal(arr, b[kind]['history'][elem][field], equal_nan=(field != 'mask')), (c, kind, elem, field)
+        assert a['config']['general'] == b['config']['general']
+        assert a['config']['sources'].keys() == b['config']['sources'].keys()
+        assert a['config']['optics'].keys() == b['config']['optics'].keys()
+        for sec in ('sources', 'optics'):
+            for elem, conf in a['config'][sec].items():
+                assert conf.keys() == b['config'][sec][elem].keys(), (sec, elem)
+                for k, v in conf.items():
+                    w = b['config'][sec][elem][k]
+                    assert np.array_equal(np.asarray(v, dtype=object), np.asarray(w, dtype=object)) or \
+                        (isinstance(v, np.ndarray) and np.allclose(v, w, equal_nan=True)), (sec, elem, k)
+    assert cached[0]['total']['meta'] == cached[4]['total']['meta']          # same seed, same rays
+    # outputs do not share their config dicts with the cache or with each other
+    cached[1]['config']['optics']['detector']['xsize'] = -1.0
+    again = run(4, 200000, False)
+    assert again['config']['optics']['detector']['xsize'] == plain[1]['config']['optics']['detector']['xsize']
+    assert again['total']['meta'] == plain[1]['total']['meta']
+    _driver.clear_scene_cache()
+
+
 @pytest.mark.parametrize('n_apertures', [2, 3, 5])
 def test_split_optic_deep_in_the_train(torch, n_apertures):
     """Crystal as 3rd, 4th, 6th optic: compile-time split index 2 and the run-time fallback."""
