@@ -44,6 +44,7 @@ def main():
     ap.add_argument('names', nargs='*', default=['config2'])
     ap.add_argument('--rays', type=float, default=1e9)
     ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--flush', action='store_true', help='256 MiB memset before every timed step (as bench.py); its time is included')
     args = ap.parse_args()
     for name in args.names:
         n = int(args.rays if name not in ('config3', 'config4', 'plasma_mesh') and not name.startswith('scene:') else min(args.rays, 1e8))
@@ -54,7 +55,10 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda') if args.flush else None
         for it in range(args.steps):
+            if flush is not None:
+                flush.zero_()
             tr.begin_iteration(it); tr.trace(it)
         e1.record(); torch.cuda.synchronize()
         meta, _ = tr.counts_and_images(True)
