@@ -48,11 +48,33 @@ int main() {
         double w = (u - 0.5) * 0.1;
         if (w != 0) ea = fmax(ea, fabs((double)((asin_small(w) - asinl((long double)w)) / asinl((long double)w))));
     }
+    // inverse normal CDF: one Newton step in long double from the value under test (erfcl on the tail that holds u)
+    double en = 0, en_tail = 0;
+    const long double SQ2 = 1.41421356237309504880168872420969808L, SQ2PI = 2.50662827463100050241576528481104525L;
+    for (int i = 0; i < 600000; ++i) {
+        double u = U(g);
+        if (i % 4 == 1) u = ldexp(u + 0.5, -(1 + i % 53));          // lower tail down to 2^-54
+        if (i % 4 == 2) u = 1.0 - ldexp(u + 0.5, -(1 + i % 52));    // upper tail up to 1 - 2^-53
+        if (i % 4 == 3) u = 0.5 + (u - 0.5) * ldexp(1.0, -(i % 50)); // around the median
+        if (!(u > 0.0 && u < 1.0)) continue;
+        const double z = inv_normal_cdf(u);
+        const long double zl = z;
+        long double f;                                               // Phi(z) - u, formed on the smaller tail
+        if (u < 0.5) f = 0.5L * erfcl(-zl / SQ2) - (long double)u;
+        else f = ((long double)1.0 - (long double)u) - 0.5L * erfcl(zl / SQ2);
+        const long double zr = zl - f * SQ2PI * expl(0.5L * zl * zl);
+        if (zr != 0) {
+            const double e = fabs((double)((zl - zr) / zr));
+            en = fmax(en, e);
+            if (u < 1e-6 || u > 1.0 - 1e-6) en_tail = fmax(en_tail, e);
+        }
+    }
+    const double zmid = inv_normal_cdf(0.5), zlo = inv_normal_cdf(ldexp(1.0, -54)), zhi = inv_normal_cdf(1.0 - ldexp(1.0, -53));
     double s0, c0, s1, c1;
     sincos_2pi(0.0, s0, c0);
     sincos_2pi(1.0, s1, c1);
-    printf("%.3e %.3e %.3e %.3e %.3e %.3e %g %g %g %g %g %g %.3e\n", es, ec, ec2, el, ee, ea,
-           s0, c0, s1, c1, log_pos(1.0), exp_neg(0.0), et);
+    printf("%.3e %.3e %.3e %.3e %.3e %.3e %g %g %g %g %g %g %.3e %.3e %.3e %.17g %.17g %.17g\n", es, ec, ec2, el, ee, ea,
+           s0, c0, s1, c1, log_pos(1.0), exp_neg(0.0), et, en, en_tail, zmid, zlo, zhi);
     return 0;
 }
 '''
@@ -74,6 +96,9 @@ def test_device_math_against_long_double(tmp_path):
     assert el < 4e-16 and ee < 4e-16 and ea < 4e-16, (el, ee, ea)       # relative
     assert [float(v) for v in out[6:12]] == [0.0, 1.0, 0.0, 1.0, 0.0, 1.0]
     assert float(out[12]) < 6e-16, out[12]                               # table version: absolute
+    # inverse normal CDF (the line-shape deviate of the exact kernels): relative, whole range and the 1e-6 tails
+    assert float(out[13]) < 1e-15 and float(out[14]) < 1e-15, out[13:15]
+    assert float(out[15]) == 0.0 and abs(float(out[16]) + 8.2923610758135947) < 1e-14 and abs(float(out[17]) - 8.2095361516013874) < 1e-14, out[15:18]
 
 
 def test_pretest_normal_deviate_coefficients_against_scipy():

@@ -16,6 +16,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <math.h>
 
 #ifdef __CUDACC__
 #define XRT_HD __host__ __device__ __forceinline__
@@ -51,6 +52,33 @@ XRT_DEFINE_TABLE(kLog, 7,
 XRT_DEFINE_TABLE(kExp, 12,
     1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
     1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5)
+// Inverse normal CDF through erfinv(x) / x as a polynomial in w = -log(1 - x^2) (centre) or sqrt(w) (tails), the form
+// of M. Giles' single-precision erfinv; coefficients: Chebyshev interpolation in 60-digit arithmetic (mpmath) converted
+// to powers of the centred variable, truncation below 4e-18 relative.
+// erfinv(x) / x = sum c_i (w - 3.125)^i,  w = -log(1 - x^2) in [0, 6.25]   (|x| <= 0.99903: 99.9 % of the uniforms)
+XRT_DEFINE_TABLE(kNinvC, 25,
+    1.6536545626831027, 0.24015818242558834, -0.006033670871426851, -0.0007407025341546431,
+    0.00018673420801981186, -1.3882523393957483e-05, -1.3654691758785656e-06, 4.23478816822246e-07,
+    -2.907039127564132e-08, -4.1126604371632185e-09, 1.051223377050429e-09, -5.414303283919504e-11,
+    -1.2978805369932565e-11, 2.6305268312595183e-12, -8.07192593899004e-14, -4.0020031087558496e-14,
+    6.521333511502239e-15, -3.94018812230432e-17, -1.2215637192404172e-16, 1.5510787009902526e-17,
+    6.075050702072414e-19, -3.4734793888538036e-19, 1.999259988861535e-20, 3.194015548136271e-21,
+    -3.5932028927020693e-22)
+// erfinv(x) / x = sum c_i (sqrt(w) - 3.25)^i,  w in [6.25, 16]
+XRT_DEFINE_TABLE(kNinvT1, 21,
+    3.0838856104922208, 1.0052589676941655, 0.005370914553555033, -0.0037512085082247342,
+    0.00249144209795696, -0.0016882755354488555, 0.0009532893415794137, -0.0003550378137852452,
+    2.4031512865758357e-05, 6.828711739251955e-05, -4.732068066544697e-05, 1.2465028224217455e-05,
+    2.93257845538535e-06, -3.985705945648173e-06, 1.4815977874022539e-06, -2.761716223816241e-08,
+    -2.4549818963339823e-07, 1.3158663683192966e-07, -2.091453334773126e-08, -1.5305397964152548e-08,
+    7.680200479077053e-09)
+// erfinv(x) / x = sum c_i (sqrt(w) - 5.01)^i,  w in [16, 36.3]   (u down to 2^-54)
+XRT_DEFINE_TABLE(kNinvT2, 20,
+    4.860009391971025, 1.010297626272141, -0.00014512482094814632, -0.00021200990027194828,
+    7.501794401970369e-05, -1.941228065183597e-05, 4.457176465510443e-06, -9.749411285981377e-07,
+    2.2309945268031453e-07, -6.475270571992455e-08, 2.739547529297803e-08, -1.4302618643547702e-08,
+    7.374469177986523e-09, -3.3530766811338047e-09, 1.258897391154837e-09, -3.702974831012114e-10,
+    7.228405264876682e-11, 1.1638608468654179e-11, -1.940432963946844e-11, 5.767787767112359e-12)
 // constants
 XRT_DEFINE_TABLE(kMisc, 6,
     1.57079632679489661923,        // pi/2
@@ -198,6 +226,36 @@ XRT_HD double log_pos(double v) {
     double R = fm(t2, z, t1);
     const double hfsq = 0.5 * f * f;
     return fm(dk, XRT_TAB(kMisc)[1], -((hfsq - fm(s, hfsq + R, dk * XRT_TAB(kMisc)[2])) - f));
+}
+
+// sum_{i < N} c[i] t^i as two interleaved Horner chains in t^2 (even and odd powers)
+template <int N>
+XRT_HD double poly_even_odd(const double *c, double t) {
+    const double t2 = t * t;
+    double pe = c[(N - 1) & ~1], po = c[((N - 2) & ~1) + 1];
+#pragma unroll
+    for (int i = ((N - 1) & ~1) - 2; i >= 0; i -= 2) pe = fm(pe, t2, c[i]);
+#pragma unroll
+    for (int i = ((N - 2) & ~1) - 1; i >= 1; i -= 2) po = fm(po, t2, c[i]);
+    return fm(po, t, pe);
+}
+
+// z with Phi(z) = u for u in [2^-54, 1 - 2^-53]: z = sqrt(2) x erfinv(x) / x with x = 2u - 1 (exact for u >= 1/4) and
+// w = -log(1 - x^2) = -log(4 u (1 - u)) formed from u itself (1 - u is exact above 1/2, u carries the tail below it).
+// 4e-16 relative against 60-digit arithmetic; one branch for 99.9 % of the uniforms (CUDA's normcdfinv: 160 instructions
+// per call, 14 - 17 % of the exact kernels).
+XRT_HD double inv_normal_cdf(double u) {
+    const double x = fm(2.0, u, -1.0);
+    double w = -log_pos(4.0 * (u * (1.0 - u)));
+    w = w > 0.0 ? w : 0.0;
+    double g;
+    if (w < 6.25) {
+        g = poly_even_odd<25>(XRT_TAB(kNinvC), w - 3.125);
+    } else {
+        const double sw = sqrt(w);
+        g = (w < 16.0) ? poly_even_odd<21>(XRT_TAB(kNinvT1), sw - 3.25) : poly_even_odd<20>(XRT_TAB(kNinvT2), sw - 5.01);
+    }
+    return 1.4142135623730951 * x * g;
 }
 
 // exp(-x) for 0 <= x <= 700

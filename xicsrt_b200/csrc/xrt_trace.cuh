@@ -137,7 +137,7 @@ struct PhiloxDraws {
     __device__ __forceinline__ double wave_z() const {
         const uint32_t hi = raw(SITE_CONE).w;
         const uint32_t lo = raw(SITE_WAVE).x;
-        return normcdfinv(u01(hi, lo) + 1.1102230246251565e-16);
+        return inv_normal_cdf(u01(hi, lo) + 1.1102230246251565e-16);
     }
     // top 32 bits of that uniform, for approximate deviates (valid after cone(0, ..) on this object)
     __device__ __forceinline__ uint32_t wave_hi() const { return spare; }
