@@ -20,8 +20,10 @@
 
 #ifdef __CUDACC__
 #define XRT_HD __host__ __device__ __forceinline__
+#define XRT_ALIGN16 __align__(16)     // a table starts on a 16-byte boundary: LDCU.128 fetches coefficient pairs
 #else
 #define XRT_HD inline
+#define XRT_ALIGN16
 #define __constant__
 #endif
 
@@ -31,7 +33,7 @@
 #define XRT_TAB(name) name##_h
 #endif
 #define XRT_DEFINE_TABLE(name, n, ...)                       \
-    static __constant__ double name##_d[n] = {__VA_ARGS__};  \
+    static __constant__ XRT_ALIGN16 double name##_d[n] = {__VA_ARGS__};  \
     static const double name##_h[n] = {__VA_ARGS__};
 
 namespace xrt {
