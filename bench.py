@@ -114,9 +114,13 @@ def workload_config(name, n_rays, seed=0, history=False, bundle_count=100000):
 # clocks
 
 class ClockSampler:
-    """nvidia-smi sampling in the background while the timed region runs."""
+    """
+    nvidia-smi sampling in the background (one sample per 10 ms with its own timestamp).  It is started well before the
+    timed region (the tool needs 0.1 - 0.3 s to come up, longer than a short timed region lasts); only the samples whose
+    timestamps fall inside the region that mark_begin / mark_end bracket are reported.
+    """
 
-    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+    QUERY = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -124,19 +128,37 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.file = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '20',
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '10',
                  '-i', str(self.gpu_index)], stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, '%Y/%m/%d %H:%M:%S.%f').timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.proc is None:
             return out
+        time.sleep(0.03)            # the sample that covers the end of the region
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -144,27 +166,36 @@ class ClockSampler:
             self.proc.kill()
         self.file.flush()
         self.file.seek(0)
-        sm, smax, reasons, power = [], [], set(), []
+        rows = []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in self.file.read().splitlines():
             f = [x.strip() for x in line.split(',')]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
+                row = (self._stamp(f[0]), float(f[2]), float(f[3]), float(f[4]),
+                       {name for name, val in zip(names, f[6:10]) if val.lower().startswith('active')})
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
+            rows.append(row)
         self.file.close()
         os.unlink(self.file.name)
-        if sm:
-            busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
-            out.update({'sm_mhz': float(np.median(busy)), 'sm_max_mhz': float(max(smax)),
-                        'power_w_max': float(max(power)), 'reasons': sorted(reasons), 'samples': len(sm)})
+        if not rows:
+            return out
+        inside = [r for r in rows if r[0] is not None and self.t_begin is not None and self.t_end is not None
+                  and self.t_begin - 0.005 <= r[0] <= self.t_end + 0.015]
+        where = 'inside the timed region'
+        if not inside:
+            # a region shorter than the sampling period: the samples under load next to it (warm-up, the steps themselves)
+            pmax = max(r[3] for r in rows)
+            inside = [r for r in rows if r[3] > 0.5 * pmax] or rows
+            where = 'under load next to the timed region (none fell inside it)'
+        reasons = set()
+        for r in inside:
+            reasons |= r[4]
+        out.update({'sm_mhz': float(np.median([r[1] for r in inside])), 'sm_max_mhz': float(max(r[2] for r in inside)),
+                    'power_w_max': float(max(r[3] for r in inside)), 'reasons': sorted(reasons), 'samples': len(inside),
+                    'samples_total': len(rows), 'sampled': where})
         return out
 
 
@@ -421,6 +452,8 @@ def timed_steps(ctx, tracer, steps, warmup, sampler=None):
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ctx.barrier()
     t_wall0 = time.perf_counter()
+    if sampler is not None:
+        sampler.mark_begin()
     start.record(main)
     launched = 0
     for k in range(steps):
@@ -433,6 +466,8 @@ def timed_steps(ctx, tracer, steps, warmup, sampler=None):
     stop.record(main)
     ctx.barrier()
     t_wall = time.perf_counter() - t_wall0
+    if sampler is not None:
+        sampler.mark_end()
     # the flushes are outside what a step is: subtract their device time (measured separately, same stream)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(main)
@@ -669,12 +704,14 @@ def run_gpu_arm(args):
 
     rays_per_gpu = int(args.rays)
     total_rays = rays_per_gpu * world if args.scaling == 'weak' else rays_per_gpu
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()             # comes up while the scene is prepared and the FP64 peak is measured
     tracer = make_tracer(ctx, headline_wl, total_rays)
     info = tracer.scene.launch_info()
     peak = fp64_peak(ctx)
 
     # ---- headline: device-timed steps
-    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     t_steps, t_kernel, launched, t_wall = timed_steps(ctx, tracer, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
     value = launched * args.steps / t_steps
