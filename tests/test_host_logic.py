@@ -512,3 +512,47 @@ def test_bragg_pretest_inequalities_are_conservative():
         fails_wide = x > 60.0
         assert cull1[fails_wide].mean() > 0.95
         assert cull2[~passes & (x > 3.0 * np.maximum(np.log(refl / u), 0.5) + 1.0)].mean() > 0.9
+
+
+def test_scene_cache_key(monkeypatch):
+    """
+    The content key under which raytrace_single keeps a prepared scene (_driver._scene_key): equal for equal element
+    configs whatever the seed, different for any changed element value, for a changed XRT_* switch (the library reads
+    them at scene creation and at launch), rank, world size or device; None -- never cached -- for plasma sources, Poisson
+    ray counts, file-backed tables, and with the cache switched off.
+    """
+    import types
+    fake = types.SimpleNamespace(cuda=types.SimpleNamespace(current_device=lambda: 0))
+    monkeypatch.setattr(_driver, '_torch', lambda: fake)
+    monkeypatch.delenv('XRT_SCENE_CACHE', raising=False)
+    monkeypatch.delenv('XRT_NO_CULL', raising=False)
+
+    def cfg_of(name, **general):
+        c = scenes.get(name)
+        c['general'].update(general)
+        return xconfig.get_config(xconfig.to_numpy(c))
+
+    k0 = _driver._scene_key(cfg_of('sphere', random_seed=1), 0, 1)
+    assert isinstance(k0, bytes)
+    assert _driver._scene_key(cfg_of('sphere', random_seed=99, output_run_suffix='0007'), 0, 1) == k0
+    moved = cfg_of('sphere')
+    moved['optics']['detector']['origin'] = moved['optics']['detector']['origin'] + 1e-9
+    assert _driver._scene_key(moved, 0, 1) != k0
+    more = cfg_of('sphere')
+    more['sources']['source']['intensity'] = more['sources']['source']['intensity'] + 1
+    assert _driver._scene_key(more, 0, 1) != k0
+    assert _driver._scene_key(cfg_of('sphere'), 1, 2) != k0
+    monkeypatch.setenv('XRT_NO_CULL', '1')
+    assert _driver._scene_key(cfg_of('sphere'), 0, 1) != k0
+    monkeypatch.delenv('XRT_NO_CULL')
+    assert _driver._scene_key(cfg_of('sphere'), 0, 1) == k0
+    fake.cuda.current_device = lambda: 3
+    assert _driver._scene_key(cfg_of('sphere'), 0, 1) != k0
+    fake.cuda.current_device = lambda: 0
+    for name in ('plasma_cubic', 'plasma_toroidal', 'plasma_datafile', 'sphere_rocking_file'):
+        assert _driver._scene_key(cfg_of(name), 0, 1) is None, name
+    poisson = cfg_of('sphere')
+    poisson['sources']['source']['use_poisson'] = True
+    assert _driver._scene_key(poisson, 0, 1) is None
+    monkeypatch.setenv('XRT_SCENE_CACHE', '0')
+    assert _driver._scene_key(cfg_of('sphere'), 0, 1) is None
