@@ -441,6 +441,7 @@ __device__ __forceinline__ int mesh_bin_of(const XrtMesh &m, V3 q, int sub, int 
     int cy = (int)floor((q.y - m.grid_y0) * m.grid_inv_dy * (double)sub);
     cx = min(max(cx, 0), m.grid_nx * sub - 1);
     cy = min(max(cy, 0), m.grid_ny * sub - 1);
+    if (tile == 1) return cy * tiles_x + cx;         // the default: no integer divisions (40 instructions per warp pass)
     return (cy / tile) * tiles_x + cx / tile;
 }
 
