@@ -575,6 +575,12 @@ def roofline_for(workload, meta, rays_per_s_kernel, peak, tracer):
            'counting': 'algorithmic flop-equivalents of the reference algorithm (SURVEY 8d), not pipe utilisation',
            'peak_source': 'DFMA-chain microbenchmark (xrt_fp64_burn) measured in this run'}
     out.update(extra)
+    try:        # DRAM bytes of one step from the committed ncu captures of the plan's kernels (profiles/r02_traffic.json)
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))['configs'][workload]
+        out['traffic'] = prof['dram_bytes_per_launch']
+        out['traffic_rays_per_launch'] = prof['rays_per_launch']
+    except (OSError, KeyError, ValueError):
+        pass
     return out
 
 
