@@ -870,9 +870,9 @@ extern "C" int xrt_trace(XrtScene *s, uint64_t seed, uint64_t stream_id, uint64_
             int rbps = 0;
             // 4 kB of static shared memory per block: a small carve-out, the rest of the SM's 256 kB is L1
             CU(cudaFuncSetAttribute(rk, cudaFuncAttributePreferredSharedMemoryCarveout, 12));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rbps, rk, kBlock, 0));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rbps, rk, kRefineBlock, 0));
             if (rbps < 1) return fail(XRT_ECUDA, "mesh refinement kernel does not fit on an SM");
-            rk<<<s->sm_count * rbps, kBlock, 0, st>>>(s->dev, pk, stream_id, begin, s->ms_sorted, s->ms_total, *out, lazy_bits);
+            rk<<<s->sm_count * rbps, kRefineBlock, 0, st>>>(s->dev, pk, stream_id, begin, s->ms_sorted, s->ms_total, *out, lazy_bits);
             CU(cudaGetLastError());
             continue;
         } else {

@@ -318,18 +318,25 @@ __global__ void __launch_bounds__(kBlock) k_mesh_scatter(const uint32_t *__restr
 }
 #endif  // XRT_MESHSORT_HOST_KERNELS
 
+// Blocks of 128 threads, 5 resident per SM: 20 warps at 96 registers.  Measured on config 4 (rays/s): 256 x 2 at 128
+// registers 1.00e10, 256 x 3 at 80 registers (224 B of stack) 1.06e10, 128 x 4 at 128 registers 1.04e10, 128 x 5 at 96
+// registers 1.10e10 (mesh sphere +2.6 %, plasma source -> mesh -2.5 %).
 #ifndef XRT_REFINE_BLOCKS
-#define XRT_REFINE_BLOCKS 3      // 85 registers with a few spills (L1 hits): +5 % over 2 blocks at 128 registers (measured)
+#define XRT_REFINE_BLOCKS 5
 #endif
+#ifndef XRT_REFINE_THREADS
+#define XRT_REFINE_THREADS 128
+#endif
+constexpr int kRefineBlock = XRT_REFINE_THREADS;
 template <uint32_t FT, bool HIST>
-__global__ void __launch_bounds__(kBlock, XRT_REFINE_BLOCKS)
+__global__ void __launch_bounds__(kRefineBlock, XRT_REFINE_BLOCKS)
 k_mesh_refine(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ PhiloxKeys pk, const uint64_t stream_id,
               const uint64_t ray_begin, const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ total,
               const XrtOutputs out, const int lazy_rt) {
     __shared__ unsigned long long s_cnt[XRT_MAX_OPTICS + 1];
     __shared__ double s_sincos[2 * kSincosTable];
     if (threadIdx.x <= XRT_MAX_OPTICS) s_cnt[threadIdx.x] = 0ull;
-    for (int i = threadIdx.x; i < kSincosTable; i += kBlock) {
+    for (int i = threadIdx.x; i < kSincosTable; i += kRefineBlock) {
         double sn, cs;
         sincos_2pi((double)i / (double)kSincosTable, sn, cs);
         s_sincos[2 * i] = cs;
@@ -346,10 +353,10 @@ k_mesh_refine(const __grid_constant__ XrtSceneDesc sc, const __grid_constant__ P
     const int nopt = sc.n_optics;
     const uint32_t n = __ldg(total);
     const uint32_t n_groups = (n + 31u) / 32u;
-    const uint32_t n_warps = gridDim.x * (kBlock / 32);
+    const uint32_t n_warps = gridDim.x * (kRefineBlock / 32);
     const double *coarse_geom = ops.mesh->coarse_geom;
     unsigned n_split = 0;
-    for (uint32_t g = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); g < n_groups; g += n_warps) {
+    for (uint32_t g = blockIdx.x * (kRefineBlock / 32) + (threadIdx.x >> 5); g < n_groups; g += n_warps) {
         const uint32_t idx = g * 32u + c.lane;
         const bool valid = idx < n;
         const uint32_t e = valid ? __ldg(sorted + idx) : 0u;
