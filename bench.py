@@ -115,7 +115,7 @@ def workload_config(name, n_rays, seed=0, history=False, bundle_count=100000):
 
 class ClockSampler:
     """
-    nvidia-smi sampling in the background (one sample per 10 ms with its own timestamp).  It is started well before the
+    nvidia-smi sampling in the background (one sample per 20 ms with its own timestamp).  It is started well before the
     timed region (the tool needs 0.1 - 0.3 s to come up, longer than a short timed region lasts); only the samples whose
     timestamps fall inside the region that mark_begin / mark_end bracket are reported.
     """
@@ -135,7 +135,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '10',
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '20',
                  '-i', str(self.gpu_index)], stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
