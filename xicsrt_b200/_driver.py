@@ -16,6 +16,7 @@ by design, a different stream than the reference's MT19937).
 
 PyTorch only owns the device buffers; there is no CPU path.
 """
+import atexit
 import collections
 import copy
 import ctypes as C
@@ -610,7 +611,13 @@ def _release_tracer(tracer, key, failed=False):
 def clear_scene_cache():
     """Free the cached scenes (device tables and buffers)."""
     while _SCENES:
-        _SCENES.popitem()[1].close()
+        try:
+            _SCENES.popitem()[1].close()
+        except Exception:       # noqa: BLE001  (interpreter shutdown: the library or the context may be gone)
+            pass
+
+
+atexit.register(clear_scene_cache)      # before the CUDA context goes away at interpreter exit
 
 
 def raytrace_single(config, _internal=False):
